@@ -1,0 +1,134 @@
+/* tha4_b200 -- C ABI of the B200-native THA4 poser hot path.
+ *
+ * The reference (pkhungurn/talking-head-anime-4-demo) is pure Python on PyTorch and has no FFI of its own
+ * (SURVEY.md F1, section 8b): the seam it offers is Python duck-typing -- the `Poser` protocol
+ * (src/tha4/poser/poser.py:132-161), `GeneralPoser02` (src/tha4/poser/general_poser_02.py:10-98) and the
+ * `nn.Module.forward` signatures of the seven networks.  Each entry point below names the reference interface it
+ * stands in for; the Python host mirror in tha4_b200/ binds them with ctypes.
+ *
+ * Conventions: extern "C", no exceptions cross the boundary; every function returns 0 on success and a negative
+ * code on failure, the message is available from tha4_last_error().  A context belongs to one (process, device)
+ * and is NOT thread-safe.  All tensor arguments are raw device pointers to contiguous fp32 NCHW buffers owned by
+ * the caller (e.g. torch tensors); `stream` is a cudaStream_t passed as void* (NULL = default stream).  The
+ * library owns only its packed weights and its activation workspace.  There is no CPU fallback.
+ */
+#ifndef THA4_B200_H
+#define THA4_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tha4_ctx tha4_ctx;
+
+#define THA4_OK 0
+#define THA4_ERR_INVALID (-1)   /* bad argument / shape mismatch / missing weights */
+#define THA4_ERR_CUDA (-2)      /* CUDA runtime error */
+
+/* networks; the names are the keys of the reference's module dictionaries
+ * (src/tha4/poser/modes/mode_07.py:20-25, src/tha4/poser/modes/mode_14.py:17-18) */
+enum tha4_net {
+    THA4_NET_EYEBROW_DECOMPOSER = 0,         /* EyebrowDecomposer00        */
+    THA4_NET_EYEBROW_MORPHING_COMBINER = 1,  /* EyebrowMorphingCombiner00  */
+    THA4_NET_FACE_MORPHER = 2,               /* FaceMorpher08              */
+    THA4_NET_BODY_MORPHER = 3,               /* Morpher00                  */
+    THA4_NET_UPSCALER = 4,                   /* Upscaler02                 */
+    THA4_NET_SIREN_FACE_MORPHER = 5,         /* SirenFaceMorpher00         */
+    THA4_NET_SIREN_BODY_MORPHER = 6,         /* SirenMorpher03             */
+    THA4_NET_COUNT = 7
+};
+
+int tha4_ctx_create(int device, tha4_ctx** out);
+int tha4_ctx_destroy(tha4_ctx* ctx);
+/* message of the last failure on this context (ctx == NULL: last failure of context creation) */
+const char* tha4_last_error(const tha4_ctx* ctx);
+
+/* options: "strict" (0: TF32 tensor-core products, the reference's own default on CUDA
+ *                    1: 3xTF32 error-compensated products == fp32 convolution),
+ *          "microbatch" (frames processed per pass of the teacher pipeline; bounds the workspace) */
+int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value);
+/* counters: "kernel_launches" (kernels this library has launched so far), "workspace_bytes" */
+int64_t tha4_get_counter(const tha4_ctx* ctx, const char* name);
+
+/* Replaces module.load_state_dict(torch_load(file)) (src/tha4/poser/modes/mode_07.py:152-155 and siblings;
+ * src/tha4/shion/core/load_save.py:12-14).  keys/dev_ptrs/shapes describe the reference-format state_dict with
+ * the tensors already on the device (fp32, contiguous); shapes holds 4 int64 per tensor (trailing dims = 1).
+ * The library packs what it needs into its own layouts; the caller's tensors may be freed afterwards. */
+int tha4_load_net(tha4_ctx* ctx, int net, int n_tensors, const char* const* keys, const void* const* dev_ptrs,
+                  const int64_t* shapes, const int* ndims, void* stream);
+
+/* ---- module-level forwards (replace nn.Module.forward of the reference; output order = the INDEX_* constants) ---- */
+/* EyebrowDecomposer00.forward (src/tha4/nn/eyebrow_decomposer/eyebrow_decomposer_00.py:46-64)
+ * image [B,4,128,128] -> 6 outputs: eyebrow_layer(4) eyebrow_alpha(1) eyebrow_color(4) background_layer(4)
+ * background_alpha(1) background_color(4) */
+int tha4_eyebrow_decomposer_forward(tha4_ctx* ctx, const float* image, int B, float* const* outputs, void* stream);
+/* EyebrowMorphingCombiner00.forward (src/tha4/nn/eyebrow_morphing_combiner/eyebrow_morphing_combiner_00.py:47-72)
+ * background_layer, eyebrow_layer [B,4,128,128], pose [B,12] (row stride pose_ld) -> 8 outputs */
+int tha4_eyebrow_morphing_combiner_forward(tha4_ctx* ctx, const float* background_layer, const float* eyebrow_layer,
+                                           const float* pose, int pose_ld, int B, float* const* outputs, void* stream);
+/* FaceMorpher08.forward (src/tha4/nn/face_morpher/face_morpher_08.py:158-193): image [B,4,192,192], pose [B,27] -> 8 */
+int tha4_face_morpher_forward(tha4_ctx* ctx, const float* image, const float* pose, int pose_ld, int B,
+                              float* const* outputs, void* stream);
+/* Morpher00.forward (src/tha4/nn/morpher/morpher_00.py:42-66): image [B,4,256,256], pose [B,6] ->
+ * merged(4) alpha(1) warped(4) grid_change(2) direct(4) */
+int tha4_morpher_forward(tha4_ctx* ctx, const float* image, const float* pose, int pose_ld, int B,
+                         float* const* outputs, void* stream);
+/* Upscaler02.forward (src/tha4/nn/upscaler/upscaler_02.py:59-96): rest_image [B,4,512,512], coarse_posed_image
+ * [B,4,S,S], coarse_grid_change [B,2,S,S], pose [B,6] -> merged alpha warped grid_change direct.
+ * coarse_size S = 512: the reference signature.  S = 256: the half-resolution body-morpher outputs; the bilinear x2
+ * upsamples of the caller (src/tha4/poser/modes/mode_07.py:114-115) are then fused into the prologue kernel. */
+int tha4_upscaler_forward(tha4_ctx* ctx, const float* rest_image, const float* coarse_posed_image,
+                          const float* coarse_grid_change, int coarse_size, const float* pose, int pose_ld, int B,
+                          float* const* outputs, void* stream);
+/* SirenFaceMorpher00.forward (src/tha4/nn/siren/face_morpher/siren_face_morpher_00.py:34-51): pose [B,39] -> [B,4,128,128] */
+int tha4_siren_face_morpher_forward(tha4_ctx* ctx, const float* pose, int pose_ld, int B, float* output, void* stream);
+/* SirenMorpher03.forward (src/tha4/nn/siren/morpher/siren_morpher_03.py:107-139): image [B,4,512,512], pose [B,45] ->
+ * blended(4) alpha(1) color_change(4) warped(4) grid_change(2) */
+int tha4_siren_morpher_forward(tha4_ctx* ctx, const float* image, const float* pose, int pose_ld, int B,
+                               float* const* outputs, void* stream);
+
+/* ---- poser-level forwards (replace GeneralPoser02.get_posing_outputs, general_poser_02.py:63-79) ---- */
+/* mode 7: FiveStepPoserComputationProtocol (src/tha4/poser/modes/mode_07.py:47-134): 33 outputs in the order
+ *   upscaler(5) face_morphed_full(1) body_morpher(5) face_morpher(8) eyebrow_morphing_combiner(8) eyebrow_decomposer(6)
+ * mode 12: the face-only teacher (src/tha4/poser/modes/mode_12.py:41-96): 22 outputs, face(8) combiner(8) decomposer(6).
+ * image [B,4,512,512], pose [B,45].  cached_decomposer: NULL, or the 6 decomposer outputs of an earlier call with
+ * the same image batch (the reference's eyebrow cache, mode_07.py:56-68); then the decomposer is skipped and the
+ * last 6 entries of `outputs` are not written. */
+int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, const float* pose, int B, float* const* outputs,
+                         int eyebrow_morphed_image_index, const float* const* cached_decomposer, void* stream);
+/* mode 14: TwoStepPoserComputationProtocol (src/tha4/poser/modes/mode_14.py:40-90): body(5) + face(1) */
+int tha4_student_forward(tha4_ctx* ctx, const float* image, const float* pose, int B, float* const* outputs, void* stream);
+/* max|a-b| > 0 ?  -- the cache-validity test of mode_07.py:61 (synchronises the stream); result written to *differ */
+int tha4_images_differ(tha4_ctx* ctx, const float* a, const float* b, int64_t n, int* differ, void* stream);
+
+/* ---- kernel-level entry points (unit tests, ncu) ---- */
+/* apply_grid_change (src/tha4/nn/image_processing_util.py:13-24): image [N,C,H,W], grid_change [N,2,H,W] ->
+ * out [N,C,H,W]; optional corner indices x0,y0 [N,H,W] int32 and lerp weights tx,ty [N,H,W] (NULL to skip) */
+int tha4_grid_sample(tha4_ctx* ctx, const float* image, const float* grid_change, int N, int C, int H, int W,
+                     float* out, int32_t* x0, int32_t* y0, float* tx, float* ty, void* stream);
+/* interpolate(mode='bilinear', align_corners=False) (mode_07.py:102,114-115) */
+int tha4_resize_bilinear(tha4_ctx* ctx, const float* in, int N, int C, int Hi, int Wi, int Ho, int Wo, float* out, void* stream);
+/* affine_grid(identity, align_corners=False) base coordinates for one axis (host output, `size` floats) */
+int tha4_base_grid(int size, float* host_out);
+/* conv kinds: 0 = 3x3 s1 p1, 1 = 4x4 s2 p1, 2 = transposed 4x4 s2 p1, 3 = 1x1.  x [N,Cin,H,W] (stored input; if
+ * in_up the conv sees its nearest x2 upsample), w in the reference layout, bias / res may be NULL,
+ * res_mode 1 same / 2 nearest-up x2 / 3 2x2 mean; y [N,Cout,Ho,Wo].  ksplit 0 = automatic. */
+int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, const float* bias, const float* res,
+                   int res_mode, int in_up, float* y, int N, int Cin, int H, int W, int Cout, int strict, int ksplit,
+                   void* stream);
+/* y = act(norm(x)) with groups == 0: InstanceNorm2d, else GroupNorm(groups); act 0 none / 1 relu / 2 silu; pool 0/1;
+ * film0 [2C] / film1 [N,2C] optional FiLM scale-shifts (unet.py:90-97) */
+int tha4_test_norm(tha4_ctx* ctx, const float* x, int N, int C, int H, int W, int groups, const float* gamma,
+                   const float* beta, const float* film0, const float* film1, int act, int pool, float* y, void* stream);
+/* qkv_attention, "new order" (src/tha4/nn/common/unet.py:192-202): qkv [N,3C,16,16] -> out [N,C,16,16] */
+int tha4_test_attention(tha4_ctx* ctx, const float* qkv, int N, int C, int heads, float* out, void* stream);
+/* y[n][o] = b[o] + sum_i f(x[n][i]) W[o][i] */
+int tha4_test_linear(tha4_ctx* ctx, const float* x, int N, int I, const float* W, const float* b, int O, int silu_in,
+                     float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THA4_B200_H */

@@ -1,0 +1,247 @@
+"""ctypes binding of libtha4_b200.so (include/tha4_b200.h) and the per-device Context wrapper.
+
+PyTorch is used for device memory and streams only: tensors are allocated with torch and handed to the library as
+raw pointers together with torch's current CUDA stream.
+"""
+import ctypes
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtha4_b200.so')
+
+NET_IDS = {
+    'eyebrow_decomposer': 0, 'eyebrow_morphing_combiner': 1, 'face_morpher': 2, 'body_morpher': 3, 'upscaler': 4,
+    'siren_face_morpher': 5, 'siren_body_morpher': 6,
+}
+
+# every symbol include/tha4_b200.h declares (tests check that the .so exports all of them)
+EXPORTED_SYMBOLS = [
+    'tha4_ctx_create', 'tha4_ctx_destroy', 'tha4_last_error', 'tha4_set_option', 'tha4_get_counter', 'tha4_load_net',
+    'tha4_eyebrow_decomposer_forward', 'tha4_eyebrow_morphing_combiner_forward', 'tha4_face_morpher_forward',
+    'tha4_morpher_forward', 'tha4_upscaler_forward', 'tha4_siren_face_morpher_forward', 'tha4_siren_morpher_forward',
+    'tha4_teacher_forward', 'tha4_student_forward', 'tha4_images_differ', 'tha4_grid_sample', 'tha4_resize_bilinear',
+    'tha4_base_grid', 'tha4_test_conv', 'tha4_test_norm', 'tha4_test_attention', 'tha4_test_linear',
+]
+
+_lib = None
+
+
+class Tha4Error(RuntimeError):
+    pass
+
+
+def load_library() -> ctypes.CDLL:
+    """Loads libtha4_b200.so; raises (loudly) if it has not been built -- there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Tha4Error('tha4_b200: %s is missing -- build it with `python __graft_entry__.py` (nvcc, sm_100a). '
+                        'There is no CPU / PyTorch fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.tha4_last_error.restype = ctypes.c_char_p
+    lib.tha4_last_error.argtypes = [ctypes.c_void_p]
+    lib.tha4_get_counter.restype = ctypes.c_int64
+    lib.tha4_get_counter.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.tha4_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]
+    lib.tha4_images_differ.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _ptr(t: Optional[Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _ptr_array(ts: Sequence[Optional[Tensor]]):
+    return (ctypes.c_void_p * len(ts))(*[0 if t is None else t.data_ptr() for t in ts])
+
+
+def _check_input(t: Tensor, device: torch.device, name: str) -> Tensor:
+    if t.device != device:
+        raise Tha4Error('%s is on %s but the poser lives on %s' % (name, t.device, device))
+    if t.dtype != torch.float32:
+        raise Tha4Error('%s must be float32 (Poser.get_dtype() == torch.float), got %s' % (name, t.dtype))
+    return t.contiguous()
+
+
+class Context:
+    """One library context = one set of the seven networks + activation workspace on one CUDA device."""
+
+    def __init__(self, device: torch.device):
+        device = torch.device(device)
+        if device.type != 'cuda':
+            raise Tha4Error('tha4_b200 runs on CUDA devices only (no CPU fallback); got device %s' % device)
+        if not torch.cuda.is_available():
+            raise Tha4Error('tha4_b200: no CUDA device is available')
+        self.device = torch.device('cuda', device.index if device.index is not None else torch.cuda.current_device())
+        self.lib = load_library()
+        handle = ctypes.c_void_p()
+        rc = self.lib.tha4_ctx_create(self.device.index, ctypes.byref(handle))
+        if rc != 0:
+            raise Tha4Error('tha4_ctx_create failed: %s' % self.lib.tha4_last_error(None).decode())
+        self.handle = handle
+        self.loaded: Dict[str, object] = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.lib.tha4_ctx_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def _call(self, fn_name: str, *args):
+        rc = getattr(self.lib, fn_name)(self.handle, *args)
+        if rc != 0:
+            raise Tha4Error('%s failed (%d): %s' % (fn_name, rc, self.lib.tha4_last_error(self.handle).decode()))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_option(self, name: str, value: int):
+        self._call('tha4_set_option', name.encode(), int(value))
+
+    def counter(self, name: str) -> int:
+        return int(self.lib.tha4_get_counter(self.handle, name.encode()))
+
+    def load_net(self, net: str, state_dict: Dict[str, Tensor]):
+        """Hands a reference-format state_dict to the library (it packs its own copies)."""
+        keys, tensors = [], []
+        for k, v in state_dict.items():
+            keys.append(k.encode())
+            tensors.append(v.detach().to(device=self.device, dtype=torch.float32).contiguous())
+        n = len(keys)
+        shapes = (ctypes.c_int64 * (4 * n))()
+        ndims = (ctypes.c_int * n)()
+        for i, t in enumerate(tensors):
+            ndims[i] = t.dim()
+            for d in range(4):
+                shapes[4 * i + d] = t.shape[d] if d < t.dim() else 1
+        with torch.cuda.device(self.device):
+            self._call('tha4_load_net', NET_IDS[net], n, (ctypes.c_char_p * n)(*keys), _ptr_array(tensors), shapes, ndims,
+                       self._stream())
+            torch.cuda.current_stream(self.device).synchronize()
+        self.loaded[net] = True
+
+    def _empty(self, specs, B: int) -> List[Tensor]:
+        return [torch.empty((B, c, s, s), dtype=torch.float32, device=self.device) for c, s in specs]
+
+    # ------------------------------------------------------------------ module level
+    def eyebrow_decomposer(self, image: Tensor) -> List[Tensor]:
+        image = _check_input(image, self.device, 'image')
+        assert image.shape[1:] == (4, 128, 128)
+        B = image.shape[0]
+        outs = self._empty([(4, 128), (1, 128), (4, 128), (4, 128), (1, 128), (4, 128)], B)
+        self._call('tha4_eyebrow_decomposer_forward', _ptr(image), B, _ptr_array(outs), self._stream())
+        return outs
+
+    def eyebrow_morphing_combiner(self, background_layer: Tensor, eyebrow_layer: Tensor, pose: Tensor) -> List[Tensor]:
+        background_layer = _check_input(background_layer, self.device, 'background_layer')
+        eyebrow_layer = _check_input(eyebrow_layer, self.device, 'eyebrow_layer')
+        pose = _check_input(pose, self.device, 'pose')
+        B = background_layer.shape[0]
+        assert background_layer.shape[1:] == (4, 128, 128) and eyebrow_layer.shape == background_layer.shape
+        assert pose.shape == (B, 12)
+        outs = self._empty([(4, 128), (1, 128), (4, 128), (4, 128), (1, 128), (4, 128), (4, 128), (2, 128)], B)
+        self._call('tha4_eyebrow_morphing_combiner_forward', _ptr(background_layer), _ptr(eyebrow_layer), _ptr(pose), 12, B,
+                   _ptr_array(outs), self._stream())
+        return outs
+
+    def face_morpher(self, image: Tensor, pose: Tensor) -> List[Tensor]:
+        image = _check_input(image, self.device, 'image')
+        pose = _check_input(pose, self.device, 'pose')
+        B = image.shape[0]
+        assert image.shape[1:] == (4, 192, 192) and pose.shape == (B, 27)
+        outs = self._empty([(4, 192), (1, 192), (4, 192), (4, 192), (1, 192), (4, 192), (4, 192), (2, 192)], B)
+        self._call('tha4_face_morpher_forward', _ptr(image), _ptr(pose), 27, B, _ptr_array(outs), self._stream())
+        return outs
+
+    def morpher(self, image: Tensor, pose: Tensor) -> List[Tensor]:
+        image = _check_input(image, self.device, 'image')
+        pose = _check_input(pose, self.device, 'pose')
+        B = image.shape[0]
+        outs = self._empty([(4, 256), (1, 256), (4, 256), (2, 256), (4, 256)], B)
+        self._call('tha4_morpher_forward', _ptr(image), _ptr(pose), 6, B, _ptr_array(outs), self._stream())
+        return outs
+
+    def upscaler(self, rest_image: Tensor, coarse_posed: Tensor, coarse_grid: Tensor, pose: Tensor) -> List[Tensor]:
+        rest_image = _check_input(rest_image, self.device, 'rest_image')
+        coarse_posed = _check_input(coarse_posed, self.device, 'coarse_posed_image')
+        coarse_grid = _check_input(coarse_grid, self.device, 'coarse_grid_change')
+        pose = _check_input(pose, self.device, 'pose')
+        B = rest_image.shape[0]
+        S = coarse_posed.shape[2]
+        assert rest_image.shape[1:] == (4, 512, 512) and S in (256, 512)
+        assert coarse_posed.shape == (B, 4, S, S) and coarse_grid.shape == (B, 2, S, S) and pose.shape == (B, 6)
+        outs = self._empty([(4, 512), (1, 512), (4, 512), (2, 512), (4, 512)], B)
+        self._call('tha4_upscaler_forward', _ptr(rest_image), _ptr(coarse_posed), _ptr(coarse_grid), S, _ptr(pose), 6, B,
+                   _ptr_array(outs), self._stream())
+        return outs
+
+    def siren_face_morpher(self, pose: Tensor) -> Tensor:
+        pose = _check_input(pose, self.device, 'pose')
+        B = pose.shape[0]
+        assert pose.shape == (B, 39)
+        out = torch.empty((B, 4, 128, 128), dtype=torch.float32, device=self.device)
+        self._call('tha4_siren_face_morpher_forward', _ptr(pose), 39, B, _ptr(out), self._stream())
+        return out
+
+    def siren_morpher(self, image: Tensor, pose: Tensor) -> List[Tensor]:
+        image = _check_input(image, self.device, 'image')
+        pose = _check_input(pose, self.device, 'pose')
+        B = image.shape[0]
+        assert image.shape[1:] == (4, 512, 512) and pose.shape == (B, 45)
+        outs = self._empty([(4, 512), (1, 512), (4, 512), (4, 512), (2, 512)], B)
+        self._call('tha4_siren_morpher_forward', _ptr(image), _ptr(pose), 45, B, _ptr_array(outs), self._stream())
+        return outs
+
+    # ------------------------------------------------------------------ poser level
+    TEACHER_SPECS = {
+        7: [(4, 512), (1, 512), (4, 512), (2, 512), (4, 512), (4, 512),
+            (4, 256), (1, 256), (4, 256), (2, 256), (4, 256)],
+        12: [],
+    }
+    FACE_COMB_DEC = [(4, 192), (1, 192), (4, 192), (4, 192), (1, 192), (4, 192), (4, 192), (2, 192),
+                     (4, 128), (1, 128), (4, 128), (4, 128), (1, 128), (4, 128), (4, 128), (2, 128),
+                     (4, 128), (1, 128), (4, 128), (4, 128), (1, 128), (4, 128)]
+
+    def teacher_forward(self, mode: int, image: Tensor, pose: Tensor, eyebrow_morphed_image_index: int = 2,
+                        cached_decomposer: Optional[List[Tensor]] = None) -> List[Tensor]:
+        image = _check_input(image, self.device, 'image')
+        pose = _check_input(pose, self.device, 'pose')
+        B = image.shape[0]
+        assert image.shape[1:] == (4, 512, 512) and pose.shape == (B, 45)
+        specs = self.TEACHER_SPECS[mode] + self.FACE_COMB_DEC
+        n = len(specs)
+        if cached_decomposer is None:
+            outs = self._empty(specs, B)
+            cached = ctypes.c_void_p(0)
+        else:
+            outs = self._empty(specs[:n - 6], B) + list(cached_decomposer)
+            cached = _ptr_array(cached_decomposer)
+        self._call('tha4_teacher_forward', mode, _ptr(image), _ptr(pose), B, _ptr_array(outs), eyebrow_morphed_image_index,
+                   cached, self._stream())
+        return outs
+
+    def student_forward(self, image: Tensor, pose: Tensor) -> List[Tensor]:
+        image = _check_input(image, self.device, 'image')
+        pose = _check_input(pose, self.device, 'pose')
+        B = image.shape[0]
+        assert image.shape[1:] == (4, 512, 512) and pose.shape == (B, 45)
+        outs = self._empty([(4, 512), (1, 512), (4, 512), (4, 512), (2, 512), (4, 128)], B)
+        self._call('tha4_student_forward', _ptr(image), _ptr(pose), B, _ptr_array(outs), self._stream())
+        return outs
+
+    def images_differ(self, a: Tensor, b: Tensor) -> bool:
+        a = _check_input(a, self.device, 'a')
+        b = _check_input(b, self.device, 'b')
+        flag = ctypes.c_int(0)
+        self._call('tha4_images_differ', _ptr(a), _ptr(b), a.numel(), ctypes.byref(flag), self._stream())
+        return flag.value != 0

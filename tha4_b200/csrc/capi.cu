@@ -1,0 +1,421 @@
+// extern "C" boundary of libtha4_b200.so (see include/tha4_b200.h) and the poser-level pipelines.
+#include "../../include/tha4_b200.h"
+#include "nets.cuh"
+#include "siren.cuh"
+#include <atomic>
+#include <cstring>
+
+namespace tha4 { std::atomic<long> g_kernel_launches{0}; }
+
+using namespace tha4;
+
+struct tha4_ctx {
+    int device = 0;
+    std::string err;
+    int strict = 0;
+    int microbatch = 8;
+    Pool persist, scratch;
+    int* flag = nullptr;
+    std::unique_ptr<EncDecNet> decomposer, combiner, face;
+    std::unique_ptr<UNetNet> body, upscaler;
+    std::unique_ptr<SirenFaceNet> sface;
+    std::unique_ptr<SirenBodyNet> sbody;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+template <typename F>
+int guarded(tha4_ctx* ctx, F&& f) {
+    if (!ctx) return THA4_ERR_INVALID;
+    try {
+        THA4_CUDA_CHECK(cudaSetDevice(ctx->device));
+        f();
+        return THA4_OK;
+    } catch (const CudaError& e) {
+        ctx->err = e.what();
+        return THA4_ERR_CUDA;
+    } catch (const std::exception& e) {
+        ctx->err = e.what();
+        return THA4_ERR_INVALID;
+    }
+}
+
+Runtime make_rt(tha4_ctx* ctx, void* stream) {
+    Runtime rt;
+    rt.persist = &ctx->persist; rt.scratch = &ctx->scratch; rt.stream = (cudaStream_t)stream; rt.strict = ctx->strict;
+    return rt;
+}
+
+// one micro-batch of the teacher pipeline (mode_07.py:72-132 / mode_12.py:66-94)
+void teacher_chunk(tha4_ctx* ctx, Runtime& rt, int mode, const float* image, const float* pose, int b, float* const* out,
+                   int eyebrow_index, const float* const* cached) {
+    cudaStream_t s = rt.stream;
+    const int base = (mode == 7) ? 11 : 0;          // index of face_morpher outputs
+    float* const* o_face = out + base;
+    float* const* o_comb = out + base + 8;
+    float* const* o_dec = out + base + 16;
+    const ImgView img = make_img(image, b, 4, 512, 512);
+    THA4_REQUIRE(eyebrow_index >= 0 && eyebrow_index < 8 && eyebrow_index != 1 && eyebrow_index != 4 && eyebrow_index != 7,
+                 "eyebrow_morphed_image_index must select a 4-channel combiner output");
+    const float* dec[6];
+    if (cached) {
+        for (int i = 0; i < 6; ++i) dec[i] = cached[i];
+    } else {
+        ctx->decomposer->forward(rt, crop_img(img, 64, 192, 128, 128), ImgView{}, nullptr, 0, o_dec);   // mode_07.py:74
+        for (int i = 0; i < 6; ++i) dec[i] = o_dec[i];
+    }
+    // combiner(background_layer = dec[3], eyebrow_layer = dec[0], pose[:, :12])   (mode_07.py:76-84)
+    ctx->combiner->forward(rt, make_img(dec[0], b, 4, 128, 128), make_img(dec[3], b, 4, 128, 128), pose, 45, o_comb);
+    // face morpher input: 192x192 crop with the morphed eyebrows pasted in   (mode_07.py:89-91)
+    float* face_in = ctx->persist.alloc((size_t)b * 4 * 192 * 192);
+    copy_window(crop_img(img, 32, 160, 192, 192), face_in, 4L * 192 * 192, 192L * 192, 192, s);
+    copy_window(make_img(o_comb[eyebrow_index], b, 4, 128, 128), face_in + 32 * 192 + 32, 4L * 192 * 192, 192L * 192, 192, s);
+    ctx->face->forward(rt, make_img(face_in, b, 4, 192, 192), ImgView{}, pose + 12, 45, o_face);
+    if (mode != 7) return;
+    // face_morphed_full (mode_07.py:93-98) and face_morphed_half (:99-103)
+    float* full = out[5];
+    copy_window(img, full, 4L * 512 * 512, 512L * 512, 512, s);
+    copy_window(make_img(o_face[0], b, 4, 192, 192), full + 32 * 512 + 160, 4L * 512 * 512, 512L * 512, 512, s);
+    const ImgView fullv = make_img(full, b, 4, 512, 512);
+    float* half = ctx->persist.alloc((size_t)b * 4 * 256 * 256);
+    resize_bilinear(fullv, half, 256, 256, s);
+    ctx->body->forward(rt, make_img(half, b, 4, 256, 256), nullptr, nullptr, 0, pose + 39, 45, out + 6);
+    ctx->upscaler->forward(rt, fullv, out[6], out[9], 256, pose + 39, 45, out + 0);
+}
+
+struct OutSpec { int c, s; };
+const OutSpec kEncDecDecomposer[6] = {{4, 128}, {1, 128}, {4, 128}, {4, 128}, {1, 128}, {4, 128}};
+const OutSpec kCombiner[8] = {{4, 128}, {1, 128}, {4, 128}, {4, 128}, {1, 128}, {4, 128}, {4, 128}, {2, 128}};
+const OutSpec kFace[8] = {{4, 192}, {1, 192}, {4, 192}, {4, 192}, {1, 192}, {4, 192}, {4, 192}, {2, 192}};
+
+void fill_unet_spec(OutSpec* o, int S) { o[0] = {4, S}; o[1] = {1, S}; o[2] = {4, S}; o[3] = {2, S}; o[4] = {4, S}; }
+
+StateDict make_sd(int n, const char* const* keys, const void* const* ptrs, const int64_t* shapes, const int* ndims) {
+    StateDict sd;
+    for (int i = 0; i < n; ++i) {
+        TensorRef t;
+        t.p = reinterpret_cast<const float*>(ptrs[i]);
+        for (int d = 0; d < ndims[i]; ++d) t.shape.push_back((long)shapes[4 * i + d]);
+        sd[keys[i]] = t;
+    }
+    return sd;
+}
+
+// Runs `fn(chunk offset n0, chunk size b)` over micro-batches; resets the workspace per chunk.
+template <typename F>
+void for_chunks(tha4_ctx* ctx, int B, F&& fn) {
+    THA4_REQUIRE(B >= 1, "batch must be >= 1");
+    for (int n0 = 0; n0 < B; n0 += ctx->microbatch) {
+        const int b = std::min(ctx->microbatch, B - n0);
+        ctx->persist.reset();
+        ctx->scratch.reset();
+        fn(n0, b);
+    }
+}
+
+template <int NOUT>
+void offset_outputs(float* const* outputs, const OutSpec* spec, int n0, float** dst) {
+    for (int i = 0; i < NOUT; ++i) dst[i] = outputs[i] + (size_t)n0 * spec[i].c * spec[i].s * spec[i].s;
+}
+
+
+}  // namespace
+
+extern "C" {
+
+int tha4_ctx_create(int device, tha4_ctx** out) {
+    if (!out) return THA4_ERR_INVALID;
+    try {
+        int count = 0;
+        THA4_CUDA_CHECK(cudaGetDeviceCount(&count));
+        THA4_REQUIRE(device >= 0 && device < count, "no such CUDA device");
+        THA4_CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        THA4_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        THA4_REQUIRE(prop.major == 10, "tha4_b200 is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+        auto* ctx = new tha4_ctx();
+        ctx->device = device;
+        THA4_CUDA_CHECK(cudaMalloc(&ctx->flag, sizeof(int)));
+        ctx->decomposer.reset(new EncDecNet(TAIL_DECOMPOSER, 128, 4, 0));
+        ctx->combiner.reset(new EncDecNet(TAIL_COMBINER, 128, 8, 12));
+        ctx->face.reset(new EncDecNet(TAIL_FACE, 192, 4, 27));
+        ctx->body.reset(new UNetNet(false, 256, 64, {1, 2, 4, 4, 4}));           // mode_07.py:210-226
+        ctx->upscaler.reset(new UNetNet(true, 512, 32, {1, 2, 4, 8, 8, 8}));     // mode_07.py:241-257
+        ctx->sface.reset(new SirenFaceNet());
+        ctx->sbody.reset(new SirenBodyNet());
+        *out = ctx;
+        return THA4_OK;
+    } catch (const CudaError& e) {
+        g_create_err = e.what();
+        return THA4_ERR_CUDA;
+    } catch (const std::exception& e) {
+        g_create_err = e.what();
+        return THA4_ERR_INVALID;
+    }
+}
+
+int tha4_ctx_destroy(tha4_ctx* ctx) {
+    if (!ctx) return THA4_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->flag) cudaFree(ctx->flag);
+    delete ctx;
+    return THA4_OK;
+}
+
+const char* tha4_last_error(const tha4_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
+    return guarded(ctx, [&] {
+        if (!strcmp(name, "strict")) ctx->strict = value ? 1 : 0;
+        else if (!strcmp(name, "microbatch")) { THA4_REQUIRE(value >= 1 && value <= 1024, "microbatch range"); ctx->microbatch = (int)value; }
+        else throw std::runtime_error(std::string("tha4: unknown option ") + name);
+    });
+}
+
+int64_t tha4_get_counter(const tha4_ctx* ctx, const char* name) {
+    if (!strcmp(name, "kernel_launches")) return g_kernel_launches.load();
+    if (ctx && !strcmp(name, "workspace_bytes")) return (int64_t)(ctx->persist.bytes() + ctx->scratch.bytes());
+    return -1;
+}
+
+int tha4_load_net(tha4_ctx* ctx, int net, int n_tensors, const char* const* keys, const void* const* dev_ptrs,
+                  const int64_t* shapes, const int* ndims, void* stream) {
+    return guarded(ctx, [&] {
+        StateDict sd = make_sd(n_tensors, keys, dev_ptrs, shapes, ndims);
+        cudaStream_t s = (cudaStream_t)stream;
+        switch (net) {
+            case THA4_NET_EYEBROW_DECOMPOSER: ctx->decomposer.reset(new EncDecNet(TAIL_DECOMPOSER, 128, 4, 0)); ctx->decomposer->load(sd, s); break;
+            case THA4_NET_EYEBROW_MORPHING_COMBINER: ctx->combiner.reset(new EncDecNet(TAIL_COMBINER, 128, 8, 12)); ctx->combiner->load(sd, s); break;
+            case THA4_NET_FACE_MORPHER: ctx->face.reset(new EncDecNet(TAIL_FACE, 192, 4, 27)); ctx->face->load(sd, s); break;
+            case THA4_NET_BODY_MORPHER: ctx->body.reset(new UNetNet(false, 256, 64, {1, 2, 4, 4, 4})); ctx->body->load(sd, s); break;
+            case THA4_NET_UPSCALER: ctx->upscaler.reset(new UNetNet(true, 512, 32, {1, 2, 4, 8, 8, 8})); ctx->upscaler->load(sd, s); break;
+            case THA4_NET_SIREN_FACE_MORPHER: ctx->sface.reset(new SirenFaceNet()); ctx->sface->load(sd, s); break;
+            case THA4_NET_SIREN_BODY_MORPHER: ctx->sbody.reset(new SirenBodyNet()); ctx->sbody->load(sd, s); break;
+            default: throw std::runtime_error("tha4: unknown network id");
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ module level
+int tha4_eyebrow_decomposer_forward(tha4_ctx* ctx, const float* image, int B, float* const* outputs, void* stream) {
+    return guarded(ctx, [&] {
+        Runtime rt = make_rt(ctx, stream);
+        for_chunks(ctx, B, [&](int n0, int b) {
+            float* o[6]; offset_outputs<6>(outputs, kEncDecDecomposer, n0, o);
+            ctx->decomposer->forward(rt, make_img(image + (size_t)n0 * 4 * 128 * 128, b, 4, 128, 128), ImgView{}, nullptr, 0, o);
+        });
+    });
+}
+
+int tha4_eyebrow_morphing_combiner_forward(tha4_ctx* ctx, const float* background_layer, const float* eyebrow_layer,
+                                           const float* pose, int pose_ld, int B, float* const* outputs, void* stream) {
+    return guarded(ctx, [&] {
+        Runtime rt = make_rt(ctx, stream);
+        for_chunks(ctx, B, [&](int n0, int b) {
+            float* o[8]; offset_outputs<8>(outputs, kCombiner, n0, o);
+            const size_t off = (size_t)n0 * 4 * 128 * 128;
+            ctx->combiner->forward(rt, make_img(eyebrow_layer + off, b, 4, 128, 128), make_img(background_layer + off, b, 4, 128, 128),
+                                   pose + (size_t)n0 * pose_ld, pose_ld, o);
+        });
+    });
+}
+
+int tha4_face_morpher_forward(tha4_ctx* ctx, const float* image, const float* pose, int pose_ld, int B,
+                              float* const* outputs, void* stream) {
+    return guarded(ctx, [&] {
+        Runtime rt = make_rt(ctx, stream);
+        for_chunks(ctx, B, [&](int n0, int b) {
+            float* o[8]; offset_outputs<8>(outputs, kFace, n0, o);
+            ctx->face->forward(rt, make_img(image + (size_t)n0 * 4 * 192 * 192, b, 4, 192, 192), ImgView{},
+                               pose + (size_t)n0 * pose_ld, pose_ld, o);
+        });
+    });
+}
+
+int tha4_morpher_forward(tha4_ctx* ctx, const float* image, const float* pose, int pose_ld, int B,
+                         float* const* outputs, void* stream) {
+    return guarded(ctx, [&] {
+        Runtime rt = make_rt(ctx, stream);
+        OutSpec spec[5]; fill_unet_spec(spec, 256);
+        for_chunks(ctx, B, [&](int n0, int b) {
+            float* o[5]; offset_outputs<5>(outputs, spec, n0, o);
+            ctx->body->forward(rt, make_img(image + (size_t)n0 * 4 * 256 * 256, b, 4, 256, 256), nullptr, nullptr, 0,
+                               pose + (size_t)n0 * pose_ld, pose_ld, o);
+        });
+    });
+}
+
+int tha4_upscaler_forward(tha4_ctx* ctx, const float* rest_image, const float* coarse_posed_image,
+                          const float* coarse_grid_change, int coarse_size, const float* pose, int pose_ld, int B,
+                          float* const* outputs, void* stream) {
+    return guarded(ctx, [&] {
+        Runtime rt = make_rt(ctx, stream);
+        OutSpec spec[5]; fill_unet_spec(spec, 512);
+        for_chunks(ctx, B, [&](int n0, int b) {
+            float* o[5]; offset_outputs<5>(outputs, spec, n0, o);
+            ctx->upscaler->forward(rt, make_img(rest_image + (size_t)n0 * 4 * 512 * 512, b, 4, 512, 512),
+                                   coarse_posed_image + (size_t)n0 * 4 * coarse_size * coarse_size,
+                                   coarse_grid_change + (size_t)n0 * 2 * coarse_size * coarse_size, coarse_size, pose + (size_t)n0 * pose_ld, pose_ld, o);
+        });
+    });
+}
+
+int tha4_siren_face_morpher_forward(tha4_ctx* ctx, const float* pose, int pose_ld, int B, float* output, void* stream) {
+    return guarded(ctx, [&] {
+        Runtime rt = make_rt(ctx, stream);
+        ctx->persist.reset(); ctx->scratch.reset();
+        ctx->sface->forward(rt, pose, pose_ld, B, output);
+    });
+}
+
+int tha4_siren_morpher_forward(tha4_ctx* ctx, const float* image, const float* pose, int pose_ld, int B,
+                               float* const* outputs, void* stream) {
+    return guarded(ctx, [&] {
+        Runtime rt = make_rt(ctx, stream);
+        ctx->persist.reset(); ctx->scratch.reset();
+        ctx->sbody->forward(rt, make_img(image, B, 4, 512, 512), pose, pose_ld, outputs);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ poser level
+int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, const float* pose, int B, float* const* outputs,
+                         int eyebrow_morphed_image_index, const float* const* cached_decomposer, void* stream) {
+    return guarded(ctx, [&] {
+        THA4_REQUIRE(mode == 7 || mode == 12, "teacher mode must be 7 or 12");
+        Runtime rt = make_rt(ctx, stream);
+        OutSpec spec[33];
+        int n = 0;
+        if (mode == 7) {
+            fill_unet_spec(spec, 512); n = 5;
+            spec[n++] = {4, 512};
+            fill_unet_spec(spec + n, 256); n += 5;
+        }
+        for (int i = 0; i < 8; ++i) spec[n++] = kFace[i];
+        for (int i = 0; i < 8; ++i) spec[n++] = kCombiner[i];
+        for (int i = 0; i < 6; ++i) spec[n++] = kEncDecDecomposer[i];
+        const int nout = n;
+        for_chunks(ctx, B, [&](int n0, int b) {
+            float* o[33];
+            for (int i = 0; i < nout; ++i) o[i] = outputs[i] ? outputs[i] + (size_t)n0 * spec[i].c * spec[i].s * spec[i].s : nullptr;
+            const float* cd[6];
+            if (cached_decomposer)
+                for (int i = 0; i < 6; ++i) cd[i] = cached_decomposer[i] + (size_t)n0 * kEncDecDecomposer[i].c * 128 * 128;
+            teacher_chunk(ctx, rt, mode, image + (size_t)n0 * 4 * 512 * 512, pose + (size_t)n0 * 45, b, o,
+                          eyebrow_morphed_image_index, cached_decomposer ? cd : nullptr);
+        });
+    });
+}
+
+int tha4_student_forward(tha4_ctx* ctx, const float* image, const float* pose, int B, float* const* outputs, void* stream) {
+    return guarded(ctx, [&] {
+        Runtime rt = make_rt(ctx, stream);
+        cudaStream_t s = rt.stream;
+        ctx->persist.reset(); ctx->scratch.reset();
+        // face SIREN from pose[:, :39] (mode_14.py:64-71), pasted at rows 80:208, cols 192:320 (:72-78)
+        ctx->sface->forward(rt, pose, 45, B, outputs[5]);
+        float* body_in = ctx->persist.alloc((size_t)B * 4 * 512 * 512);
+        copy_window(make_img(image, B, 4, 512, 512), body_in, 4L * 512 * 512, 512L * 512, 512, s);
+        copy_window(make_img(outputs[5], B, 4, 128, 128), body_in + 80 * 512 + 192, 4L * 512 * 512, 512L * 512, 512, s);
+        ctx->sbody->forward(rt, make_img(body_in, B, 4, 512, 512), pose, 45, outputs);
+    });
+}
+
+int tha4_images_differ(tha4_ctx* ctx, const float* a, const float* b, int64_t n, int* differ, void* stream) {
+    return guarded(ctx, [&] { *differ = images_differ(a, b, (size_t)n, ctx->flag, (cudaStream_t)stream) ? 1 : 0; });
+}
+
+// ------------------------------------------------------------------------------------------------ kernel level
+int tha4_grid_sample(tha4_ctx* ctx, const float* image, const float* grid_change, int N, int C, int H, int W,
+                     float* out, int32_t* x0, int32_t* y0, float* tx, float* ty, void* stream) {
+    return guarded(ctx, [&] { grid_sample(make_img(image, N, C, H, W), grid_change, out, x0, y0, tx, ty, (cudaStream_t)stream); });
+}
+
+int tha4_resize_bilinear(tha4_ctx* ctx, const float* in, int N, int C, int Hi, int Wi, int Ho, int Wo, float* out, void* stream) {
+    return guarded(ctx, [&] { resize_bilinear(make_img(in, N, C, Hi, Wi), out, Ho, Wo, (cudaStream_t)stream); });
+}
+
+int tha4_base_grid(int size, float* host_out) {
+    if (size < 2 || !host_out) return THA4_ERR_INVALID;
+    base_grid_host(size, host_out);
+    return THA4_OK;
+}
+
+int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, const float* bias, const float* res,
+                   int res_mode, int in_up, float* y, int N, int Cin, int H, int W, int Cout, int strict, int ksplit,
+                   void* stream) {
+    return guarded(ctx, [&] {
+        cudaStream_t s = (cudaStream_t)stream;
+        ctx->persist.reset(); ctx->scratch.reset();
+        Pool* P = &ctx->persist;
+        const int cin_k = round_up(Cin, 4);
+        ConvWeights cw;
+        conv_describe(cw, (ConvKind)kind, cin_k, Cout);
+        cw.w = P->alloc(conv_packed_floats(cw));
+        THA4_CUDA_CHECK(cudaMemsetAsync(cw.w, 0, conv_packed_floats(cw) * sizeof(float), s));
+        conv_pack(cw, (ConvKind)kind, w, Cin, 0, s);
+        cw.bias = const_cast<float*>(bias);
+        auto mk = [&](int h, int ww, int c) { View v; v.N = N; v.H = h; v.W = ww; v.C = c; v.ld = c; v.p = P->alloc((size_t)N * h * ww * c); return v; };
+        View xin = mk(H, W, cin_k);
+        if (cin_k != Cin) THA4_CUDA_CHECK(cudaMemsetAsync(xin.p, 0, xin.pixels() * cin_k * sizeof(float), s));
+        nchw_to_nhwc(make_img(x, N, Cin, H, W), xin.slice(0, Cin), s);
+        const int LH = in_up ? 2 * H : H, LW = in_up ? 2 * W : W;
+        const int Ho = (kind == CONV_4x4_S2) ? LH / 2 : (kind == CONVT_4x4_S2 ? LH * 2 : LH);
+        const int Wo = (kind == CONV_4x4_S2) ? LW / 2 : (kind == CONVT_4x4_S2 ? LW * 2 : LW);
+        View yo = mk(Ho, Wo, Cout);
+        ConvArgs a;
+        a.in = xin; a.in_up = in_up; a.out = yo; a.strict = strict; a.ksplit = ksplit;
+        if (res) {
+            const int rh = res_mode == RES_UP2 ? Ho / 2 : (res_mode == RES_DOWN2 ? Ho * 2 : Ho);
+            const int rw = res_mode == RES_UP2 ? Wo / 2 : (res_mode == RES_DOWN2 ? Wo * 2 : Wo);
+            View r = mk(rh, rw, Cout);
+            nchw_to_nhwc(make_img(res, N, Cout, rh, rw), r, s);
+            a.res = r; a.res_mode = res_mode;
+        }
+        conv_forward(cw, a, s);
+        nhwc_to_nchw(yo, y, s);
+    });
+}
+
+int tha4_test_norm(tha4_ctx* ctx, const float* x, int N, int C, int H, int W, int groups, const float* gamma,
+                   const float* beta, const float* film0, const float* film1, int act, int pool, float* y, void* stream) {
+    return guarded(ctx, [&] {
+        cudaStream_t s = (cudaStream_t)stream;
+        ctx->persist.reset(); ctx->scratch.reset();
+        Pool* P = &ctx->persist;
+        View xin; xin.N = N; xin.H = H; xin.W = W; xin.C = C; xin.ld = C; xin.p = P->alloc((size_t)N * H * W * C);
+        nchw_to_nhwc(make_img(x, N, C, H, W), xin, s);
+        double* sums = P->alloc_f64((size_t)N * C * 2);
+        THA4_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(double), s));
+        norm_stats(xin, sums, s);
+        float* coef = P->alloc((size_t)N * C * 2);
+        norm_finalize(sums, N, C, H * W, groups, gamma, beta, film0, film1, 2 * C, coef, s);
+        View yo = xin;
+        if (pool) { yo.H = H / 2; yo.W = W / 2; }
+        yo.p = P->alloc((size_t)N * yo.H * yo.W * C);
+        norm_apply(xin, coef, act, pool, nullptr, yo, s);
+        nhwc_to_nchw(yo, y, s);
+    });
+}
+
+int tha4_test_attention(tha4_ctx* ctx, const float* qkv, int N, int C, int heads, float* out, void* stream) {
+    return guarded(ctx, [&] {
+        cudaStream_t s = (cudaStream_t)stream;
+        ctx->persist.reset(); ctx->scratch.reset();
+        Pool* P = &ctx->persist;
+        View q; q.N = N; q.H = 16; q.W = 16; q.C = 3 * C; q.ld = 3 * C; q.p = P->alloc((size_t)N * 256 * 3 * C);
+        nchw_to_nhwc(make_img(qkv, N, 3 * C, 16, 16), q, s);
+        View o; o.N = N; o.H = 16; o.W = 16; o.C = C; o.ld = C; o.p = P->alloc((size_t)N * 256 * C);
+        attention_forward(q, heads, o, s);
+        nhwc_to_nchw(o, out, s);
+    });
+}
+
+int tha4_test_linear(tha4_ctx* ctx, const float* x, int N, int I, const float* W, const float* b, int O, int silu_in,
+                     float* y, void* stream) {
+    return guarded(ctx, [&] { linear_forward(x, I, N, I, W, b, O, silu_in, y, O, (cudaStream_t)stream); });
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Shared declarations for the tha4_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <stdexcept>
+#include <atomic>
+#include <algorithm>
+
+namespace tha4 {
+
+extern std::atomic<long> g_kernel_launches;   // every kernel this library launches is counted (bench "gpu_launches")
+
+// NHWC fp32 activation view.  `ld` is the pixel stride in floats (>= C) so that a tensor can live in a channel
+// slice of a wider buffer (U-Net skip concatenation is free: producers write into their slice).
+struct View {
+    float* p = nullptr;
+    int N = 0, H = 0, W = 0, C = 0, ld = 0;
+    __host__ __device__ long pix(int n, int y, int x) const { return (((long)n * H + y) * W + x) * ld; }
+    View slice(int c0, int c) const { View v = *this; v.p = p + c0; v.C = c; return v; }
+    size_t pixels() const { return (size_t)N * H * W; }
+};
+
+// NCHW fp32 view with explicit strides (crops of a larger image need no copy).
+struct ImgView {
+    const float* p = nullptr;
+    int N = 0, C = 0, H = 0, W = 0;
+    long sn = 0, sc = 0, sh = 0;   // strides in floats; sw == 1
+};
+inline ImgView make_img(const float* p, int N, int C, int H, int W) {
+    ImgView v; v.p = p; v.N = N; v.C = C; v.H = H; v.W = W; v.sc = (long)H * W; v.sn = (long)C * H * W; v.sh = W; return v;
+}
+inline ImgView crop_img(const ImgView& s, int y0, int x0, int h, int w) {
+    ImgView v = s; v.p = s.p + (long)y0 * s.sh + x0; v.H = h; v.W = w; return v;
+}
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define THA4_CUDA_CHECK(expr)                                                                     \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            throw tha4::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) +     \
+                                  " at " + __FILE__ + ":" + std::to_string(__LINE__));            \
+    } while (0)
+
+#define THA4_LAUNCH_CHECK()                                                                       \
+    do {                                                                                          \
+        tha4::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);                          \
+        THA4_CUDA_CHECK(cudaGetLastError());                                                      \
+    } while (0)
+
+#define THA4_REQUIRE(cond, msg)                                                                   \
+    do {                                                                                          \
+        if (!(cond)) throw std::runtime_error(std::string("tha4: ") + (msg) + " [" #cond "] at " + \
+                                              __FILE__ + ":" + std::to_string(__LINE__));         \
+    } while (0)
+
+inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == ACT_RELU) return fmaxf(v, 0.0f);
+    if (act == ACT_SILU) return v / (1.0f + expf(-v));
+    return v;
+}
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+}  // namespace tha4

@@ -1,0 +1,54 @@
+// Implicit-GEMM convolution on NHWC fp32 activations (declarations).
+//
+// One kernel family covers every dense contraction of the teacher networks:
+//   3x3 s1 p1 (nn/conv.py:38-41, unet.py:133,142,454,529), 4x4 s2 p1 downsample (nn/conv.py:141-147),
+//   4x4 s2 p1 transposed upsample as 4 output phases of 2x2 taps (nn/conv.py:171-177), 1x1 (unet.py:152,224-225).
+// GEMM view: M = output pixels, N = Cout, K = taps * Cin.
+#pragma once
+#include "common.cuh"
+
+namespace tha4 {
+
+constexpr int CONV_MAX_TAPS = 16;
+constexpr int CONV_MAX_PHASES = 4;
+
+enum ResMode { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2, RES_DOWN2 = 3 };
+
+// Packed weights: [phase][tap][cout_pad][cin_pad] fp32, cin_pad % 32 == 0, cout_pad % 32 == 0, zero padded.
+struct ConvWeights {
+    float* w = nullptr;
+    float* bias = nullptr;      // [cout] or nullptr
+    int cin = 0, cout = 0, cin_pad = 0, cout_pad = 0;
+    int ntaps = 0, nphase = 1;
+    int stride = 1;             // input stride
+    int out_mul = 1;            // output coordinate = m * out_mul + phase offset (2 for the transposed conv)
+    signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
+    signed char dx[CONV_MAX_PHASES][CONV_MAX_TAPS];
+    signed char ph_oy[CONV_MAX_PHASES], ph_ox[CONV_MAX_PHASES];
+};
+
+enum ConvKind { CONV_3x3 = 0, CONV_4x4_S2 = 1, CONVT_4x4_S2 = 2, CONV_1x1 = 3 };
+
+// Fills the tap tables of `cw` for `kind` (no allocation).
+void conv_describe(ConvWeights& cw, ConvKind kind, int cin, int cout);
+
+// Packs reference-layout weights (Conv2d: [Cout,Cin,kh,kw]; ConvTranspose2d: [Cin,Cout,kh,kw]) into cw.w
+// (device buffer of conv_packed_floats(cw) floats, zero-filled by this call).  `cin_offset` lets two Conv2d
+// weights share one packed tensor along Cin (Upscaler02's first_conv + coarse_image_conv).
+size_t conv_packed_floats(const ConvWeights& cw);
+void conv_pack(const ConvWeights& cw, ConvKind kind, const float* w_ref, int w_cin, int cin_offset, cudaStream_t s);
+
+struct ConvArgs {
+    View in;                    // stored input (if in_up: stored at half the logical resolution)
+    int in_up = 0;              // nearest-neighbour x2 upsample fused into the gather (unet.py:46)
+    View out;
+    View res;                   // residual added in the epilogue (res.p == nullptr: none)
+    int res_mode = RES_NONE;    // RES_UP2: res stored at half resolution; RES_DOWN2: res at double resolution (2x2 mean)
+    int strict = 0;             // 1: 3xTF32 error-compensated products (fp32-equivalent); 0: single TF32
+    int ksplit = 0;             // 0: choose automatically
+};
+
+// out = conv(in) + bias (+ res).  When the launch splits K, `out` is zeroed first on the same stream.
+void conv_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);
+
+}  // namespace tha4

@@ -1,0 +1,504 @@
+// Network assembly: weight loading / packing and the launch sequences of the five teacher networks.
+#include "nets.cuh"
+#include <algorithm>
+#include <cmath>
+
+namespace tha4 {
+
+// ------------------------------------------------------------------------------------------------ Pool
+Pool::~Pool() { for (auto& b : blocks_) cudaFree(b.p); }
+
+float* Pool::alloc(size_t nfloats) {
+    size_t bytes = ((nfloats * sizeof(float) + 255) / 256) * 256;
+    if (bytes == 0) bytes = 256;
+    for (auto& b : blocks_)
+        if (!b.used && b.bytes == bytes) { b.used = true; return reinterpret_cast<float*>(b.p); }
+    void* p = nullptr;
+    THA4_CUDA_CHECK(cudaMalloc(&p, bytes));
+    blocks_.push_back({p, bytes, true});
+    total_ += bytes;
+    return reinterpret_cast<float*>(p);
+}
+
+void Pool::reset() { for (auto& b : blocks_) b.used = false; }
+
+long TensorRef::numel() const { long n = 1; for (long d : shape) n *= d; return n; }
+
+// ------------------------------------------------------------------------------------------------ helpers
+namespace {
+
+const TensorRef& sd_get(const StateDict& sd, const std::string& key) {
+    auto it = sd.find(key);
+    if (it == sd.end()) throw std::runtime_error("tha4: state_dict is missing key '" + key + "'");
+    return it->second;
+}
+
+float* dev_alloc(size_t n) {
+    float* p = nullptr;
+    THA4_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(float)));
+    return p;
+}
+
+float* dev_clone(const TensorRef& t, cudaStream_t s) {
+    float* p = dev_alloc(t.numel());
+    THA4_CUDA_CHECK(cudaMemcpyAsync(p, t.p, t.numel() * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return p;
+}
+
+NormW load_norm(const StateDict& sd, const std::string& prefix, cudaStream_t s) {
+    NormW n;
+    const TensorRef& g = sd_get(sd, prefix + ".weight");
+    n.C = (int)g.numel();
+    n.gamma = dev_clone(g, s);
+    n.beta = dev_clone(sd_get(sd, prefix + ".bias"), s);
+    return n;
+}
+
+// cin_kernel: channel count of the activation tensor the kernel will read (>= the reference Cin, multiple of 4).
+ConvWeights load_conv(const StateDict& sd, const std::string& prefix, ConvKind kind, bool bias, cudaStream_t s,
+                      int cin_kernel = 0) {
+    const TensorRef& w = sd_get(sd, prefix + ".weight");
+    THA4_REQUIRE(w.shape.size() == 4, "conv weight rank: " + prefix);
+    const int cout = (int)(kind == CONVT_4x4_S2 ? w.shape[1] : w.shape[0]);
+    const int cin = (int)(kind == CONVT_4x4_S2 ? w.shape[0] : w.shape[1]);
+    const int k = (kind == CONV_3x3) ? 3 : (kind == CONV_1x1 ? 1 : 4);
+    THA4_REQUIRE(w.shape[2] == k && w.shape[3] == k, "conv kernel size: " + prefix);
+    ConvWeights cw;
+    conv_describe(cw, kind, cin_kernel > 0 ? cin_kernel : cin, cout);
+    THA4_REQUIRE(cw.cin >= cin && cw.cin % 4 == 0, "conv cin: " + prefix);
+    cw.w = dev_alloc(conv_packed_floats(cw));
+    THA4_CUDA_CHECK(cudaMemsetAsync(cw.w, 0, conv_packed_floats(cw) * sizeof(float), s));
+    conv_pack(cw, kind, w.p, cin, 0, s);
+    if (bias) cw.bias = dev_clone(sd_get(sd, prefix + ".bias"), s);
+    return cw;
+}
+
+__global__ void tail_pack_kernel(float* w, float* b, const float* src_w, const float* src_b, int C, int cout, int co_off) {
+    const int total = cout * C * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9;
+        const int c = (i / 9) % C;
+        const int co = i / (9 * C);
+        w[(tap * C + c) * TAIL_CO_PAD + co_off + co] = src_w[i];
+    }
+    if (src_b && blockIdx.x == 0 && threadIdx.x < cout) b[co_off + threadIdx.x] = src_b[threadIdx.x];
+}
+
+void tail_init(TailWeights& tw, int C, cudaStream_t s) {
+    tw.C = C; tw.CO = 0;
+    tw.w = dev_alloc((size_t)9 * C * TAIL_CO_PAD);
+    tw.bias = dev_alloc(TAIL_CO_PAD);
+    THA4_CUDA_CHECK(cudaMemsetAsync(tw.w, 0, (size_t)9 * C * TAIL_CO_PAD * sizeof(float), s));
+    THA4_CUDA_CHECK(cudaMemsetAsync(tw.bias, 0, TAIL_CO_PAD * sizeof(float), s));
+}
+
+void tail_add_head(TailWeights& tw, const StateDict& sd, const std::string& prefix, bool bias, cudaStream_t s) {
+    const TensorRef& w = sd_get(sd, prefix + ".weight");
+    THA4_REQUIRE(w.shape.size() == 4 && w.shape[1] == tw.C && w.shape[2] == 3 && w.shape[3] == 3, "head shape: " + prefix);
+    const int cout = (int)w.shape[0];
+    THA4_REQUIRE(tw.CO + cout <= TAIL_CO_PAD, "too many head channels");
+    const float* b = bias ? sd_get(sd, prefix + ".bias").p : nullptr;
+    tail_pack_kernel<<<32, 256, 0, s>>>(tw.w, tw.bias, w.p, b, tw.C, cout, tw.CO);
+    THA4_LAUNCH_CHECK();
+    tw.CO += cout;
+}
+
+__global__ void vec_add_kernel(float* dst, const float* a, const float* b, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = a[i] + b[i];
+}
+
+View make_view(Pool* pool, int N, int H, int W, int C) {
+    View v; v.N = N; v.H = H; v.W = W; v.C = C; v.ld = C;
+    v.p = pool->alloc((size_t)N * H * W * C);
+    return v;
+}
+
+// statistics -> per-(n,c) affine (InstanceNorm when groups == 0, GroupNorm otherwise), from the scratch pool
+float* norm_coef(Runtime& rt, const View& x, const NormW& nw, int groups, const float* film0, const float* film1,
+                 int film1_ld) {
+    THA4_REQUIRE(nw.C == x.C, "norm: channel mismatch");
+    const size_t n = (size_t)x.N * x.C * 2;
+    double* sums = rt.scratch->alloc_f64(n);
+    THA4_CUDA_CHECK(cudaMemsetAsync(sums, 0, n * sizeof(double), rt.stream));
+    norm_stats(x, sums, rt.stream);
+    float* coef = rt.scratch->alloc(n);
+    norm_finalize(sums, x.N, x.C, x.H * x.W, groups, nw.gamma, nw.beta, film0, film1, film1_ld, coef, rt.stream);
+    return coef;
+}
+
+void run_conv(Runtime& rt, const ConvWeights& cw, const View& in, const View& out, int in_up = 0,
+              const View* res = nullptr, int res_mode = RES_NONE) {
+    ConvArgs a;
+    a.in = in; a.in_up = in_up; a.out = out; a.strict = rt.strict;
+    if (res) { a.res = *res; a.res_mode = res_mode; }
+    conv_forward(cw, a, rt.stream);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ EncDecNet
+EncDecNet::EncDecNet(TailKind kind, int size, int in_ch, int pose_ch)
+    : kind_(kind), S_(size), in_ch_(in_ch), pose_ch_(pose_ch), pose_pad_(round_up(pose_ch, 4)) {}
+
+void EncDecNet::load(const StateDict& sd, cudaStream_t s) {
+    const std::string p = (kind_ == TAIL_FACE) ? "" : "body.";
+    down_[0] = load_conv(sd, p + "downsample_blocks.0.0", CONV_3x3, false, s);
+    down_n_[0] = load_norm(sd, p + "downsample_blocks.0.1", s);
+    for (int i = 1; i < 4; ++i) {
+        down_[i] = load_conv(sd, p + "downsample_blocks." + std::to_string(i) + ".0", CONV_4x4_S2, false, s);
+        down_n_[i] = load_norm(sd, p + "downsample_blocks." + std::to_string(i) + ".1", s);
+    }
+    bott0_ = load_conv(sd, p + "bottleneck_blocks.0.0", CONV_3x3, false, s, 512 + pose_pad_);
+    bott0_n_ = load_norm(sd, p + "bottleneck_blocks.0.1", s);
+    for (int i = 0; i < 5; ++i) {
+        const std::string rp = p + "bottleneck_blocks." + std::to_string(i + 1) + ".resnet_path.";
+        res_[i][0] = load_conv(sd, rp + "0", CONV_3x3, false, s);
+        res_n_[i][0] = load_norm(sd, rp + "1", s);
+        res_[i][1] = load_conv(sd, rp + "3", CONV_3x3, false, s);
+        res_n_[i][1] = load_norm(sd, rp + "4", s);
+    }
+    for (int i = 0; i < 3; ++i) {
+        up_[i] = load_conv(sd, p + "upsample_blocks." + std::to_string(i) + ".0", CONVT_4x4_S2, false, s);
+        up_n_[i] = load_norm(sd, p + "upsample_blocks." + std::to_string(i) + ".1", s);
+    }
+    tail_init(tail_, 64, s);
+    if (kind_ == TAIL_DECOMPOSER) {           // packing order expected by tail.cu
+        tail_add_head(tail_, sd, "background_layer_alpha.0", true, s);
+        tail_add_head(tail_, sd, "background_layer_color_change.0", true, s);
+        tail_add_head(tail_, sd, "eyebrow_layer_alpha.0", true, s);
+        tail_add_head(tail_, sd, "eyebrow_layer_color_change.0", true, s);
+    } else if (kind_ == TAIL_COMBINER) {
+        tail_add_head(tail_, sd, "morphed_eyebrow_layer_grid_change", false, s);
+        tail_add_head(tail_, sd, "morphed_eyebrow_layer_alpha.0", true, s);
+        tail_add_head(tail_, sd, "morphed_eyebrow_layer_color_change.0", true, s);
+        tail_add_head(tail_, sd, "combine_alpha.0", true, s);
+    } else {
+        tail_add_head(tail_, sd, "iris_mouth_grid_change", false, s);
+        tail_add_head(tail_, sd, "iris_mouth_color_change.0", true, s);
+        tail_add_head(tail_, sd, "iris_mouth_alpha.0", true, s);
+        tail_add_head(tail_, sd, "eye_color_change.0", true, s);
+        tail_add_head(tail_, sd, "eye_alpha.0", true, s);
+    }
+    THA4_CUDA_CHECK(cudaStreamSynchronize(s));
+    loaded_ = true;
+}
+
+void EncDecNet::forward(Runtime& rt, const ImgView& image0, const ImgView& image1, const float* pose, int pose_ld,
+                        float* const* outputs) {
+    THA4_REQUIRE(loaded_, "network weights not loaded");
+    THA4_REQUIRE(image0.H == S_ && image0.W == S_ && image0.C == 4, "encdec: image size");
+    const int B = image0.N;
+    cudaStream_t s = rt.stream;
+    Pool* P = rt.persist;
+    rt.scratch->reset();
+
+    View x0 = make_view(P, B, S_, S_, in_ch_);
+    if (kind_ == TAIL_COMBINER) {   // cat([background_layer, eyebrow_layer], dim=1)  (eyebrow_morphing_combiner_00.py:48)
+        nchw_to_nhwc(image1, x0.slice(0, 4), s);
+        nchw_to_nhwc(image0, x0.slice(4, 4), s);
+    } else {
+        nchw_to_nhwc(image0, x0, s);
+    }
+    // conv -> InstanceNorm -> ReLU; the activated tensor goes to `dst`
+    auto conv_in_relu = [&](const ConvWeights& cw, const NormW& nw, const View& in, int oh, const View* dst) -> View {
+        View raw = make_view(P, B, oh, oh, cw.cout);
+        run_conv(rt, cw, in, raw);
+        float* coef = norm_coef(rt, raw, nw, 0, nullptr, nullptr, 0);
+        const View& y = dst ? *dst : raw;
+        norm_apply(raw, coef, ACT_RELU, 0, nullptr, y, s);
+        return y;
+    };
+    View f = conv_in_relu(down_[0], down_n_[0], x0, S_, nullptr);
+    f = conv_in_relu(down_[1], down_n_[1], f, S_ / 2, nullptr);
+    f = conv_in_relu(down_[2], down_n_[2], f, S_ / 4, nullptr);
+    const int b = S_ / 8;
+    View bin = make_view(P, B, b, b, 512 + pose_pad_);
+    View bfeat = bin.slice(0, 512);
+    conv_in_relu(down_[3], down_n_[3], f, b, &bfeat);
+    if (pose_pad_ > 0) tile_vector(pose, pose_ld, pose_ch_, bin.slice(512, pose_pad_), s);   // poser_encoder_decoder_00.py:110-113
+    View x = conv_in_relu(bott0_, bott0_n_, bin, b, nullptr);
+    for (int i = 0; i < 5; ++i) {   // ResnetBlock: x + IN(conv(relu(IN(conv(x)))))  (resnet_block.py:52-67)
+        View h = conv_in_relu(res_[i][0], res_n_[i][0], x, b, nullptr);
+        View raw = make_view(P, B, b, b, 512);
+        run_conv(rt, res_[i][1], h, raw);
+        float* coef = norm_coef(rt, raw, res_n_[i][1], 0, nullptr, nullptr, 0);
+        norm_apply(raw, coef, ACT_NONE, 0, &x, raw, s);
+        x = raw;
+    }
+    x = conv_in_relu(up_[0], up_n_[0], x, b * 2, nullptr);
+    x = conv_in_relu(up_[1], up_n_[1], x, b * 4, nullptr);
+    // last block: leave InstanceNorm + ReLU pending; the tail kernel applies them while staging its halo tile
+    View raw = make_view(P, B, S_, S_, 64);
+    run_conv(rt, up_[2], x, raw);
+    float* coef = norm_coef(rt, raw, up_n_[2], 0, nullptr, nullptr, 0);
+    tail_forward(kind_, tail_, raw, coef, ACT_RELU, image0, image1, outputs, s);
+}
+
+// ------------------------------------------------------------------------------------------------ UNetNet
+UNetNet::UNetNet(bool upscaler, int size, int model_channels, std::vector<int> mults)
+    : upscaler_(upscaler), S_(size), mc_(model_channels), L_((int)mults.size()), mults_(std::move(mults)) {}
+
+namespace {
+
+ResBlockW load_res_block(const StateDict& sd, const std::string& p, cudaStream_t s) {
+    ResBlockW w;
+    w.norm0 = load_norm(sd, p + ".norm0", s);
+    w.conv0 = load_conv(sd, p + ".conv0", CONV_3x3, true, s);
+    w.norm1 = load_norm(sd, p + ".norm1", s);
+    w.conv1 = load_conv(sd, p + ".conv1", CONV_3x3, true, s);
+    w.cin = w.conv0.cin; w.cout = w.conv0.cout;
+    w.has_skip = sd.count(p + ".skip.weight") > 0;
+    if (w.has_skip) w.skip = load_conv(sd, p + ".skip", CONV_1x1, true, s);
+    return w;
+}
+
+AttnW load_attn(const StateDict& sd, const std::string& p, cudaStream_t s) {
+    AttnW a;
+    a.norm = load_norm(sd, p + ".norm", s);
+    a.qkv = load_conv(sd, p + ".qkv", CONV_1x1, true, s);
+    a.proj = load_conv(sd, p + ".conv", CONV_1x1, true, s);
+    a.C = a.proj.cout;
+    return a;
+}
+
+}  // namespace
+
+void UNetNet::load(const StateDict& sd, cudaStream_t s) {
+    const std::string p = "body.";
+    std::vector<std::pair<ResBlockW*, std::string>> all_blocks;   // for FiLM batching
+    // first conv (Upscaler02: first_conv(rest) + coarse_image_conv(cat(coarse_posed, warped, coarse_grid)) fused
+    // into one 16-input-channel conv; upscaler_02.py:79-82, unet.py:645-646)
+    if (!upscaler_) {
+        first_ = load_conv(sd, p + "first_conv", CONV_3x3, true, s);
+    } else {
+        const TensorRef& w1 = sd_get(sd, p + "first_conv.weight");
+        const TensorRef& w2 = sd_get(sd, "coarse_image_conv.weight");
+        THA4_REQUIRE(w1.shape[1] == 4 && w2.shape[1] == 10 && w1.shape[0] == w2.shape[0], "upscaler first conv shapes");
+        conv_describe(first_, CONV_3x3, 16, (int)w1.shape[0]);
+        first_.w = dev_alloc(conv_packed_floats(first_));
+        THA4_CUDA_CHECK(cudaMemsetAsync(first_.w, 0, conv_packed_floats(first_) * sizeof(float), s));
+        conv_pack(first_, CONV_3x3, w1.p, 4, 0, s);
+        conv_pack(first_, CONV_3x3, w2.p, 10, 4, s);
+        first_.bias = dev_alloc(first_.cout);
+        vec_add_kernel<<<ceil_div(first_.cout, 128), 128, 0, s>>>(first_.bias, sd_get(sd, p + "first_conv.bias").p,
+                                                                  sd_get(sd, "coarse_image_conv.bias").p, first_.cout);
+        THA4_LAUNCH_CHECK();
+    }
+    down_res_.resize(L_); down_ds_.resize(L_ - 1);
+    for (int i = 0; i < L_; ++i) {
+        const std::string bp = p + "down_blocks." + std::to_string(i);
+        down_res_[i] = load_res_block(sd, bp + ".res_blocks.0", s);
+        all_blocks.push_back({&down_res_[i], bp + ".res_blocks.0"});
+        if (i == L_ - 1) down_attn_ = load_attn(sd, bp + ".attention_blocks.0", s);
+        if (i < L_ - 1) {
+            down_ds_[i] = load_res_block(sd, bp + ".downsample", s);
+            all_blocks.push_back({&down_ds_[i], bp + ".downsample"});
+        }
+    }
+    mid_res_.resize(4); mid_attn_.resize(3);
+    for (int j = 0; j < 7; ++j) {
+        const std::string mp = p + "middle_blocks." + std::to_string(j);
+        if (j % 2 == 0) { mid_res_[j / 2] = load_res_block(sd, mp, s); all_blocks.push_back({&mid_res_[j / 2], mp}); }
+        else mid_attn_[j / 2] = load_attn(sd, mp + ".module", s);
+    }
+    up_res_.resize(2 * L_); up_us_.resize(L_ - 1); up_attn_.resize(2);
+    for (int bi = 0; bi < L_; ++bi) {
+        const std::string bp = p + "up_blocks." + std::to_string(bi);
+        for (int r = 0; r < 2; ++r) {
+            const std::string rp = bp + ".resnet_blocks." + std::to_string(r);
+            up_res_[2 * bi + r] = load_res_block(sd, rp, s);
+            all_blocks.push_back({&up_res_[2 * bi + r], rp});
+            if (bi == 0) up_attn_[r] = load_attn(sd, bp + ".attention_blocks." + std::to_string(r), s);
+        }
+        if (bi < L_ - 1) {
+            up_us_[bi] = load_res_block(sd, bp + ".upsample", s);
+            all_blocks.push_back({&up_us_[bi], bp + ".upsample"});
+        }
+    }
+    last_n_ = load_norm(sd, p + "last.0", s);
+    tail_init(tail_, mc_, s);
+    tail_add_head(tail_, sd, p + "last.2", true, s);
+
+    // pose embedding MLP (unet.py:449-452)
+    cond_w0_ = dev_clone(sd_get(sd, p + "cond_embed.0.weight"), s);
+    cond_b0_ = dev_clone(sd_get(sd, p + "cond_embed.0.bias"), s);
+    cond_w2_ = dev_clone(sd_get(sd, p + "cond_embed.2.weight"), s);
+    cond_b2_ = dev_clone(sd_get(sd, p + "cond_embed.2.bias"), s);
+
+    // time embedding at t = 0 is a constant: cat(cos(0)..., sin(0)...) -> Linear -> SiLU -> Linear  (unet.py:365-376,443-447)
+    std::vector<float> t0(mc_, 0.0f);
+    for (int i = 0; i < mc_ / 2; ++i) t0[i] = 1.0f;
+    float* d_t0 = dev_alloc(mc_);
+    THA4_CUDA_CHECK(cudaMemcpyAsync(d_t0, t0.data(), mc_ * sizeof(float), cudaMemcpyHostToDevice, s));
+    float* d_t1 = dev_alloc(256);
+    float* d_t2 = dev_alloc(256);
+    linear_forward(d_t0, mc_, 1, mc_, sd_get(sd, p + "time_embed.1.weight").p, sd_get(sd, p + "time_embed.1.bias").p, 256, 0, d_t1, 256, s);
+    linear_forward(d_t1, 256, 1, 256, sd_get(sd, p + "time_embed.3.weight").p, sd_get(sd, p + "time_embed.3.bias").p, 256, 1, d_t2, 256, s);
+
+    // per-block FiLM: cond0 (time) folded to constants; cond1 (pose) stacked into one [R,256] projection
+    film1_total_ = 0;
+    for (auto& e : all_blocks) { e.first->film1_off = film1_total_; film1_total_ += 2 * e.first->cout; }
+    film1_w_ = dev_alloc((size_t)film1_total_ * 256);
+    film1_b_ = dev_alloc(film1_total_);
+    for (auto& e : all_blocks) {
+        ResBlockW* w = e.first;
+        const TensorRef& c0w = sd_get(sd, e.second + ".cond0_layers.1.weight");
+        THA4_REQUIRE(c0w.shape[0] == 2 * w->cout && c0w.shape[1] == 256, "cond0 shape: " + e.second);
+        w->film0 = dev_alloc(2 * w->cout);
+        linear_forward(d_t2, 256, 1, 256, c0w.p, sd_get(sd, e.second + ".cond0_layers.1.bias").p, 2 * w->cout, 1, w->film0, 2 * w->cout, s);
+        const TensorRef& c1w = sd_get(sd, e.second + ".cond1_layers.1.weight");
+        THA4_REQUIRE(c1w.shape[0] == 2 * w->cout && c1w.shape[1] == 256, "cond1 shape: " + e.second);
+        THA4_CUDA_CHECK(cudaMemcpyAsync(film1_w_ + (size_t)w->film1_off * 256, c1w.p, c1w.numel() * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        THA4_CUDA_CHECK(cudaMemcpyAsync(film1_b_ + w->film1_off, sd_get(sd, e.second + ".cond1_layers.1.bias").p,
+                                        2 * w->cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    THA4_CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(d_t0); cudaFree(d_t1); cudaFree(d_t2);
+    loaded_ = true;
+}
+
+// ResBlock (unet.py:154-165).  mode: 0 same, 1 up (nearest x2), 2 down (AvgPool2d(2)).
+void UNetNet::res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode, const float* film1, const View& out) {
+    cudaStream_t s = rt.stream;
+    rt.scratch->reset();
+    THA4_REQUIRE(x.C == w.cin && out.C == w.cout, "res_block: channels");
+    const int B = x.N;
+    // norm0 -> SiLU -> (avg-pool) ; the nearest-upsample is folded into conv0's gather
+    float* coef0 = norm_coef(rt, x, w.norm0, 32, nullptr, nullptr, 0);
+    const int th = (mode == 2) ? x.H / 2 : x.H;
+    View t0 = make_view(rt.scratch, B, th, th, w.cin);
+    norm_apply(x, coef0, ACT_SILU, mode == 2 ? 1 : 0, nullptr, t0, s);
+    View h = make_view(rt.scratch, B, out.H, out.W, w.cout);
+    run_conv(rt, w.conv0, t0, h, mode == 1 ? 1 : 0);
+    // norm1 -> FiLM(time) -> FiLM(pose) -> SiLU, folded into one per-(n,c) affine
+    float* coef1 = norm_coef(rt, h, w.norm1, 32, w.film0, film1 + w.film1_off, film1_total_);
+    norm_apply(h, coef1, ACT_SILU, 0, nullptr, h, s);
+    if (w.has_skip) {
+        THA4_REQUIRE(mode == 0, "res_block: skip conv only on same-resolution blocks");
+        View sk = make_view(rt.scratch, B, x.H, x.W, w.cout);
+        run_conv(rt, w.skip, x, sk);
+        run_conv(rt, w.conv1, h, out, 0, &sk, RES_SAME);
+    } else {
+        run_conv(rt, w.conv1, h, out, 0, &x, mode == 0 ? RES_SAME : (mode == 1 ? RES_UP2 : RES_DOWN2));
+    }
+}
+
+// AttentionBlock (unet.py:230-239)
+void UNetNet::attn_block(Runtime& rt, const AttnW& w, const View& x, const View& out) {
+    cudaStream_t s = rt.stream;
+    rt.scratch->reset();
+    float* coef = norm_coef(rt, x, w.norm, 32, nullptr, nullptr, 0);
+    View t = make_view(rt.scratch, x.N, x.H, x.W, x.C);
+    norm_apply(x, coef, ACT_NONE, 0, nullptr, t, s);
+    View qkv = make_view(rt.scratch, x.N, x.H, x.W, 3 * x.C);
+    run_conv(rt, w.qkv, t, qkv);
+    View a = make_view(rt.scratch, x.N, x.H, x.W, x.C);
+    attention_forward(qkv, 8, a, s);
+    run_conv(rt, w.proj, a, out, 0, &x, RES_SAME);
+}
+
+void UNetNet::forward(Runtime& rt, const ImgView& image, const float* coarse_posed, const float* coarse_grid, int coarse_size,
+                      const float* pose, int pose_ld, float* const* outputs) {
+    THA4_REQUIRE(loaded_, "network weights not loaded");
+    THA4_REQUIRE(image.H == S_ && image.W == S_ && image.C == 4, "unet: image size");
+    const int B = image.N;
+    cudaStream_t s = rt.stream;
+    Pool* P = rt.persist;
+    rt.scratch->reset();
+
+    // pose embedding and all FiLM vectors of this forward in three tiny launches
+    float* c1 = P->alloc((size_t)B * 256);
+    float* c2 = P->alloc((size_t)B * 256);
+    float* film1 = P->alloc((size_t)B * film1_total_);
+    linear_forward(pose, pose_ld, B, 6, cond_w0_, cond_b0_, 256, 0, c1, 256, s);
+    linear_forward(c1, 256, B, 256, cond_w2_, cond_b2_, 256, 1, c2, 256, s);
+    linear_forward(c2, 256, B, 256, film1_w_, film1_b_, film1_total_, 1, film1, film1_total_, s);
+
+    View x0;
+    if (upscaler_) {
+        x0 = make_view(P, B, S_, S_, 16);
+        upscaler_prologue(image, coarse_posed, coarse_grid, coarse_size, x0, s);
+    } else {
+        x0 = make_view(P, B, S_, S_, 4);
+        nchw_to_nhwc(image, x0, s);
+    }
+
+    // ---- plan the skip concatenations: up res-block j reads cat(h_j, hs[2L-1-j]) from one buffer ----
+    const int NH = 2 * L_;
+    std::vector<int> hs_ch(NH);
+    hs_ch[0] = mc_;
+    for (int i = 0; i < L_; ++i) {
+        hs_ch[2 * i + 1] = mc_ * mults_[i];
+        if (i < L_ - 1) hs_ch[2 * i + 2] = mc_ * mults_[i];
+    }
+    std::vector<View> cat(NH), hs(NH);
+    std::vector<int> ch_h(NH);
+    for (int j = 0; j < NH; ++j) {
+        const int lvl = L_ - 1 - j / 2;
+        const int sp = S_ >> lvl;
+        ch_h[j] = (j == 0) ? mc_ * mults_[L_ - 1] : ((j & 1) ? mc_ * mults_[lvl] : mc_ * mults_[lvl + 1]);
+        const int cs = hs_ch[NH - 1 - j];
+        THA4_REQUIRE(ch_h[j] + cs == up_res_[j].cin, "unet: concat plan does not match weights");
+        cat[j] = make_view(P, B, sp, sp, ch_h[j] + cs);
+        hs[NH - 1 - j] = cat[j].slice(ch_h[j], cs);
+    }
+
+    // ---- down path (unet.py:534-536) ----
+    run_conv(rt, first_, x0, hs[0]);
+    View cur = hs[0];
+    for (int i = 0; i < L_; ++i) {
+        if (i == L_ - 1) {
+            View tmp = make_view(P, B, cur.H, cur.W, down_res_[i].cout);
+            res_block(rt, down_res_[i], cur, 0, film1, tmp);
+            attn_block(rt, down_attn_, tmp, hs[2 * i + 1]);
+        } else {
+            res_block(rt, down_res_[i], cur, 0, film1, hs[2 * i + 1]);
+        }
+        cur = hs[2 * i + 1];
+        if (i < L_ - 1) {
+            res_block(rt, down_ds_[i], cur, 2, film1, hs[2 * i + 2]);
+            cur = hs[2 * i + 2];
+        }
+    }
+    // ---- middle: Res, Attn, Res, Attn, Res, Attn, Res (unet.py:481-498) ----
+    for (int j = 0; j < 4; ++j) {
+        const bool last = (j == 3);
+        View r = last ? cat[0].slice(0, ch_h[0]) : make_view(P, B, cur.H, cur.W, cur.C);
+        res_block(rt, mid_res_[j], cur, 0, film1, r);
+        cur = r;
+        if (!last) {
+            View a = make_view(P, B, cur.H, cur.W, cur.C);
+            attn_block(rt, mid_attn_[j], cur, a);
+            cur = a;
+        }
+    }
+    // ---- up path (unet.py:540-544) ----
+    View feat;
+    for (int j = 0; j < NH; ++j) {
+        const int lvl = L_ - 1 - j / 2;
+        const bool second = (j & 1);
+        const int co = up_res_[j].cout;
+        View dst;
+        if (!second) dst = cat[j + 1].slice(0, ch_h[j + 1]);
+        else dst = make_view(P, B, cat[j].H, cat[j].W, co);      // goes to the upsampler or is the final feature
+        if (lvl == L_ - 1) {
+            View tmp = make_view(P, B, cat[j].H, cat[j].W, co);
+            res_block(rt, up_res_[j], cat[j], 0, film1, tmp);
+            attn_block(rt, up_attn_[second ? 1 : 0], tmp, dst);
+        } else {
+            res_block(rt, up_res_[j], cat[j], 0, film1, dst);
+        }
+        if (second) {
+            if (lvl > 0) res_block(rt, up_us_[L_ - 1 - lvl], dst, 1, film1, cat[j + 1].slice(0, ch_h[j + 1]));
+            else feat = dst;
+        }
+    }
+    // ---- last: GroupNorm + SiLU pending, applied inside the fused tail (unet.py:526-529; morpher_00.py:53-58) ----
+    rt.scratch->reset();
+    float* coef = norm_coef(rt, feat, last_n_, 32, nullptr, nullptr, 0);
+    ImgView none{};
+    tail_forward(TAIL_UNET, tail_, feat, coef, ACT_SILU, image, none, outputs, s);
+}
+
+}  // namespace tha4

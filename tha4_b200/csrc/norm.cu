@@ -1,0 +1,148 @@
+// InstanceNorm2d / GroupNorm32 (+FiLM, +activation, +2x2 mean pool, +residual) on NHWC fp32 activations.
+// Three small HBM-bound kernels: per-(n,c) sum / sum-of-squares -> per-(n,c) affine -> elementwise apply.
+#include "ops.cuh"
+
+namespace tha4 {
+namespace {
+
+constexpr int STAT_PIX_PER_THREAD = 32;
+
+__global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ x, int HW, int C, int ld,
+                                                         double* __restrict__ sums) {
+    __shared__ float red[256][9];
+    const int cq = C >> 2;
+    const int PL = 256 / cq;
+    const int tid = threadIdx.x;
+    const int pl = tid / cq, q = tid - pl * cq;
+    const int n = blockIdx.y;
+    const bool active = pl < PL;
+    float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    if (active) {
+        const long base = (long)blockIdx.x * PL * STAT_PIX_PER_THREAD;
+        const float* xp = x + (long)n * HW * ld + 4 * q;
+#pragma unroll 4
+        for (int i = 0; i < STAT_PIX_PER_THREAD; ++i) {
+            long pix = base + (long)i * PL + pl;
+            if (pix < HW) {
+                float4 v = *reinterpret_cast<const float4*>(xp + pix * ld);
+                s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+                ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { red[tid][k] = s[k]; red[tid][4 + k] = ss[k]; }
+    __syncthreads();
+    if (active && pl == 0) {
+        double acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+        for (int j = 0; j < PL; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += (double)red[j * cq + q][k];
+        double* dst = sums + ((long)n * C + 4 * q) * 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            atomicAdd(dst + 2 * k, acc[k]);
+            atomicAdd(dst + 2 * k + 1, acc[4 + k]);
+        }
+    }
+}
+
+__global__ void norm_finalize_kernel(const double* __restrict__ sums, int C, int HW, int groups,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ film0, const float* __restrict__ film1, int film1_ld,
+                                     float* __restrict__ coef) {
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double su = 0.0, sq = 0.0, cnt;
+        if (groups == 0) {
+            su = sums[((long)n * C + c) * 2]; sq = sums[((long)n * C + c) * 2 + 1]; cnt = (double)HW;
+        } else {
+            const int cpg = C / groups, g0 = (c / cpg) * cpg;
+            for (int j = 0; j < cpg; ++j) { su += sums[((long)n * C + g0 + j) * 2]; sq += sums[((long)n * C + g0 + j) * 2 + 1]; }
+            cnt = (double)HW * cpg;
+        }
+        const double mean = su / cnt;
+        double var = sq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+        float A = rstd * gamma[c];
+        float B = beta[c] - (float)mean * A;
+        if (film0) { const float sc = 1.0f + film0[c], sh = film0[C + c]; A *= sc; B = B * sc + sh; }
+        if (film1) { const float* f = film1 + (long)n * film1_ld; const float sc = 1.0f + f[c], sh = f[C + c]; A *= sc; B = B * sc + sh; }
+        coef[((long)n * C + c) * 2] = A;
+        coef[((long)n * C + c) * 2 + 1] = B;
+    }
+}
+
+__global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ x, int xH, int xW, int x_ld,
+                                                         const float* __restrict__ coef, int act, int pool,
+                                                         const float* __restrict__ res, int res_ld,
+                                                         float* __restrict__ y, int yH, int yW, int y_ld, int C, long total) {
+    const int cq = C >> 2;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % cq);
+        long pix = i / cq;
+        const int ox = (int)(pix % yW); pix /= yW;
+        const int oy = (int)(pix % yH);
+        const int n = (int)(pix / yH);
+        const float4 c0 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2);
+        const float4 c1 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2 + 4);
+        float4 r;
+        if (!pool) {
+            const float4 v = *reinterpret_cast<const float4*>(x + (((long)n * xH + oy) * xW + ox) * x_ld + 4 * q);
+            r.x = act_apply(v.x * c0.x + c0.y, act); r.y = act_apply(v.y * c0.z + c0.w, act);
+            r.z = act_apply(v.z * c1.x + c1.y, act); r.w = act_apply(v.w * c1.z + c1.w, act);
+        } else {
+            r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const float4 v = *reinterpret_cast<const float4*>(
+                        x + (((long)n * xH + 2 * oy + dy) * xW + 2 * ox + dx) * x_ld + 4 * q);
+                    r.x += act_apply(v.x * c0.x + c0.y, act); r.y += act_apply(v.y * c0.z + c0.w, act);
+                    r.z += act_apply(v.z * c1.x + c1.y, act); r.w += act_apply(v.w * c1.z + c1.w, act);
+                }
+            r.x *= 0.25f; r.y *= 0.25f; r.z *= 0.25f; r.w *= 0.25f;
+        }
+        if (res) {
+            const float4 v = *reinterpret_cast<const float4*>(res + (((long)n * yH + oy) * yW + ox) * res_ld + 4 * q);
+            r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+        }
+        *reinterpret_cast<float4*>(y + (((long)n * yH + oy) * yW + ox) * y_ld + 4 * q) = r;
+    }
+}
+
+}  // namespace
+
+void norm_stats(const View& x, double* sums, cudaStream_t s) {
+    THA4_REQUIRE(x.C % 4 == 0 && x.C <= 1024 && x.ld % 4 == 0, "norm_stats: channels");
+    const int cq = x.C / 4, PL = 256 / cq;
+    const int HW = x.H * x.W;
+    dim3 grid(ceil_div(HW, PL * STAT_PIX_PER_THREAD), x.N);
+    norm_stats_kernel<<<grid, 256, 0, s>>>(x.p, HW, x.C, x.ld, sums);
+    THA4_LAUNCH_CHECK();
+}
+
+void norm_finalize(const double* sums, int N, int C, int HW, int groups, const float* gamma, const float* beta,
+                   const float* film0, const float* film1, int film1_ld, float* coef, cudaStream_t s) {
+    THA4_REQUIRE(groups == 0 || C % groups == 0, "norm_finalize: groups");
+    norm_finalize_kernel<<<N, 256, 0, s>>>(sums, C, HW, groups, gamma, beta, film0, film1, film1_ld, coef);
+    THA4_LAUNCH_CHECK();
+}
+
+void norm_apply(const View& x, const float* coef, int act, int pool, const View* res, const View& y, cudaStream_t s) {
+    THA4_REQUIRE(x.C == y.C && x.C % 4 == 0 && x.ld % 4 == 0 && y.ld % 4 == 0, "norm_apply: channels");
+    if (pool) THA4_REQUIRE(y.H * 2 == x.H && y.W * 2 == x.W, "norm_apply: pool dims");
+    else THA4_REQUIRE(y.H == x.H && y.W == x.W, "norm_apply: dims");
+    if (res) THA4_REQUIRE(res->H == y.H && res->W == y.W && res->C == y.C && res->ld % 4 == 0, "norm_apply: res dims");
+    const long total = (long)y.N * y.H * y.W * (y.C / 4);
+    const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    norm_apply_kernel<<<blocks, 256, 0, s>>>(x.p, x.H, x.W, x.ld, coef, act, pool, res ? res->p : nullptr,
+                                             res ? res->ld : 0, y.p, y.H, y.W, y.ld, x.C, total);
+    THA4_LAUNCH_CHECK();
+}
+
+}  // namespace tha4

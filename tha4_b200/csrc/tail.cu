@@ -1,0 +1,198 @@
+// Fused "decoder tail" kernels (SURVEY.md section 8 a-T): from the last feature map of a network to every tensor
+// that network returns, in one pass:
+//   pending norm affine + activation (applied while staging the halo tile; zero padding is applied after it, as
+//   the reference pads the activated tensor) -> 3x3 head conv(s) -> channel split -> sigmoid / tanh ->
+//   affine_grid + grid_sample index math -> 4-tap bilinear gather of the RGBA image -> alpha blend(s) ->
+//   coalesced NCHW stores of all outputs.
+// Reference: eyebrow_decomposer_00.py:46-64, eyebrow_morphing_combiner_00.py:51-72, face_morpher_08.py:170-193,
+// morpher_00.py:53-66, upscaler_02.py:84-96.
+// v1: CUDA-core FFMA head conv from a shared-memory halo tile (16x16 output pixels per CTA).
+#include "ops.cuh"
+#include "gridsample.cuh"
+
+namespace tha4 {
+namespace {
+
+constexpr int TILE = 16, HALO = TILE + 2;
+constexpr int CO_PAD = TAIL_CO_PAD;
+
+__device__ __forceinline__ void store4(float* out, long plane, long pix, const float (&v)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c * plane + pix] = v[c];
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ feat, int S, int C, int ld,
+                                                   const float* __restrict__ coef, int act,
+                                                   const float* __restrict__ wg, const float* __restrict__ bg,
+                                                   ImgView img0, ImgView img1, const float* __restrict__ base,
+                                                   float* o0, float* o1, float* o2, float* o3, float* o4, float* o5,
+                                                   float* o6, float* o7) {
+    extern __shared__ __align__(16) float sm[];
+    const int CP = C + 1;
+    float* wsm = sm;                          // [9*C][CO_PAD]
+    float* fsm = sm + 9 * C * CO_PAD;         // [HALO*HALO][CP]
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z;
+    const int by0 = blockIdx.y * TILE, bx0 = blockIdx.x * TILE;
+
+    for (int i = tid; i < 9 * C * CO_PAD / 4; i += 256)
+        reinterpret_cast<float4*>(wsm)[i] = reinterpret_cast<const float4*>(wg)[i];
+    const int cq = C >> 2;
+    for (int i = tid; i < HALO * HALO * cq; i += 256) {
+        const int q = i % cq, hp = i / cq;
+        const int hy = hp / HALO, hx = hp - hy * HALO;
+        const int gy = by0 + hy - 1, gx = bx0 + hx - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < S && gx >= 0 && gx < S) {
+            v = *reinterpret_cast<const float4*>(feat + (((long)n * S + gy) * S + gx) * ld + 4 * q);
+            const float4 c0 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2);
+            const float4 c1 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2 + 4);
+            v.x = act_apply(v.x * c0.x + c0.y, act); v.y = act_apply(v.y * c0.z + c0.w, act);
+            v.z = act_apply(v.z * c1.x + c1.y, act); v.w = act_apply(v.w * c1.z + c1.w, act);
+        }
+        float* d = fsm + hp * CP + 4 * q;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+
+    const int ty = tid / TILE, tx = tid % TILE;
+    float o[CO_PAD];
+#pragma unroll
+    for (int j = 0; j < CO_PAD; ++j) o[j] = bg[j];
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const float* fp = fsm + ((ty + tap / 3) * HALO + tx + tap % 3) * CP;
+        const float* wp = wsm + tap * C * CO_PAD;
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+            const float f = fp[c];
+            const float4 w0 = *reinterpret_cast<const float4*>(wp + c * CO_PAD);
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + c * CO_PAD + 4);
+            const float4 w2 = *reinterpret_cast<const float4*>(wp + c * CO_PAD + 8);
+            o[0] = fmaf(f, w0.x, o[0]); o[1] = fmaf(f, w0.y, o[1]); o[2] = fmaf(f, w0.z, o[2]); o[3] = fmaf(f, w0.w, o[3]);
+            o[4] = fmaf(f, w1.x, o[4]); o[5] = fmaf(f, w1.y, o[5]); o[6] = fmaf(f, w1.z, o[6]); o[7] = fmaf(f, w1.w, o[7]);
+            o[8] = fmaf(f, w2.x, o[8]); o[9] = fmaf(f, w2.y, o[9]); o[10] = fmaf(f, w2.z, o[10]); o[11] = fmaf(f, w2.w, o[11]);
+        }
+    }
+
+    const int y = by0 + ty, x = bx0 + tx;
+    const long plane = (long)S * S, pix = (long)y * S + x;
+    float* p0 = o0 + n * 4 * plane;   // most outputs are 4-channel; single/dual-channel ones are offset below
+    if (KIND == TAIL_UNET) {
+        // o: direct(0..3) grid_change(4,5) alpha-logit(6)
+        float direct[4] = {o[0], o[1], o[2], o[3]};
+        const float alpha = sigmoid_f(o[6]);
+        const GsTap t = gs_locate(base[x], base[y], o[4], o[5], S, S);
+        float warped[4], merged[4];
+        gs_sample<4>(img0.p + n * img0.sn, img0.sc, img0.sh, S, S, t, warped);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) merged[c] = direct[c] * alpha + warped[c] * (1.0f - alpha);
+        store4(p0, plane, pix, merged);
+        o1[n * plane + pix] = alpha;
+        store4(o2 + n * 4 * plane, plane, pix, warped);
+        o3[(n * 2L) * plane + pix] = o[4];
+        o3[(n * 2L + 1) * plane + pix] = o[5];
+        store4(o4 + n * 4 * plane, plane, pix, direct);
+    } else if (KIND == TAIL_DECOMPOSER) {
+        // o: bg_alpha(0) bg_color(1..4) eb_alpha(5) eb_color(6..9)
+        float img[4], bgc[4], ebc[4], bgl[4], ebl[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) img[c] = __ldg(img0.p + n * img0.sn + c * img0.sc + (long)y * img0.sh + x);
+        const float bga = sigmoid_f(o[0]), eba = sigmoid_f(o[5]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            bgc[c] = tanhf(o[1 + c]); ebc[c] = tanhf(o[6 + c]);
+            bgl[c] = bgc[c] * bga + img[c] * (1.0f - bga);
+            ebl[c] = img[c] * eba + ebc[c] * (1.0f - eba);     // apply_color_change(alpha, image, color): roles swapped
+        }
+        store4(p0, plane, pix, ebl);
+        o1[n * plane + pix] = eba;
+        store4(o2 + n * 4 * plane, plane, pix, ebc);
+        store4(o3 + n * 4 * plane, plane, pix, bgl);
+        o4[n * plane + pix] = bga;
+        store4(o5 + n * 4 * plane, plane, pix, bgc);
+    } else if (KIND == TAIL_COMBINER) {
+        // o: grid(0,1) alpha(2) color(3..6) combine_alpha(7); img0 = eyebrow layer (warped), img1 = background layer
+        const GsTap t = gs_locate(base[x], base[y], o[0], o[1], S, S);
+        float warped[4], color[4], morphed[4], bgv[4], e0[4], e1[4];
+        gs_sample<4>(img0.p + n * img0.sn, img0.sc, img0.sh, S, S, t, warped);
+        const float alpha = sigmoid_f(o[2]), ca = sigmoid_f(o[7]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            color[c] = tanhf(o[3 + c]);
+            morphed[c] = color[c] * alpha + warped[c] * (1.0f - alpha);
+            bgv[c] = __ldg(img1.p + n * img1.sn + c * img1.sc + (long)y * img1.sh + x);
+        }
+        const float a2 = (morphed[3] + 1.0f) / 2.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            e0[c] = morphed[c] * ca + bgv[c] * (1.0f - ca);
+            e1[c] = morphed[c] * a2 + bgv[c] * (1.0f - a2);
+        }
+        e0[3] = bgv[3]; e1[3] = bgv[3];
+        store4(p0, plane, pix, e0);
+        o1[n * plane + pix] = ca;
+        store4(o2 + n * 4 * plane, plane, pix, e1);
+        store4(o3 + n * 4 * plane, plane, pix, morphed);
+        o4[n * plane + pix] = alpha;
+        store4(o5 + n * 4 * plane, plane, pix, color);
+        store4(o6 + n * 4 * plane, plane, pix, warped);
+        o7[(n * 2L) * plane + pix] = o[0];
+        o7[(n * 2L + 1) * plane + pix] = o[1];
+    } else {  // TAIL_FACE
+        // o: grid(0,1) im_color(2..5) im_alpha(6) eye_color(7..10) eye_alpha(11)
+        const GsTap t = gs_locate(base[x], base[y], o[0], o[1], S, S);
+        float im0[4], imc[4], im1[4], eyc[4], outv[4];
+        gs_sample<4>(img0.p + n * img0.sn, img0.sc, img0.sh, S, S, t, im0);
+        const float ima = sigmoid_f(o[6]), eya = sigmoid_f(o[11]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            imc[c] = tanhf(o[2 + c]); eyc[c] = tanhf(o[7 + c]);
+            im1[c] = imc[c] * ima + im0[c] * (1.0f - ima);
+            outv[c] = eyc[c] * eya + im1[c] * (1.0f - eya);
+        }
+        store4(p0, plane, pix, outv);
+        o1[n * plane + pix] = eya;
+        store4(o2 + n * 4 * plane, plane, pix, eyc);
+        store4(o3 + n * 4 * plane, plane, pix, im1);
+        o4[n * plane + pix] = ima;
+        store4(o5 + n * 4 * plane, plane, pix, imc);
+        store4(o6 + n * 4 * plane, plane, pix, im0);
+        o7[(n * 2L) * plane + pix] = o[0];
+        o7[(n * 2L + 1) * plane + pix] = o[1];
+    }
+}
+
+template <int KIND>
+void launch_tail(const TailWeights& tw, const View& f, const float* coef, int act, const ImgView& i0, const ImgView& i1,
+                 float* const* o, int nout, cudaStream_t s) {
+    const size_t smem = ((size_t)9 * tw.C * CO_PAD + (size_t)HALO * HALO * (tw.C + 1)) * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    float* op[8];
+    for (int i = 0; i < 8; ++i) op[i] = i < nout ? o[i] : nullptr;
+    dim3 grid(f.W / TILE, f.H / TILE, f.N);
+    tail_kernel<KIND><<<grid, 256, smem, s>>>(f.p, f.H, f.C, f.ld, coef, act, tw.w, tw.bias, i0, i1,
+                                             base_grid_table(f.H), op[0], op[1], op[2], op[3], op[4], op[5], op[6], op[7]);
+    THA4_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+void tail_forward(TailKind kind, const TailWeights& tw, const View& feature, const float* coef, int act,
+                  const ImgView& image0, const ImgView& image1, float* const* outputs, cudaStream_t s) {
+    THA4_REQUIRE(feature.H == feature.W && feature.H % TILE == 0 && feature.C == tw.C && tw.C % 4 == 0, "tail: feature dims");
+    THA4_REQUIRE(image0.H == feature.H && image0.W == feature.W && image0.C == 4, "tail: image dims");
+    switch (kind) {
+        case TAIL_UNET: launch_tail<TAIL_UNET>(tw, feature, coef, act, image0, image1, outputs, 5, s); break;
+        case TAIL_DECOMPOSER: launch_tail<TAIL_DECOMPOSER>(tw, feature, coef, act, image0, image1, outputs, 6, s); break;
+        case TAIL_COMBINER: launch_tail<TAIL_COMBINER>(tw, feature, coef, act, image0, image1, outputs, 8, s); break;
+        case TAIL_FACE: launch_tail<TAIL_FACE>(tw, feature, coef, act, image0, image1, outputs, 8, s); break;
+    }
+}
+
+}  // namespace tha4
