@@ -47,9 +47,11 @@ const char* tha4_last_error(const tha4_ctx* ctx);
 
 /* options: "strict" (0: TF32 tensor-core products, the reference's own default on CUDA
  *                    1: 3xTF32 error-compensated products == fp32 convolution),
- *          "microbatch" (frames processed per pass of the teacher pipeline; bounds the workspace) */
+ *          "microbatch" (frames processed per pass of the teacher pipeline; bounds the workspace),
+ *          "profile" (1: time every kernel class with CUDA events on the launching stream, 2: same + reset, 0: off) */
 int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value);
-/* counters: "kernel_launches" (kernels this library has launched so far), "workspace_bytes" */
+/* counters: "kernel_launches" (kernels this library has launched so far), "workspace_bytes",
+ *           "prof_{us|launches|flops|bytes}_{conv|norm|tail|attn|glue|siren}" (profile mode; synchronises) */
 int64_t tha4_get_counter(const tha4_ctx* ctx, const char* name);
 
 /* Replaces module.load_state_dict(torch_load(file)) (src/tha4/poser/modes/mode_07.py:152-155 and siblings;

@@ -1,0 +1,107 @@
+"""Helpers for the -m gpu tests: thin ctypes wrappers over the kernel-level entry points of the C ABI."""
+import ctypes
+
+import torch
+
+from tha4_b200._lib import Context, _ptr
+
+_ctx = None
+
+
+def ctx() -> Context:
+    global _ctx
+    if _ctx is None:
+        _ctx = Context(torch.device('cuda:0'))
+    return _ctx
+
+
+def dev(t):
+    return t.to('cuda:0').contiguous()
+
+
+def conv(kind, x, w, bias=None, res=None, res_mode=0, in_up=0, strict=1, ksplit=0):
+    c = ctx()
+    N, Cin, H, W = x.shape
+    Cout = w.shape[1] if kind == 2 else w.shape[0]
+    LH, LW = (2 * H, 2 * W) if in_up else (H, W)
+    Ho, Wo = {0: (LH, LW), 1: (LH // 2, LW // 2), 2: (LH * 2, LW * 2), 3: (LH, LW)}[kind]
+    y = torch.empty(N, Cout, Ho, Wo, device='cuda:0')
+    xd, wd = dev(x), dev(w)
+    bd = dev(bias) if bias is not None else None
+    rd = dev(res) if res is not None else None
+    c._call('tha4_test_conv', kind, _ptr(xd), _ptr(wd), _ptr(bd), _ptr(rd), res_mode, in_up, _ptr(y), N, Cin, H, W, Cout,
+            strict, ksplit, c._stream())
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+def norm(x, groups, gamma, beta, film0=None, film1=None, act=0, pool=0):
+    c = ctx()
+    N, C, H, W = x.shape
+    y = torch.empty(N, C, H // 2 if pool else H, W // 2 if pool else W, device='cuda:0')
+    args = [dev(x), dev(gamma), dev(beta), dev(film0) if film0 is not None else None, dev(film1) if film1 is not None else None]
+    c._call('tha4_test_norm', _ptr(args[0]), N, C, H, W, groups, _ptr(args[1]), _ptr(args[2]), _ptr(args[3]), _ptr(args[4]),
+            act, pool, _ptr(y), c._stream())
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+def attention(qkv, heads=8):
+    c = ctx()
+    N, C3 = qkv.shape[0], qkv.shape[1]
+    out = torch.empty(N, C3 // 3, 16, 16, device='cuda:0')
+    q = dev(qkv)
+    c._call('tha4_test_attention', _ptr(q), N, C3 // 3, heads, _ptr(out), c._stream())
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def linear(x, W, b, silu_in):
+    c = ctx()
+    y = torch.empty(x.shape[0], W.shape[0], device='cuda:0')
+    xd, wd, bd = dev(x), dev(W), dev(b)
+    c._call('tha4_test_linear', _ptr(xd), x.shape[0], x.shape[1], _ptr(wd), _ptr(bd), W.shape[0], silu_in, _ptr(y), c._stream())
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+def grid_sample(img, gc, want_taps=True):
+    c = ctx()
+    N, C, H, W = img.shape
+    out = torch.empty(N, C, H, W, device='cuda:0')
+    x0 = torch.empty(N, H, W, dtype=torch.int32, device='cuda:0')
+    y0 = torch.empty_like(x0)
+    tx = torch.empty(N, H, W, device='cuda:0')
+    ty = torch.empty_like(tx)
+    i, g = dev(img), dev(gc)
+    c._call('tha4_grid_sample', _ptr(i), _ptr(g), N, C, H, W, _ptr(out), _ptr(x0), _ptr(y0), _ptr(tx), _ptr(ty), c._stream())
+    torch.cuda.synchronize()
+    return out.cpu(), x0.cpu(), y0.cpu(), tx.cpu(), ty.cpu()
+
+
+def resize(x, ho, wo):
+    c = ctx()
+    N, C, H, W = x.shape
+    out = torch.empty(N, C, ho, wo, device='cuda:0')
+    xd = dev(x)
+    c._call('tha4_resize_bilinear', _ptr(xd), N, C, H, W, ho, wo, _ptr(out), c._stream())
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def oracle_grid_sample(clib, img, gc):
+    N, C, H, W = img.shape
+    out = torch.empty_like(img)
+    x0 = torch.empty(N, H, W, dtype=torch.int32)
+    y0 = torch.empty_like(x0)
+    tx = torch.empty(N, H, W)
+    ty = torch.empty_like(tx)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    img, gc = img.contiguous(), gc.contiguous()
+    clib.tha4o_grid_sample(p(img), p(gc), N, C, H, W, p(out), p(x0), p(y0), p(tx), p(ty))
+    return out, x0, y0, tx, ty
+
+
+def err(a, b):
+    d = (a.double() - b.double()).abs()
+    return d.max().item(), d.mean().item()

@@ -1,0 +1,164 @@
+"""Kernel-level parity on the B200 (-m gpu): every CUDA kernel family against a plain fp32 PyTorch reference of the
+same op (CPU), and the grid_sample / interpolate index math bit-exactly against the C oracle."""
+import ctypes
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import synth, tha4_oracle as O
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------ grid_sample / resize
+@pytest.mark.parametrize('size,amp', [(128, 0.05), (192, 0.3), (256, 1.5), (512, 0.02)])
+def test_grid_sample_bit_exact_vs_c_oracle(oracle_clib, size, amp):
+    n = 2
+    img = synth.synthetic_image(size, n)[:, :, :size, :size].contiguous()
+    gc = torch.randn(n, 2, size, size, generator=_gen(size)) * amp
+    out, x0, y0, tx, ty = G.grid_sample(img, gc)
+    ro, rx0, ry0, rtx, rty = G.oracle_grid_sample(oracle_clib, img, gc)
+    assert torch.equal(x0, rx0) and torch.equal(y0, ry0), 'integer corner indices must be bit-exact'
+    assert torch.equal(tx, rtx) and torch.equal(ty, rty), 'lerp weights must be bit-exact'
+    assert torch.equal(out, ro), 'sampled values follow the same op order as the oracle'
+    ref = O.apply_grid_change(gc, img)
+    assert G.err(out, ref)[0] < 2e-5
+
+
+def test_grid_sample_adversarial_grids(oracle_clib):
+    size, n = 128, 1
+    img = synth.synthetic_image(5, n)[:, :, :size, :size].contiguous()
+    cases = {
+        'zero': torch.zeros(n, 2, size, size),
+        'far_positive': torch.full((n, 2, size, size), 5.0),
+        'far_negative': torch.full((n, 2, size, size), -5.0),
+        'half_pixel': torch.full((n, 2, size, size), 1.0 / size),      # source index lands on .5 boundaries
+        'one_pixel': torch.full((n, 2, size, size), 2.0 / size),       # exact integer shift
+    }
+    for name, gc in cases.items():
+        out, x0, y0, tx, ty = G.grid_sample(img, gc)
+        ro, rx0, ry0, rtx, rty = G.oracle_grid_sample(oracle_clib, img, gc)
+        assert torch.equal(x0, rx0) and torch.equal(y0, ry0) and torch.equal(tx, rtx) and torch.equal(ty, rty), name
+        assert torch.equal(out, ro), name
+        assert G.err(out, O.apply_grid_change(gc, img))[0] < 2e-5, name
+    out = G.grid_sample(img, cases['zero'])[0]
+    assert G.err(out, img)[0] < 1e-5
+    out = G.grid_sample(img, cases['far_positive'])[0]
+    assert torch.equal(out, img[:, :, -1:, -1:].expand_as(out).contiguous())
+
+
+@pytest.mark.parametrize('hi,ho', [(512, 256), (256, 512), (128, 256)])
+def test_resize_bilinear_vs_oracle(oracle_clib, hi, ho):
+    a = torch.rand(2, 4, hi, hi, generator=_gen(hi))
+    out = G.resize(a, ho, ho)
+    ref = torch.empty(2, 4, ho, ho)
+    oracle_clib.tha4o_resize_bilinear(ctypes.c_void_p(a.data_ptr()), 2, 4, hi, hi, ho, ho, ctypes.c_void_p(ref.data_ptr()))
+    assert torch.equal(out, ref)
+    assert G.err(out, F.interpolate(a, size=(ho, ho), mode='bilinear', align_corners=False))[0] < 3e-7
+
+
+# ------------------------------------------------------------------------------------------ convolution
+def _conv_ref(kind, x, w, bias, in_up):
+    if in_up:
+        x = F.interpolate(x, scale_factor=2, mode='nearest')
+    if kind == 0:
+        return F.conv2d(x, w, bias, 1, 1)
+    if kind == 1:
+        return F.conv2d(x, w, bias, 2, 1)
+    if kind == 2:
+        return F.conv_transpose2d(x, w, bias, 2, 1)
+    return F.conv2d(x, w, bias)
+
+
+CONV_CASES = [
+    # kind, N, Cin, H, Cout, bias, res_mode, in_up, ksplit
+    (0, 2, 4, 32, 64, False, 0, 0, 0),
+    (0, 1, 8, 48, 64, False, 0, 0, 0),
+    (0, 2, 64, 32, 64, True, 1, 0, 0),
+    (0, 1, 96, 32, 32, True, 0, 0, 0),
+    (0, 1, 524, 16, 512, False, 0, 0, 0),        # pose-concat bottleneck (Cin padded to 544), auto split-K
+    (0, 1, 540, 24, 512, False, 0, 0, 3),
+    (0, 2, 128, 16, 128, True, 2, 1, 0),         # up-sampling ResBlock: nearest x2 gather + upsampled residual
+    (0, 2, 128, 16, 128, True, 3, 0, 0),         # down-sampling ResBlock residual: 2x2 mean
+    (0, 1, 16, 64, 32, True, 0, 0, 0),
+    (1, 2, 64, 64, 128, False, 0, 0, 0),
+    (1, 1, 256, 32, 512, False, 0, 0, 0),
+    (2, 1, 512, 16, 256, False, 0, 0, 0),
+    (2, 2, 128, 24, 64, False, 0, 0, 0),
+    (3, 2, 256, 16, 768, True, 0, 0, 0),
+    (3, 1, 384, 32, 128, True, 1, 0, 0),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('strict', [1, 0])
+def test_conv_vs_torch(case, strict):
+    kind, N, Cin, H, Cout, has_bias, res_mode, in_up, ksplit = case
+    g = _gen(hash(case) % 10000)
+    k = {0: 3, 1: 4, 2: 4, 3: 1}[kind]
+    x = torch.randn(N, Cin, H, H, generator=g)
+    wshape = (Cin, Cout, k, k) if kind == 2 else (Cout, Cin, k, k)
+    w = torch.randn(wshape, generator=g) / math.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, generator=g) if has_bias else None
+    ref = _conv_ref(kind, x, w, bias, in_up)
+    res = None
+    if res_mode:
+        Ho = ref.shape[2]
+        rh = {1: Ho, 2: Ho // 2, 3: Ho * 2}[res_mode]
+        res = torch.randn(N, Cout, rh, rh, generator=g)
+        ref = ref + {1: res, 2: F.interpolate(res, scale_factor=2, mode='nearest'), 3: F.avg_pool2d(res, 2, 2)}[res_mode]
+    out = G.conv(kind, x, w, bias, res, res_mode, in_up, strict, ksplit)
+    mx, mean = G.err(out, ref)
+    tol = 2e-5 if strict else 6e-3          # 3xTF32 == fp32; single TF32: 2^-11 relative per product
+    assert mx < tol * max(1.0, ref.abs().max().item()), (case, strict, mx, mean)
+
+
+# ------------------------------------------------------------------------------------------ normalisation
+@pytest.mark.parametrize('C,H', [(64, 48), (512, 16), (128, 24)])
+def test_instance_norm_relu(C, H):
+    g = _gen(C + H)
+    x = torch.randn(2, C, H, H, generator=g) * 3 + 1
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.relu(F.instance_norm(x, weight=gamma, bias=beta, eps=1e-5))
+    assert G.err(G.norm(x, 0, gamma, beta, act=1), ref)[0] < 2e-5
+
+
+@pytest.mark.parametrize('C,H,pool', [(32, 64, 0), (96, 32, 0), (192, 16, 1), (384, 16, 0), (512, 16, 1)])
+def test_group_norm_film_silu_pool(C, H, pool):
+    g = _gen(C * 7 + H)
+    x = torch.randn(2, C, H, H, generator=g) * 2 - 0.5
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    f0, f1 = torch.randn(2 * C, generator=g) * 0.3, torch.randn(2, 2 * C, generator=g) * 0.3
+    h = F.group_norm(x, 32, gamma, beta, eps=1e-5)
+    h = O._scaleshift(h, f0.unsqueeze(0).expand(2, -1))
+    h = O._scaleshift(h, f1)
+    ref = F.silu(h)
+    if pool:
+        ref = F.avg_pool2d(ref, 2, 2)
+    assert G.err(G.norm(x, 32, gamma, beta, f0, f1, act=2, pool=pool), ref)[0] < 5e-5
+
+
+def test_attention_vs_reference():
+    g = _gen(11)
+    qkv = torch.randn(2, 768, 16, 16, generator=g)
+    b, c, L, heads = 2, 256, 256, 8
+    q, k, v = qkv.reshape(b, 3 * c, L).chunk(3, dim=1)
+    scale = 1.0 / math.sqrt(math.sqrt(c // heads))
+    w = torch.einsum('bct,bcs->bts', (q * scale).reshape(b * heads, c // heads, L), (k * scale).reshape(b * heads, c // heads, L))
+    w = torch.softmax(w, dim=-1)
+    ref = torch.einsum('bts,bcs->bct', w, v.reshape(b * heads, c // heads, L)).reshape(b, c, 16, 16)
+    assert G.err(G.attention(qkv), ref)[0] < 2e-5
+
+
+def test_linear_silu():
+    g = _gen(3)
+    x, W, b = torch.randn(3, 256, generator=g), torch.randn(640, 256, generator=g) / 16, torch.randn(640, generator=g)
+    assert G.err(G.linear(x, W, b, 1), F.linear(F.silu(x), W, b))[0] < 2e-5
+    assert G.err(G.linear(x[:, :6].contiguous(), W[:, :6].contiguous(), b, 0), F.linear(x[:, :6], W[:, :6], b))[0] < 1e-5

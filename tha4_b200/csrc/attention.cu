@@ -2,6 +2,7 @@
 // One CTA per (sample, head); K and V of the head live in shared memory (64 KB), each thread owns one query row
 // and runs an online softmax over the 256 keys.  0.4 GFLOP per network: latency-, not throughput-critical.
 #include "ops.cuh"
+#include "profiler.cuh"
 
 namespace tha4 {
 namespace {
@@ -76,6 +77,7 @@ void attention_forward(const View& qkv, int heads, const View& out, cudaStream_t
         THA4_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    ProfScope prof(PROF_ATTN, s);
     attention_kernel<<<qkv.N * heads, L, smem, s>>>(qkv.p, qkv.ld, out.C, heads, out.p, out.ld);
     THA4_LAUNCH_CHECK();
 }

@@ -2,6 +2,7 @@
 #include "../../include/tha4_b200.h"
 #include "nets.cuh"
 #include "siren.cuh"
+#include "profiler.cuh"
 #include <atomic>
 #include <cstring>
 
@@ -170,6 +171,7 @@ const char* tha4_last_error(const tha4_ctx* ctx) { return ctx ? ctx->err.c_str()
 int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
     return guarded(ctx, [&] {
         if (!strcmp(name, "strict")) ctx->strict = value ? 1 : 0;
+        else if (!strcmp(name, "profile")) { prof_enable(value != 0); if (value == 2) prof_reset(); }
         else if (!strcmp(name, "microbatch")) { THA4_REQUIRE(value >= 1 && value <= 1024, "microbatch range"); ctx->microbatch = (int)value; }
         else throw std::runtime_error(std::string("tha4: unknown option ") + name);
     });
@@ -177,6 +179,16 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
 
 int64_t tha4_get_counter(const tha4_ctx* ctx, const char* name) {
     if (!strcmp(name, "kernel_launches")) return g_kernel_launches.load();
+    {   // "prof_<what>_<cat>": what in us|launches|flops|bytes, cat in conv|norm|tail|attn|glue|siren
+        static const char* cats[] = {"conv", "norm", "tail", "attn", "glue", "siren"};
+        static const char* whats[] = {"us", "launches", "flops", "bytes"};
+        if (!strncmp(name, "prof_", 5))
+            for (int w = 0; w < 4; ++w)
+                for (int c = 0; c < 6; ++c)
+                    if (std::string(name) == std::string("prof_") + whats[w] + "_" + cats[c]) {
+                        try { return (int64_t)prof_read(c, w); } catch (...) { return -1; }
+                    }
+    }
     if (ctx && !strcmp(name, "workspace_bytes")) return (int64_t)(ctx->persist.bytes() + ctx->scratch.bytes());
     return -1;
 }

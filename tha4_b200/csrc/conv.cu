@@ -6,6 +6,7 @@
 // cp.async ring feeds mma.sync.m16n8k8.tf32.  `strict` switches to 3xTF32 error-compensated products, which
 // reproduces fp32 convolution to ~1e-6 relative and is what the tight parity tests use.
 #include "conv.cuh"
+#include "profiler.cuh"
 
 namespace tha4 {
 
@@ -398,6 +399,8 @@ void conv_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
                                           a.out.pixels(), s));
     }
     dim3 grid(tiles_m, tiles_n, cw.nphase * ksplit);
+    ProfScope prof(PROF_CONV, s);
+    prof_add_work(PROF_CONV, 2.0 * (double)p.M_total * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
     if (bn == 128) launch_conv<128, 2, 4, 3>(p, grid, s);
     else if (bn == 64) launch_conv<64, 4, 2, 4>(p, grid, s);
     else launch_conv<32, 8, 1, 4>(p, grid, s);

@@ -1,6 +1,7 @@
 // InstanceNorm2d / GroupNorm32 (+FiLM, +activation, +2x2 mean pool, +residual) on NHWC fp32 activations.
 // Three small HBM-bound kernels: per-(n,c) sum / sum-of-squares -> per-(n,c) affine -> elementwise apply.
 #include "ops.cuh"
+#include "profiler.cuh"
 
 namespace tha4 {
 namespace {
@@ -122,6 +123,8 @@ void norm_stats(const View& x, double* sums, cudaStream_t s) {
     const int cq = x.C / 4, PL = 256 / cq;
     const int HW = x.H * x.W;
     dim3 grid(ceil_div(HW, PL * STAT_PIX_PER_THREAD), x.N);
+    ProfScope prof(PROF_NORM, s);
+    prof_add_work(PROF_NORM, 0.0, (double)x.pixels() * x.C * 4);
     norm_stats_kernel<<<grid, 256, 0, s>>>(x.p, HW, x.C, x.ld, sums);
     THA4_LAUNCH_CHECK();
 }
@@ -140,6 +143,8 @@ void norm_apply(const View& x, const float* coef, int act, int pool, const View*
     if (res) THA4_REQUIRE(res->H == y.H && res->W == y.W && res->C == y.C && res->ld % 4 == 0, "norm_apply: res dims");
     const long total = (long)y.N * y.H * y.W * (y.C / 4);
     const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    ProfScope prof(PROF_NORM, s);
+    prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() + y.pixels() + (res ? y.pixels() : 0)) * x.C * 4);
     norm_apply_kernel<<<blocks, 256, 0, s>>>(x.p, x.H, x.W, x.ld, coef, act, pool, res ? res->p : nullptr,
                                              res ? res->ld : 0, y.p, y.H, y.W, y.ld, x.C, total);
     THA4_LAUNCH_CHECK();

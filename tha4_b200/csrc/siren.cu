@@ -12,6 +12,7 @@
 #include "siren.cuh"
 #include "gridsample.cuh"
 #include <cuda_fp16.h>
+#include "profiler.cuh"
 
 namespace tha4 {
 namespace {
@@ -496,6 +497,7 @@ void SirenFaceNet::forward(Runtime& rt, const float* pose, int pose_ld, int B, f
     using SM = Smem<128, 128, 3>;
     static bool cfg = false;
     if (!cfg) { set_smem(siren_face_kernel, SM::bytes); cfg = true; }
+    ProfScope prof(PROF_SIREN, rt.stream);
     siren_face_kernel<<<B * R * (R / TP), NTHREADS, SM::bytes, rt.stream>>>(L, layers_[0].NPAD, base_grid_table(R), R, out);
     THA4_LAUNCH_CHECK();
 }
@@ -537,6 +539,7 @@ void SirenBodyNet::forward(Runtime& rt, const ImgView& image, const float* pose,
         set_smem(siren_body_l2_kernel, SM2::bytes);
         cfg = true;
     }
+    ProfScope prof(PROF_SIREN, s);
     siren_body_l0_kernel<<<B * 128 * (128 / TP), NTHREADS, SM0::bytes, s>>>(lw(l_[0][0], pb0), lw(l_[0][1]), lw(l_[0][2]), 384,
                                                                           base_grid_table(128), 128, f0);
     THA4_LAUNCH_CHECK();

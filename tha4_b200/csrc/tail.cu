@@ -9,6 +9,7 @@
 // v1: CUDA-core FFMA head conv from a shared-memory halo tile (16x16 output pixels per CTA).
 #include "ops.cuh"
 #include "gridsample.cuh"
+#include "profiler.cuh"
 
 namespace tha4 {
 namespace {
@@ -176,6 +177,12 @@ void launch_tail(const TailWeights& tw, const View& f, const float* coef, int ac
     float* op[8];
     for (int i = 0; i < 8; ++i) op[i] = i < nout ? o[i] : nullptr;
     dim3 grid(f.W / TILE, f.H / TILE, f.N);
+    ProfScope prof(PROF_TAIL, s);
+    {   // compulsory traffic: feature map + 4-channel image(s) read once, every returned tensor written once
+        const int out_ch[4] = {15, 18, 24, 24};
+        const int img_ch = (KIND == TAIL_COMBINER) ? 8 : 4;
+        prof_add_work(PROF_TAIL, 2.0 * f.pixels() * 9 * tw.C * tw.CO, (double)f.pixels() * (f.C + img_ch + out_ch[KIND]) * 4);
+    }
     tail_kernel<KIND><<<grid, 256, smem, s>>>(f.p, f.H, f.C, f.ld, coef, act, tw.w, tw.bias, i0, i1,
                                              base_grid_table(f.H), op[0], op[1], op[2], op[3], op[4], op[5], op[6], op[7]);
     THA4_LAUNCH_CHECK();
