@@ -98,8 +98,12 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize('case', CONV_CASES)
-@pytest.mark.parametrize('strict', [1, 0])
-def test_conv_vs_torch(case, strict):
+@pytest.mark.parametrize('path', ['strict_mma', 'tf32_tcgen05', 'tf32_mma'])
+def test_conv_vs_torch(case, path):
+    """strict_mma: 3xTF32 mma.sync (== fp32); tf32_tcgen05: TMA + tcgen05.mma kind::tf32 where the configuration is
+    supported (stride-1 taps, no fused upsample), else mma.sync; tf32_mma: single-TF32 mma.sync everywhere."""
+    strict = 1 if path == 'strict_mma' else 0
+    G.ctx().set_option('tcgen05', 0 if path == 'tf32_mma' else 1)
     kind, N, Cin, H, Cout, has_bias, res_mode, in_up, ksplit = case
     g = _gen(hash(case) % 10000)
     k = {0: 3, 1: 4, 2: 4, 3: 1}[kind]
@@ -117,7 +121,8 @@ def test_conv_vs_torch(case, strict):
     out = G.conv(kind, x, w, bias, res, res_mode, in_up, strict, ksplit)
     mx, mean = G.err(out, ref)
     tol = 2e-5 if strict else 6e-3          # 3xTF32 == fp32; single TF32: 2^-11 relative per product
-    assert mx < tol * max(1.0, ref.abs().max().item()), (case, strict, mx, mean)
+    G.ctx().set_option('tcgen05', 1)
+    assert mx < tol * max(1.0, ref.abs().max().item()), (case, path, mx, mean)
 
 
 # ------------------------------------------------------------------------------------------ normalisation

@@ -5,6 +5,7 @@ raw pointers together with torch's current CUDA stream.
 """
 import ctypes
 import os
+import weakref
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -87,6 +88,7 @@ class Context:
             raise Tha4Error('tha4_ctx_create failed: %s' % self.lib.tha4_last_error(None).decode())
         self.handle = handle
         self.loaded: Dict[str, object] = {}
+        self.modules = weakref.WeakSet()     # NativeModules whose weights live in this context
 
     def __del__(self):
         try:
@@ -107,6 +109,9 @@ class Context:
 
     def set_option(self, name: str, value: int):
         self._call('tha4_set_option', name.encode(), int(value))
+        if name == 'strict':      # weight packing depends on it (TF32-rounded vs exact fp32): re-upload lazily
+            for m in list(self.modules):
+                m._uploaded_key = None
 
     def counter(self, name: str) -> int:
         return int(self.lib.tha4_get_counter(self.handle, name.encode()))

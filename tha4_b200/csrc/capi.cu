@@ -170,7 +170,8 @@ const char* tha4_last_error(const tha4_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
     return guarded(ctx, [&] {
-        if (!strcmp(name, "strict")) ctx->strict = value ? 1 : 0;
+        if (!strcmp(name, "strict")) { ctx->strict = value ? 1 : 0; }
+        else if (!strcmp(name, "tcgen05")) conv_enable_tc(value != 0);
         else if (!strcmp(name, "profile")) { prof_enable(value != 0); if (value == 2) prof_reset(); }
         else if (!strcmp(name, "microbatch")) { THA4_REQUIRE(value >= 1 && value <= 1024, "microbatch range"); ctx->microbatch = (int)value; }
         else throw std::runtime_error(std::string("tha4: unknown option ") + name);
@@ -198,6 +199,7 @@ int tha4_load_net(tha4_ctx* ctx, int net, int n_tensors, const char* const* keys
     return guarded(ctx, [&] {
         StateDict sd = make_sd(n_tensors, keys, dev_ptrs, shapes, ndims);
         cudaStream_t s = (cudaStream_t)stream;
+        conv_set_pack_rounding(!ctx->strict);     // non-strict: weights are rounded to TF32 once, at pack time
         switch (net) {
             case THA4_NET_EYEBROW_DECOMPOSER: ctx->decomposer.reset(new EncDecNet(TAIL_DECOMPOSER, 128, 4, 0)); ctx->decomposer->load(sd, s); break;
             case THA4_NET_EYEBROW_MORPHING_COMBINER: ctx->combiner.reset(new EncDecNet(TAIL_COMBINER, 128, 8, 12)); ctx->combiner->load(sd, s); break;
@@ -365,6 +367,8 @@ int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, cons
         const int cin_k = round_up(Cin, 4);
         ConvWeights cw;
         conv_describe(cw, (ConvKind)kind, cin_k, Cout);
+        conv_set_pack_rounding(!strict);
+        cw.tf32_rounded = !strict;
         cw.w = P->alloc(conv_packed_floats(cw));
         THA4_CUDA_CHECK(cudaMemsetAsync(cw.w, 0, conv_packed_floats(cw) * sizeof(float), s));
         conv_pack(cw, (ConvKind)kind, w, Cin, 0, s);

@@ -67,6 +67,13 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == ACT_SILU) return v / (1.0f + expf(-v));
     return v;
 }
+// round-to-nearest TF32 (10-bit mantissa) as the tensor cores would ideally see it; tcgen05 kind::tf32 truncates the
+// low mantissa bits of what it reads, so producers of conv operands round once when they write (non-strict mode).
+__device__ __forceinline__ float round_tf32(float v) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
 
 }  // namespace tha4

@@ -274,7 +274,7 @@ void launch_conv(const ConvKernelParams& p, dim3 grid, cudaStream_t s) {
 
 // ---- weight packing -------------------------------------------------------------------------------------
 __global__ void conv_pack_kernel(float* dst, const float* src, int kind, int w_cin, int cin_offset, int cout,
-                                 int cin_pad, int cout_pad, int ntaps, int nphase) {
+                                 int cin_pad, int cout_pad, int ntaps, int nphase, int round_w) {
     long total = (long)nphase * ntaps * cout * w_cin;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         int ci = (int)(i % w_cin);
@@ -295,7 +295,7 @@ __global__ void conv_pack_kernel(float* dst, const float* src, int kind, int w_c
             int kx = (px == 0) ? (tx == 0 ? 1 : 3) : (tx == 0 ? 0 : 2);
             v = src[(((long)ci * cout + co) * 4 + ky) * 4 + kx];
         }
-        dst[(((long)ph * ntaps + tap) * cout_pad + co) * cin_pad + cin_offset + ci] = v;
+        dst[(((long)ph * ntaps + tap) * cout_pad + co) * cin_pad + cin_offset + ci] = round_w ? round_tf32(v) : v;
     }
 }
 
@@ -334,6 +334,10 @@ void conv_describe(ConvWeights& cw, ConvKind kind, int cin, int cout) {
     }
 }
 
+static bool g_pack_round = true;
+void conv_set_pack_rounding(bool r) { g_pack_round = r; }
+bool conv_pack_rounding() { return g_pack_round; }
+
 size_t conv_packed_floats(const ConvWeights& cw) {
     return (size_t)cw.nphase * cw.ntaps * cw.cout_pad * cw.cin_pad;
 }
@@ -343,11 +347,20 @@ void conv_pack(const ConvWeights& cw, ConvKind kind, const float* w_ref, int w_c
     long total = (long)cw.nphase * cw.ntaps * cw.cout * w_cin;
     int blocks = (int)std::min<long>(4096, (total + 255) / 256);
     conv_pack_kernel<<<blocks, 256, 0, s>>>(cw.w, w_ref, (int)kind, w_cin, cin_offset, cw.cout, cw.cin_pad,
-                                           cw.cout_pad, cw.ntaps, cw.nphase);
+                                           cw.cout_pad, cw.ntaps, cw.nphase, g_pack_round ? 1 : 0);
     THA4_LAUNCH_CHECK();
 }
 
+static bool g_use_tc = true;
+void conv_enable_tc(bool on) { g_use_tc = on; }
+
 void conv_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
+    if (g_use_tc && conv_tc_supported(cw, a)) conv_tc_forward(cw, a, s);
+    else conv_mma_forward(cw, a, s);
+}
+
+void conv_mma_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
+    THA4_REQUIRE(!(a.strict && cw.tf32_rounded), "strict mode needs weights packed without TF32 rounding: set the option before loading");
     ConvKernelParams p{};
     THA4_REQUIRE(a.in.C == cw.cin, "conv: input channels");
     THA4_REQUIRE(a.out.C == cw.cout, "conv: output channels");

@@ -20,6 +20,7 @@ struct ConvWeights {
     float* bias = nullptr;      // [cout] or nullptr
     int cin = 0, cout = 0, cin_pad = 0, cout_pad = 0;
     int ntaps = 0, nphase = 1;
+    bool tf32_rounded = false;  // weights were rounded to TF32 at pack time (non-strict contexts)
     int stride = 1;             // input stride
     int out_mul = 1;            // output coordinate = m * out_mul + phase offset (2 for the transposed conv)
     signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
@@ -37,6 +38,8 @@ void conv_describe(ConvWeights& cw, ConvKind kind, int cin, int cout);
 // weights share one packed tensor along Cin (Upscaler02's first_conv + coarse_image_conv).
 size_t conv_packed_floats(const ConvWeights& cw);
 void conv_pack(const ConvWeights& cw, ConvKind kind, const float* w_ref, int w_cin, int cin_offset, cudaStream_t s);
+void conv_set_pack_rounding(bool round_tf32);   // applies to subsequent conv_pack calls (set from the context's strict option)
+bool conv_pack_rounding();
 
 struct ConvArgs {
     View in;                    // stored input (if in_up: stored at half the logical resolution)
@@ -49,6 +52,11 @@ struct ConvArgs {
 };
 
 // out = conv(in) + bias (+ res).  When the launch splits K, `out` is zeroed first on the same stream.
+// Dispatches to the tcgen05 kernel (conv_tc.cu) when it supports the configuration, else to the mma.sync kernel.
 void conv_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);
+void conv_mma_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);     // conv.cu (general shapes, strict mode)
+bool conv_tc_supported(const ConvWeights& cw, const ConvArgs& a);
+void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);      // conv_tc.cu (tcgen05 + TMA + TMEM)
+void conv_enable_tc(bool on);                                                        // default: on
 
 }  // namespace tha4

@@ -1,0 +1,363 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores: TMA-staged operands, tcgen05.mma (kind::tf32)
+// with the accumulator in TMEM, warp-specialised producer / MMA-issuer / epilogue roles.
+//
+// GEMM view per CTA: D[128 pixels x BN couts] += A[128 x 32] * B[BN x 32]^T per k-block, k-blocks = taps x (Cin/32).
+//  * A (activations, NHWC fp32): one 4-D TMA box {32 ch, 16 w, 8 h, 1 n} per (tap, channel chunk).  The box lands in
+//    shared memory as 128 rows x 128 bytes with the 128-byte swizzle, which is exactly the canonical K-major UMMA
+//    layout; the tap offset (dy,dx) is just a shift of the box origin, and TMA's out-of-bounds zero fill *is* the
+//    convolution's zero padding (and the channel / edge-tile padding).  No im2col buffer, no index arithmetic.
+//  * B (weights, packed [phase*tap][cout_pad][cin_pad]): 3-D TMA box {32 cin, BN cout, 1 tap}, same layout.
+//  * D: fp32 accumulator in tensor memory (BN columns x 128 lanes), drained by 4 epilogue warps with tcgen05.ld,
+//    bias / residual fused, NHWC stores (atomic accumulation when K is split across CTAs).
+// Handles every stride-1 tap table of conv.cuh (3x3, 1x1, the four phases of the transposed 4x4); the stride-2 conv
+// and the nearest-upsample-fused gather stay on the mma.sync kernel in conv.cu.
+#include "conv.cuh"
+#include "profiler.cuh"
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+namespace tha4 {
+namespace {
+
+constexpr int TILE_W = 16, TILE_H = 8;          // 128 output pixels per CTA
+constexpr int KCH = 32;                          // channels per k-block (128 bytes of fp32 = one swizzle row)
+constexpr int A_BYTES = 128 * KCH * 4;           // 16 KB
+constexpr int TC_THREADS = 192;                  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+struct TcParams {
+    float* out; int outH, outW, outC, out_ld;
+    const float* bias;
+    const float* res; int resH, resW, res_ld, res_mode;
+    int N, MH, MW, tiles_x, tiles_y;
+    int ntaps, cpt, ksplit, out_mul;
+    signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
+    signed char dx[CONV_MAX_PHASES][CONV_MAX_TAPS];
+    signed char ph_oy[CONV_MAX_PHASES], ph_ox[CONV_MAX_PHASES];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s watchdog: fail loudly instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    constexpr int B_BYTES = BN * KCH * 4;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * B_BYTES);   // full[STAGES], empty[STAGES], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y;
+    const int n = tile / p.tiles_y;
+    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+    const int n0 = blockIdx.y * BN;
+    const int phase = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
+    const int KT = p.ntaps * p.cpt;
+    const int k_per = (KT + p.ksplit - 1) / p.ksplit;
+    const int kb = split * k_per;
+    const int nk = max(0, min(KT, kb + k_per) - kb);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STAGES + s), 1); }
+        mbar_init(smem_u32(bars + 2 * STAGES), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (nk > 0) {
+        if (warp == 0) {
+            if (lane == 0) {   // ===== TMA producer =====
+                for (int i = 0; i < nk; ++i) {
+                    const int s = i % STAGES;
+                    mbar_wait(smem_u32(bars + STAGES + s), ((i / STAGES) & 1) ^ 1);
+                    const uint32_t full = smem_u32(bars + s);
+                    mbar_expect_tx(full, A_BYTES + B_BYTES);
+                    const int kt = kb + i;
+                    const int tap = kt / p.cpt;
+                    const int c0 = (kt - tap * p.cpt) * KCH;
+                    tma_load_4d(smem_u32(smA + s * A_BYTES), &tmA, c0, x0 + p.dx[phase][tap], y0 + p.dy[phase][tap], n, full);
+                    tma_load_3d(smem_u32(smB + s * B_BYTES), &tmB, c0, n0, phase * p.ntaps + tap, full);
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {   // ===== MMA issuer (single thread) =====
+                // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
+                constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+                for (int i = 0; i < nk; ++i) {
+                    const int s = i % STAGES;
+                    mbar_wait(smem_u32(bars + s), (i / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint64_t adesc = make_smem_desc(smem_u32(smA + s * A_BYTES));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smB + s * B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < KCH / 8; ++k)     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (>>4)
+                        umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(smem_u32(bars + STAGES + s));          // frees the smem slot when these MMAs retire
+                }
+                umma_commit(smem_u32(bars + 2 * STAGES));              // accumulator complete -> epilogue
+            }
+        } else {               // ===== epilogue warps: TMEM -> registers -> global =====
+            const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
+            mbar_wait(smem_u32(bars + 2 * STAGES), 0);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const int row = q * 32 + lane;
+            const int my = y0 + row / TILE_W, mx = x0 + row % TILE_W;
+            const bool valid = my < p.MH && mx < p.MW;
+            const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
+            float* orow = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld;
+            const bool lead = (split == 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                if (!valid) continue;
+                const int cbase = n0 + c0;
+                if (cbase >= p.outC) continue;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                const int cn = min(32, p.outC - cbase);
+                if (lead) {
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
+                    }
+                    if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
+                        const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
+                        const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + cbase;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += rr[j];
+                    } else if (p.res_mode == RES_DOWN2) {
+                        const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + cbase;
+                        const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < cn) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+                    }
+                }
+                if (p.ksplit > 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j < cn) atomicAdd(orow + cbase + j, v[j]);
+                } else if (cn == 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(orow + cbase + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j < cn) orow[cbase + j] = v[j];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        THA4_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q));
+        THA4_REQUIRE(ptr != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled unavailable");
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+using MapKey = std::tuple<const void*, long, long, long, long, long, int>;
+std::map<MapKey, CUtensorMap> g_maps;
+
+const CUtensorMap& activation_map(const View& v) {
+    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -1};
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) return it->second;
+    CUtensorMap m;
+    cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+    cuuint64_t strides[3] = {(cuuint64_t)v.ld * 4, (cuuint64_t)v.W * v.ld * 4, (cuuint64_t)v.H * v.W * v.ld * 4};
+    cuuint32_t box[4] = {KCH, TILE_W, TILE_H, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    THA4_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+    return g_maps.emplace(key, m).first->second;
+}
+
+const CUtensorMap& weight_map(const ConvWeights& cw, int bn) {
+    MapKey key{cw.w, cw.cin_pad, cw.cout_pad, cw.ntaps, cw.nphase, 0, bn};
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) return it->second;
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)cw.cin_pad, (cuuint64_t)cw.cout_pad, (cuuint64_t)cw.ntaps * cw.nphase};
+    cuuint64_t strides[2] = {(cuuint64_t)cw.cin_pad * 4, (cuuint64_t)cw.cout_pad * cw.cin_pad * 4};
+    cuuint32_t box[3] = {KCH, (cuuint32_t)bn, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, cw.w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    THA4_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+    return g_maps.emplace(key, m).first->second;
+}
+
+template <int BN, int STAGES>
+void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
+    constexpr size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BN * KCH * 4) + (2 * STAGES + 1) * 8 + 16;
+    static bool configured = false;
+    if (!configured) {
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
+    THA4_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvWeights& cw, const ConvArgs& a) {
+    if (a.in_up || cw.stride != 1 || a.strict) return false;
+    if (a.in.ld % 4 != 0 || (((uintptr_t)a.in.p) & 15) != 0) return false;
+    if (a.out.ld % 4 != 0 || (((uintptr_t)a.out.p) & 15) != 0) return false;
+    if (cw.cout_pad % 32 != 0) return false;
+    return true;
+}
+
+void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
+    THA4_REQUIRE(conv_tc_supported(cw, a), "conv_tc: unsupported configuration");
+    THA4_REQUIRE(a.in.C == cw.cin && a.out.C == cw.cout && a.in.N == a.out.N, "conv_tc: shapes");
+    TcParams p{};
+    p.out = a.out.p; p.outH = a.out.H; p.outW = a.out.W; p.outC = a.out.C; p.out_ld = a.out.ld;
+    p.bias = cw.bias;
+    p.res = a.res.p; p.res_mode = a.res.p ? a.res_mode : RES_NONE;
+    p.resH = a.res.H; p.resW = a.res.W; p.res_ld = a.res.ld;
+    p.N = a.in.N;
+    p.out_mul = cw.out_mul;
+    p.MH = a.out.H / cw.out_mul; p.MW = a.out.W / cw.out_mul;
+    THA4_REQUIRE(p.MH == a.in.H && p.MW == a.in.W, "conv_tc: geometry");
+    p.tiles_x = ceil_div(p.MW, TILE_W); p.tiles_y = ceil_div(p.MH, TILE_H);
+    p.ntaps = cw.ntaps; p.cpt = cw.cin_pad / KCH;
+    for (int ph = 0; ph < CONV_MAX_PHASES; ++ph) {
+        p.ph_oy[ph] = cw.ph_oy[ph]; p.ph_ox[ph] = cw.ph_ox[ph];
+        for (int t = 0; t < CONV_MAX_TAPS; ++t) { p.dy[ph][t] = cw.dy[ph][t]; p.dx[ph][t] = cw.dx[ph][t]; }
+    }
+    const int bn = (cw.cout_pad % 256 == 0) ? 256 : (cw.cout_pad % 128 == 0 ? 128 : (cw.cout_pad % 64 == 0 ? 64 : 32));
+    const int tiles_m = p.tiles_x * p.tiles_y * p.N;
+    const int tiles_n = cw.cout_pad / bn;
+    const int KT = cw.ntaps * p.cpt;
+    int ksplit = a.ksplit;
+    if (ksplit <= 0) {
+        const long ctas = (long)tiles_m * tiles_n * cw.nphase;
+        ksplit = 1;
+        if (ctas < 120) {
+            ksplit = (int)((148 + ctas - 1) / ctas);
+            ksplit = std::min(ksplit, std::max(1, KT / 4));
+            ksplit = std::min(ksplit, 32);
+        }
+    }
+    ksplit = std::max(1, std::min(ksplit, KT));
+    p.ksplit = ksplit;
+    ProfScope prof(PROF_CONV, s);
+    prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
+    if (ksplit > 1)
+        THA4_CUDA_CHECK(cudaMemset2DAsync(a.out.p, (size_t)a.out.ld * sizeof(float), 0, (size_t)a.out.C * sizeof(float), a.out.pixels(), s));
+    const CUtensorMap& ma = activation_map(a.in);
+    const CUtensorMap& mb = weight_map(cw, bn);
+    dim3 grid(tiles_m, tiles_n, cw.nphase * ksplit);
+    static int stages_mode = -1;     // experiment knob: THA4_TC_STAGES=deep|mid|shallow
+    if (stages_mode < 0) {
+        const char* e = getenv("THA4_TC_STAGES");
+        stages_mode = (e && !strcmp(e, "deep")) ? 0 : ((e && !strcmp(e, "shallow")) ? 2 : 1);
+    }
+    if (stages_mode == 0) {
+        if (bn == 256) launch_tc<256, 4>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<128, 6>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<64, 8>(ma, mb, p, grid, s);
+        else launch_tc<32, 8>(ma, mb, p, grid, s);
+    } else if (stages_mode == 1) {
+        if (bn == 256) launch_tc<256, 2>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<128, 3>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<64, 4>(ma, mb, p, grid, s);
+        else launch_tc<32, 5>(ma, mb, p, grid, s);
+    } else {
+        if (bn == 256) launch_tc<256, 2>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<128, 2>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<64, 2>(ma, mb, p, grid, s);
+        else launch_tc<32, 3>(ma, mb, p, grid, s);
+    }
+}
+
+}  // namespace tha4

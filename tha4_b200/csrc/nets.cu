@@ -69,6 +69,7 @@ ConvWeights load_conv(const StateDict& sd, const std::string& prefix, ConvKind k
     cw.w = dev_alloc(conv_packed_floats(cw));
     THA4_CUDA_CHECK(cudaMemsetAsync(cw.w, 0, conv_packed_floats(cw) * sizeof(float), s));
     conv_pack(cw, kind, w.p, cin, 0, s);
+    cw.tf32_rounded = conv_pack_rounding();
     if (bias) cw.bias = dev_clone(sd_get(sd, prefix + ".bias"), s);
     return cw;
 }
@@ -206,7 +207,7 @@ void EncDecNet::forward(Runtime& rt, const ImgView& image0, const ImgView& image
         run_conv(rt, cw, in, raw);
         float* coef = norm_coef(rt, raw, nw, 0, nullptr, nullptr, 0);
         const View& y = dst ? *dst : raw;
-        norm_apply(raw, coef, ACT_RELU, 0, nullptr, y, s);
+        norm_apply(raw, coef, ACT_RELU, 0, nullptr, y, s, !rt.strict);
         return y;
     };
     View f = conv_in_relu(down_[0], down_n_[0], x0, S_, nullptr);
@@ -223,7 +224,7 @@ void EncDecNet::forward(Runtime& rt, const ImgView& image0, const ImgView& image
         View raw = make_view(P, B, b, b, 512);
         run_conv(rt, res_[i][1], h, raw);
         float* coef = norm_coef(rt, raw, res_n_[i][1], 0, nullptr, nullptr, 0);
-        norm_apply(raw, coef, ACT_NONE, 0, &x, raw, s);
+        norm_apply(raw, coef, ACT_NONE, 0, &x, raw, s, !rt.strict);
         x = raw;
     }
     x = conv_in_relu(up_[0], up_n_[0], x, b * 2, nullptr);
@@ -280,6 +281,7 @@ void UNetNet::load(const StateDict& sd, cudaStream_t s) {
         THA4_CUDA_CHECK(cudaMemsetAsync(first_.w, 0, conv_packed_floats(first_) * sizeof(float), s));
         conv_pack(first_, CONV_3x3, w1.p, 4, 0, s);
         conv_pack(first_, CONV_3x3, w2.p, 10, 4, s);
+        first_.tf32_rounded = conv_pack_rounding();
         first_.bias = dev_alloc(first_.cout);
         vec_add_kernel<<<ceil_div(first_.cout, 128), 128, 0, s>>>(first_.bias, sd_get(sd, p + "first_conv.bias").p,
                                                                   sd_get(sd, "coarse_image_conv.bias").p, first_.cout);
@@ -368,12 +370,12 @@ void UNetNet::res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode
     float* coef0 = norm_coef(rt, x, w.norm0, 32, nullptr, nullptr, 0);
     const int th = (mode == 2) ? x.H / 2 : x.H;
     View t0 = make_view(rt.scratch, B, th, th, w.cin);
-    norm_apply(x, coef0, ACT_SILU, mode == 2 ? 1 : 0, nullptr, t0, s);
+    norm_apply(x, coef0, ACT_SILU, mode == 2 ? 1 : 0, nullptr, t0, s, !rt.strict);
     View h = make_view(rt.scratch, B, out.H, out.W, w.cout);
     run_conv(rt, w.conv0, t0, h, mode == 1 ? 1 : 0);
     // norm1 -> FiLM(time) -> FiLM(pose) -> SiLU, folded into one per-(n,c) affine
     float* coef1 = norm_coef(rt, h, w.norm1, 32, w.film0, film1 + w.film1_off, film1_total_);
-    norm_apply(h, coef1, ACT_SILU, 0, nullptr, h, s);
+    norm_apply(h, coef1, ACT_SILU, 0, nullptr, h, s, !rt.strict);
     if (w.has_skip) {
         THA4_REQUIRE(mode == 0, "res_block: skip conv only on same-resolution blocks");
         View sk = make_view(rt.scratch, B, x.H, x.W, w.cout);
@@ -390,7 +392,7 @@ void UNetNet::attn_block(Runtime& rt, const AttnW& w, const View& x, const View&
     rt.scratch->reset();
     float* coef = norm_coef(rt, x, w.norm, 32, nullptr, nullptr, 0);
     View t = make_view(rt.scratch, x.N, x.H, x.W, x.C);
-    norm_apply(x, coef, ACT_NONE, 0, nullptr, t, s);
+    norm_apply(x, coef, ACT_NONE, 0, nullptr, t, s, !rt.strict);
     View qkv = make_view(rt.scratch, x.N, x.H, x.W, 3 * x.C);
     run_conv(rt, w.qkv, t, qkv);
     View a = make_view(rt.scratch, x.N, x.H, x.W, x.C);

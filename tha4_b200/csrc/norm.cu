@@ -80,7 +80,8 @@ __global__ void norm_finalize_kernel(const double* __restrict__ sums, int C, int
 __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ x, int xH, int xW, int x_ld,
                                                          const float* __restrict__ coef, int act, int pool,
                                                          const float* __restrict__ res, int res_ld,
-                                                         float* __restrict__ y, int yH, int yW, int y_ld, int C, long total) {
+                                                         float* __restrict__ y, int yH, int yW, int y_ld, int C, long total,
+                                                         int round_out) {
     const int cq = C >> 2;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int q = (int)(i % cq);
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
             const float4 v = *reinterpret_cast<const float4*>(res + (((long)n * yH + oy) * yW + ox) * res_ld + 4 * q);
             r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
         }
+        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
         *reinterpret_cast<float4*>(y + (((long)n * yH + oy) * yW + ox) * y_ld + 4 * q) = r;
     }
 }
@@ -136,7 +138,8 @@ void norm_finalize(const double* sums, int N, int C, int HW, int groups, const f
     THA4_LAUNCH_CHECK();
 }
 
-void norm_apply(const View& x, const float* coef, int act, int pool, const View* res, const View& y, cudaStream_t s) {
+void norm_apply(const View& x, const float* coef, int act, int pool, const View* res, const View& y, cudaStream_t s,
+                int round_out) {
     THA4_REQUIRE(x.C == y.C && x.C % 4 == 0 && x.ld % 4 == 0 && y.ld % 4 == 0, "norm_apply: channels");
     if (pool) THA4_REQUIRE(y.H * 2 == x.H && y.W * 2 == x.W, "norm_apply: pool dims");
     else THA4_REQUIRE(y.H == x.H && y.W == x.W, "norm_apply: dims");
@@ -146,7 +149,7 @@ void norm_apply(const View& x, const float* coef, int act, int pool, const View*
     ProfScope prof(PROF_NORM, s);
     prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() + y.pixels() + (res ? y.pixels() : 0)) * x.C * 4);
     norm_apply_kernel<<<blocks, 256, 0, s>>>(x.p, x.H, x.W, x.ld, coef, act, pool, res ? res->p : nullptr,
-                                             res ? res->ld : 0, y.p, y.H, y.W, y.ld, x.C, total);
+                                             res ? res->ld : 0, y.p, y.H, y.W, y.ld, x.C, total, round_out);
     THA4_LAUNCH_CHECK();
 }
 

@@ -19,7 +19,9 @@ void norm_finalize(const double* sums, int N, int C, int HW, int groups, const f
 
 // y = act(x * A + B) (+ res).  pool == 1: y has half the resolution and is the 2x2 mean of the activated values
 // (AvgPool2d(2) after SiLU, unet.py:58,158).  x and y may alias when pool == 0.
-void norm_apply(const View& x, const float* coef, int act, int pool, const View* res, const View& y, cudaStream_t s);
+// round_out: round the result to TF32 (it is a tensor-core operand of the next conv; see round_tf32 in common.cuh).
+void norm_apply(const View& x, const float* coef, int act, int pool, const View* res, const View& y, cudaStream_t s,
+                int round_out = 0);
 
 // ---------------------------------------------------------------- small dense layers (linear.cu)
 // y[n][o] = bias[o] + sum_i f(x[n][i]) * W[o][i],  f = SiLU if silu_in else identity.  x: [N][x_ld], y: [N][y_ld].

@@ -86,6 +86,7 @@ class NativeModule(Module):
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if key != self._uploaded_key:
             ctx.load_net(self.NET_NAME, self.state_dict())
+            ctx.modules.add(self)
             self._uploaded_key = key
         return ctx
 
