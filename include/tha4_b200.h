@@ -115,7 +115,8 @@ int tha4_grid_sample(tha4_ctx* ctx, const float* image, const float* grid_change
 int tha4_resize_bilinear(tha4_ctx* ctx, const float* in, int N, int C, int Hi, int Wi, int Ho, int Wo, float* out, void* stream);
 /* affine_grid(identity, align_corners=False) base coordinates for one axis (host output, `size` floats) */
 int tha4_base_grid(int size, float* host_out);
-/* conv kinds: 0 = 3x3 s1 p1, 1 = 4x4 s2 p1, 2 = transposed 4x4 s2 p1, 3 = 1x1.  x [N,Cin,H,W] (stored input; if
+/* conv kinds: 0 = 3x3 s1 p1, 1 = 4x4 s2 p1, 2 = transposed 4x4 s2 p1, 3 = 1x1, 4 = nearest x2 upsample + 3x3 s1 p1
+ * (phase-decomposed on the low-resolution input).  x [N,Cin,H,W] (stored input; if
  * in_up the conv sees its nearest x2 upsample), w in the reference layout, bias / res may be NULL,
  * res_mode 1 same / 2 nearest-up x2 / 3 2x2 mean; y [N,Cout,Ho,Wo].  ksplit 0 = automatic. */
 int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, const float* bias, const float* res,

@@ -24,7 +24,7 @@ def conv(kind, x, w, bias=None, res=None, res_mode=0, in_up=0, strict=1, ksplit=
     N, Cin, H, W = x.shape
     Cout = w.shape[1] if kind == 2 else w.shape[0]
     LH, LW = (2 * H, 2 * W) if in_up else (H, W)
-    Ho, Wo = {0: (LH, LW), 1: (LH // 2, LW // 2), 2: (LH * 2, LW * 2), 3: (LH, LW)}[kind]
+    Ho, Wo = {0: (LH, LW), 1: (LH // 2, LW // 2), 2: (LH * 2, LW * 2), 3: (LH, LW), 4: (LH * 2, LW * 2)}[kind]
     y = torch.empty(N, Cout, Ho, Wo, device='cuda:0')
     xd, wd = dev(x), dev(w)
     bd = dev(bias) if bias is not None else None

@@ -378,8 +378,9 @@ int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, cons
         if (cin_k != Cin) THA4_CUDA_CHECK(cudaMemsetAsync(xin.p, 0, xin.pixels() * cin_k * sizeof(float), s));
         nchw_to_nhwc(make_img(x, N, Cin, H, W), xin.slice(0, Cin), s);
         const int LH = in_up ? 2 * H : H, LW = in_up ? 2 * W : W;
-        const int Ho = (kind == CONV_4x4_S2) ? LH / 2 : (kind == CONVT_4x4_S2 ? LH * 2 : LH);
-        const int Wo = (kind == CONV_4x4_S2) ? LW / 2 : (kind == CONVT_4x4_S2 ? LW * 2 : LW);
+        const bool x2 = (kind == CONVT_4x4_S2 || kind == CONV_UP2_3x3);
+        const int Ho = (kind == CONV_4x4_S2) ? LH / 2 : (x2 ? LH * 2 : LH);
+        const int Wo = (kind == CONV_4x4_S2) ? LW / 2 : (x2 ? LW * 2 : LW);
         View yo = mk(Ho, Wo, Cout);
         ConvArgs a;
         a.in = xin; a.in_up = in_up; a.out = yo; a.strict = strict; a.ksplit = ksplit;
@@ -390,6 +391,8 @@ int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, cons
             nchw_to_nhwc(make_img(res, N, Cout, rh, rw), r, s);
             a.res = r; a.res_mode = res_mode;
         }
+        const size_t wsf = conv_workspace_floats(cw, a);
+        if (wsf) { a.ws = ctx->scratch.alloc(wsf); a.ws_floats = wsf; }
         conv_forward(cw, a, s);
         nhwc_to_nchw(yo, y, s);
     });

@@ -289,6 +289,15 @@ __global__ void conv_pack_kernel(float* dst, const float* src, int kind, int w_c
             v = src[(((long)co * w_cin + ci) * 4 + tap / 4) * 4 + tap % 4];
         } else if (kind == CONV_1x1) {
             v = src[(long)co * w_cin + ci];
+        } else if (kind == CONV_UP2_3x3) {
+            // out[2a+py] = sum_ky up(x)[2a+py+ky-1] w[ky] with up(x)[r] = x[r>>1]:
+            //   py=0: ky=0 -> x[a-1];  ky=1,2 -> x[a]        py=1: ky=0,1 -> x[a];  ky=2 -> x[a+1]
+            const int py = ph >> 1, px = ph & 1, ty = tap >> 1, tx = tap & 1;
+            const int ky0 = (py == 0) ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), ky1 = (py == 0) ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+            const int kx0 = (px == 0) ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), kx1 = (px == 0) ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+            v = 0.0f;
+            for (int ky = ky0; ky <= ky1; ++ky)
+                for (int kx = kx0; kx <= kx1; ++kx) v += src[(((long)co * w_cin + ci) * 3 + ky) * 3 + kx];
         } else {  // CONVT_4x4_S2: weight [Cin][Cout][4][4]; phase (py,px), tap (ty,tx): k = (p==0) ? {1,3}[t] : {0,2}[t]
             int py = ph >> 1, px = ph & 1, ty = tap >> 1, tx = tap & 1;
             int ky = (py == 0) ? (ty == 0 ? 1 : 3) : (ty == 0 ? 0 : 2);
@@ -318,6 +327,17 @@ void conv_describe(ConvWeights& cw, ConvKind kind, int cin, int cout) {
         for (int t = 0; t < 16; ++t) { cw.dy[0][t] = (signed char)(t / 4 - 1); cw.dx[0][t] = (signed char)(t % 4 - 1); }
     } else if (kind == CONV_1x1) {
         cw.ntaps = 1;
+    } else if (kind == CONV_UP2_3x3) {
+        cw.ntaps = 4; cw.nphase = 4; cw.out_mul = 2;
+        for (int ph = 0; ph < 4; ++ph) {
+            int py = ph >> 1, px = ph & 1;
+            cw.ph_oy[ph] = (signed char)py; cw.ph_ox[ph] = (signed char)px;
+            for (int t = 0; t < 4; ++t) {
+                int ty = t >> 1, tx = t & 1;
+                cw.dy[ph][t] = (signed char)((py == 0) ? (ty == 0 ? -1 : 0) : (ty == 0 ? 0 : 1));
+                cw.dx[ph][t] = (signed char)((px == 0) ? (tx == 0 ? -1 : 0) : (tx == 0 ? 0 : 1));
+            }
+        }
     } else {
         // out[2a+py] = sum_ky in[(2a+py+1-ky)/2] w[ky]  (stride 2, pad 1):  py=0: ky=1 -> a, ky=3 -> a-1;
         //                                                                py=1: ky=0 -> a+1, ky=2 -> a.

@@ -28,7 +28,10 @@ struct ConvWeights {
     signed char ph_oy[CONV_MAX_PHASES], ph_ox[CONV_MAX_PHASES];
 };
 
-enum ConvKind { CONV_3x3 = 0, CONV_4x4_S2 = 1, CONVT_4x4_S2 = 2, CONV_1x1 = 3 };
+// CONV_UP2_3x3: nearest-neighbour x2 upsample followed by a 3x3 conv (the up-sampling ResBlock, unet.py:46,119-123),
+// evaluated on the LOW-resolution input as four output phases of 2x2 taps whose weights are pre-summed at pack time
+// (rows/cols of the 3x3 kernel that read the same source pixel are added): 2.25x fewer MACs, no upsampled tensor.
+enum ConvKind { CONV_3x3 = 0, CONV_4x4_S2 = 1, CONVT_4x4_S2 = 2, CONV_1x1 = 3, CONV_UP2_3x3 = 4 };
 
 // Fills the tap tables of `cw` for `kind` (no allocation).
 void conv_describe(ConvWeights& cw, ConvKind kind, int cin, int cout);
@@ -49,7 +52,12 @@ struct ConvArgs {
     int res_mode = RES_NONE;    // RES_UP2: res stored at half resolution; RES_DOWN2: res at double resolution (2x2 mean)
     int strict = 0;             // 1: 3xTF32 error-compensated products (fp32-equivalent); 0: single TF32
     int ksplit = 0;             // 0: choose automatically
+    float* ws = nullptr;        // optional split-K workspace (conv_workspace_floats); without it split-K accumulates atomically
+    size_t ws_floats = 0;
 };
+
+// Floats of workspace the tcgen05 kernel wants for this call (0: none needed / not the tcgen05 path).
+size_t conv_workspace_floats(const ConvWeights& cw, const ConvArgs& a);
 
 // out = conv(in) + bias (+ res).  When the launch splits K, `out` is zeroed first on the same stream.
 // Dispatches to the tcgen05 kernel (conv_tc.cu) when it supports the configuration, else to the mma.sync kernel.

@@ -33,6 +33,7 @@ struct TcParams {
     const float* res; int resH, resW, res_ld, res_mode;
     int N, MH, MW, tiles_x, tiles_y;
     int ntaps, cpt, ksplit, out_mul;
+    float* ws; long ws_rows; int ws_ld;            // split-K partials: ws[z][tile*128 + row][cout_pad]
     signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
     signed char dx[CONV_MAX_PHASES][CONV_MAX_TAPS];
     signed char ph_oy[CONV_MAX_PHASES], ph_ox[CONV_MAX_PHASES];
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 const int cn = min(32, p.outC - cbase);
-                if (lead) {
+                if (lead && !(p.ksplit > 1 && p.ws)) {
                     if (p.bias) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
@@ -203,7 +204,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                             if (j < cn) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
                     }
                 }
-                if (p.ksplit > 1) {
+                if (p.ksplit > 1 && p.ws) {
+                    float* wrow = p.ws + ((long)blockIdx.z * p.ws_rows + (long)blockIdx.x * 128 + row) * p.ws_ld + cbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(wrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else if (p.ksplit > 1) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if (j < cn) atomicAdd(orow + cbase + j, v[j]);
                 } else if (cn == 32) {
@@ -221,6 +227,44 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// out = sum_splits ws + bias + res  (deterministic split-K reduction; replaces fp32 atomics)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcParams p, int nphase, int cout_pad) {
+    const int cq = (p.outC + 3) >> 2;
+    const long total = (long)nphase * p.N * p.MH * p.MW * cq;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % cq);
+        long r = i / cq;
+        const int mx = (int)(r % p.MW); r /= p.MW;
+        const int my = (int)(r % p.MH); r /= p.MH;
+        const int n = (int)(r % p.N);
+        const int phase = (int)(r / p.N);
+        const long tile = ((long)n * p.tiles_y + my / TILE_H) * p.tiles_x + mx / TILE_W;
+        const int row = (my % TILE_H) * TILE_W + mx % TILE_W;
+        const int c = 4 * q;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < p.ksplit; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(p.ws + ((long)(phase * p.ksplit + s) * p.ws_rows + tile * 128 + row) * p.ws_ld + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
+        float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        const int cn = min(4, p.outC - c);
+        if (p.bias) for (int j = 0; j < cn; ++j) v[j] += __ldg(p.bias + c + j);
+        if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
+            const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
+            const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + c;
+            for (int j = 0; j < cn; ++j) v[j] += rr[j];
+        } else if (p.res_mode == RES_DOWN2) {
+            const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + c;
+            const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
+            for (int j = 0; j < cn; ++j) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+        }
+        float* o = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld + c;
+        if (cn == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else for (int j = 0; j < cn; ++j) o[j] = v[j];
     }
 }
 
@@ -288,6 +332,40 @@ void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
 
 }  // namespace
 
+namespace {
+struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW; };
+TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
+    TcPlan pl;
+    pl.MH = a.out.H / cw.out_mul; pl.MW = a.out.W / cw.out_mul;
+    pl.tiles_x = ceil_div(pl.MW, TILE_W); pl.tiles_y = ceil_div(pl.MH, TILE_H);
+    pl.bn = (cw.cout_pad % 256 == 0) ? 256 : (cw.cout_pad % 128 == 0 ? 128 : (cw.cout_pad % 64 == 0 ? 64 : 32));
+    pl.tiles_m = pl.tiles_x * pl.tiles_y * a.in.N;
+    pl.tiles_n = cw.cout_pad / pl.bn;
+    const int KT = cw.ntaps * (cw.cin_pad / KCH);
+    int ksplit = a.ksplit;
+    if (ksplit <= 0) {
+        const long ctas = (long)pl.tiles_m * pl.tiles_n * cw.nphase;
+        ksplit = 1;
+        if (ctas < 120) {
+            ksplit = (int)((148 + ctas - 1) / ctas);
+            ksplit = std::min(ksplit, std::max(1, KT / 4));
+            ksplit = std::min(ksplit, 32);
+        }
+    }
+    ksplit = std::max(1, std::min(ksplit, KT));
+    const int k_per = (KT + ksplit - 1) / ksplit;
+    pl.ksplit = (KT + k_per - 1) / k_per;          // every split owns at least one k-block
+    return pl;
+}
+}  // namespace
+
+size_t conv_workspace_floats(const ConvWeights& cw, const ConvArgs& a) {
+    if (!conv_tc_supported(cw, a)) return 0;
+    const TcPlan pl = tc_plan(cw, a);
+    if (pl.ksplit <= 1) return 0;
+    return (size_t)cw.nphase * pl.ksplit * pl.tiles_m * 128 * cw.cout_pad;
+}
+
 bool conv_tc_supported(const ConvWeights& cw, const ConvArgs& a) {
     if (a.in_up || cw.stride != 1 || a.strict) return false;
     if (a.in.ld % 4 != 0 || (((uintptr_t)a.in.p) & 15) != 0) return false;
@@ -306,33 +384,23 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     p.resH = a.res.H; p.resW = a.res.W; p.res_ld = a.res.ld;
     p.N = a.in.N;
     p.out_mul = cw.out_mul;
-    p.MH = a.out.H / cw.out_mul; p.MW = a.out.W / cw.out_mul;
+    const TcPlan pl = tc_plan(cw, a);
+    p.MH = pl.MH; p.MW = pl.MW;
     THA4_REQUIRE(p.MH == a.in.H && p.MW == a.in.W, "conv_tc: geometry");
-    p.tiles_x = ceil_div(p.MW, TILE_W); p.tiles_y = ceil_div(p.MH, TILE_H);
+    p.tiles_x = pl.tiles_x; p.tiles_y = pl.tiles_y;
     p.ntaps = cw.ntaps; p.cpt = cw.cin_pad / KCH;
     for (int ph = 0; ph < CONV_MAX_PHASES; ++ph) {
         p.ph_oy[ph] = cw.ph_oy[ph]; p.ph_ox[ph] = cw.ph_ox[ph];
         for (int t = 0; t < CONV_MAX_TAPS; ++t) { p.dy[ph][t] = cw.dy[ph][t]; p.dx[ph][t] = cw.dx[ph][t]; }
     }
-    const int bn = (cw.cout_pad % 256 == 0) ? 256 : (cw.cout_pad % 128 == 0 ? 128 : (cw.cout_pad % 64 == 0 ? 64 : 32));
-    const int tiles_m = p.tiles_x * p.tiles_y * p.N;
-    const int tiles_n = cw.cout_pad / bn;
-    const int KT = cw.ntaps * p.cpt;
-    int ksplit = a.ksplit;
-    if (ksplit <= 0) {
-        const long ctas = (long)tiles_m * tiles_n * cw.nphase;
-        ksplit = 1;
-        if (ctas < 120) {
-            ksplit = (int)((148 + ctas - 1) / ctas);
-            ksplit = std::min(ksplit, std::max(1, KT / 4));
-            ksplit = std::min(ksplit, 32);
-        }
-    }
-    ksplit = std::max(1, std::min(ksplit, KT));
+    const int bn = pl.bn, tiles_m = pl.tiles_m, tiles_n = pl.tiles_n, ksplit = pl.ksplit;
     p.ksplit = ksplit;
+    const size_t ws_need = (size_t)cw.nphase * ksplit * tiles_m * 128 * cw.cout_pad;
+    const bool use_ws = ksplit > 1 && a.ws && a.ws_floats >= ws_need;
+    p.ws = use_ws ? a.ws : nullptr; p.ws_rows = (long)tiles_m * 128; p.ws_ld = cw.cout_pad;
     ProfScope prof(PROF_CONV, s);
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
-    if (ksplit > 1)
+    if (ksplit > 1 && !use_ws)
         THA4_CUDA_CHECK(cudaMemset2DAsync(a.out.p, (size_t)a.out.ld * sizeof(float), 0, (size_t)a.out.C * sizeof(float), a.out.pixels(), s));
     const CUtensorMap& ma = activation_map(a.in);
     const CUtensorMap& mb = weight_map(cw, bn);
@@ -340,7 +408,7 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     static int stages_mode = -1;     // experiment knob: THA4_TC_STAGES=deep|mid|shallow
     if (stages_mode < 0) {
         const char* e = getenv("THA4_TC_STAGES");
-        stages_mode = (e && !strcmp(e, "deep")) ? 0 : ((e && !strcmp(e, "shallow")) ? 2 : 1);
+        stages_mode = (e && !strcmp(e, "deep")) ? 0 : ((e && !strcmp(e, "mid")) ? 1 : 2);   // default: shallow (2-3 CTAs/SM)
     }
     if (stages_mode == 0) {
         if (bn == 256) launch_tc<256, 4>(ma, mb, p, grid, s);
@@ -357,6 +425,12 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
         else if (bn == 128) launch_tc<128, 2>(ma, mb, p, grid, s);
         else if (bn == 64) launch_tc<64, 2>(ma, mb, p, grid, s);
         else launch_tc<32, 3>(ma, mb, p, grid, s);
+    }
+    if (use_ws) {
+        const long total = (long)cw.nphase * p.N * p.MH * p.MW * ((p.outC + 3) / 4);
+        const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 8);
+        splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p, cw.nphase, cw.cout_pad);
+        THA4_LAUNCH_CHECK();
     }
 }
 

@@ -61,7 +61,7 @@ ConvWeights load_conv(const StateDict& sd, const std::string& prefix, ConvKind k
     THA4_REQUIRE(w.shape.size() == 4, "conv weight rank: " + prefix);
     const int cout = (int)(kind == CONVT_4x4_S2 ? w.shape[1] : w.shape[0]);
     const int cin = (int)(kind == CONVT_4x4_S2 ? w.shape[0] : w.shape[1]);
-    const int k = (kind == CONV_3x3) ? 3 : (kind == CONV_1x1 ? 1 : 4);
+    const int k = (kind == CONV_3x3 || kind == CONV_UP2_3x3) ? 3 : (kind == CONV_1x1 ? 1 : 4);
     THA4_REQUIRE(w.shape[2] == k && w.shape[3] == k, "conv kernel size: " + prefix);
     ConvWeights cw;
     conv_describe(cw, kind, cin_kernel > 0 ? cin_kernel : cin, cout);
@@ -133,6 +133,8 @@ void run_conv(Runtime& rt, const ConvWeights& cw, const View& in, const View& ou
     ConvArgs a;
     a.in = in; a.in_up = in_up; a.out = out; a.strict = rt.strict;
     if (res) { a.res = *res; a.res_mode = res_mode; }
+    const size_t ws = conv_workspace_floats(cw, a);
+    if (ws) { a.ws = rt.scratch->alloc(ws); a.ws_floats = ws; }
     conv_forward(cw, a, rt.stream);
 }
 
@@ -242,10 +244,10 @@ UNetNet::UNetNet(bool upscaler, int size, int model_channels, std::vector<int> m
 
 namespace {
 
-ResBlockW load_res_block(const StateDict& sd, const std::string& p, cudaStream_t s) {
+ResBlockW load_res_block(const StateDict& sd, const std::string& p, cudaStream_t s, bool upsampling = false) {
     ResBlockW w;
     w.norm0 = load_norm(sd, p + ".norm0", s);
-    w.conv0 = load_conv(sd, p + ".conv0", CONV_3x3, true, s);
+    w.conv0 = load_conv(sd, p + ".conv0", upsampling ? CONV_UP2_3x3 : CONV_3x3, true, s);
     w.norm1 = load_norm(sd, p + ".norm1", s);
     w.conv1 = load_conv(sd, p + ".conv1", CONV_3x3, true, s);
     w.cin = w.conv0.cin; w.cout = w.conv0.cout;
@@ -314,7 +316,7 @@ void UNetNet::load(const StateDict& sd, cudaStream_t s) {
             if (bi == 0) up_attn_[r] = load_attn(sd, bp + ".attention_blocks." + std::to_string(r), s);
         }
         if (bi < L_ - 1) {
-            up_us_[bi] = load_res_block(sd, bp + ".upsample", s);
+            up_us_[bi] = load_res_block(sd, bp + ".upsample", s, true);
             all_blocks.push_back({&up_us_[bi], bp + ".upsample"});
         }
     }
@@ -372,7 +374,7 @@ void UNetNet::res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode
     View t0 = make_view(rt.scratch, B, th, th, w.cin);
     norm_apply(x, coef0, ACT_SILU, mode == 2 ? 1 : 0, nullptr, t0, s, !rt.strict);
     View h = make_view(rt.scratch, B, out.H, out.W, w.cout);
-    run_conv(rt, w.conv0, t0, h, mode == 1 ? 1 : 0);
+    run_conv(rt, w.conv0, t0, h);      // mode 1: conv0 was packed as CONV_UP2_3x3 (upsample folded into 4 phases)
     // norm1 -> FiLM(time) -> FiLM(pose) -> SiLU, folded into one per-(n,c) affine
     float* coef1 = norm_coef(rt, h, w.norm1, 32, w.film0, film1 + w.film1_off, film1_total_);
     norm_apply(h, coef1, ACT_SILU, 0, nullptr, h, s, !rt.strict);
