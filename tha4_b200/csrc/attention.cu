@@ -8,25 +8,32 @@ namespace tha4 {
 namespace {
 
 constexpr int L = 256, D = 32;
+constexpr int DP = D + 4;     // shared-memory row pitch: the 4 key-split lanes of a query hit 4 different banks
 
-__global__ void __launch_bounds__(L) attention_kernel(const float* __restrict__ qkv, int qkv_ld, int C, int heads,
-                                                      float* __restrict__ out, int out_ld) {
+// grid = N * heads * 4 (query quarter), block = 256 threads = 64 queries x 4 key splits.  Each thread runs an online
+// softmax over its 64 keys; the 4 partial (max, sum, acc) triples of a query are merged with warp shuffles.
+constexpr int QPB = 64, KSPLIT = 4;
+__global__ void __launch_bounds__(QPB * KSPLIT) attention_kernel(const float* __restrict__ qkv, int qkv_ld, int C, int heads,
+                                                                 float* __restrict__ out, int out_ld) {
     extern __shared__ __align__(16) float sm[];
-    float* Ks = sm;            // [L][D]
-    float* Vs = sm + L * D;    // [L][D]
-    const int n = blockIdx.x / heads, h = blockIdx.x % heads;
-    const int t = threadIdx.x;
+    float* Ks = sm;            // [L][DP]
+    float* Vs = sm + L * DP;   // [L][DP]
+    const int qq = blockIdx.x % (L / QPB);
+    const int nh = blockIdx.x / (L / QPB);
+    const int n = nh / heads, h = nh % heads;
+    const int tid = threadIdx.x;
     const float* base = qkv + (long)n * L * qkv_ld;
-    // stage K and V: thread t copies token t
-    {
-        const float4* kp = reinterpret_cast<const float4*>(base + (long)t * qkv_ld + C + h * D);
-        const float4* vp = reinterpret_cast<const float4*>(base + (long)t * qkv_ld + 2 * C + h * D);
+    {   // stage K and V of this head: thread tid copies token tid
+        const float4* kp = reinterpret_cast<const float4*>(base + (long)tid * qkv_ld + C + h * D);
+        const float4* vp = reinterpret_cast<const float4*>(base + (long)tid * qkv_ld + 2 * C + h * D);
 #pragma unroll
         for (int j = 0; j < D / 4; ++j) {
-            reinterpret_cast<float4*>(Ks + t * D)[j] = kp[j];
-            reinterpret_cast<float4*>(Vs + t * D)[j] = vp[j];
+            reinterpret_cast<float4*>(Ks + tid * DP)[j] = kp[j];
+            reinterpret_cast<float4*>(Vs + tid * DP)[j] = vp[j];
         }
     }
+    const int t = qq * QPB + tid / KSPLIT;      // query token
+    const int ks = tid % KSPLIT;                // key split: keys ks, ks + 4, ks + 8, ...
     float q[D];
     {
         const float4* qp = reinterpret_cast<const float4*>(base + (long)t * qkv_ld + h * D);
@@ -45,8 +52,8 @@ __global__ void __launch_bounds__(L) attention_kernel(const float* __restrict__ 
     float m = -INFINITY, l = 0.0f, acc[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) acc[j] = 0.0f;
-    for (int s = 0; s < L; ++s) {
-        const float* kr = Ks + s * D;
+    for (int s = ks; s < L; s += KSPLIT) {
+        const float* kr = Ks + s * DP;
         float dot = 0.0f;
 #pragma unroll
         for (int j = 0; j < D; ++j) dot = fmaf(q[j], kr[j] * scale, dot);
@@ -54,16 +61,33 @@ __global__ void __launch_bounds__(L) attention_kernel(const float* __restrict__ 
         const float corr = expf(m - mn);
         const float pw = expf(dot - mn);
         l = l * corr + pw;
-        const float* vr = Vs + s * D;
+        const float* vr = Vs + s * DP;
 #pragma unroll
         for (int j = 0; j < D; ++j) acc[j] = fmaf(acc[j], corr, pw * vr[j]);
         m = mn;
     }
-    const float inv = 1.0f / l;
-    float4* op = reinterpret_cast<float4*>(out + ((long)n * L + t) * out_ld + h * D);
+    // merge the KSPLIT partials of this query (adjacent lanes)
 #pragma unroll
-    for (int j = 0; j < D / 4; ++j)
-        op[j] = make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
+    for (int off = 1; off < KSPLIT; off <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+        const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+        const float mn = fmaxf(m, mo);
+        const float ca = expf(m - mn), cb = expf(mo - mn);
+        l = l * ca + lo * cb;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const float ao = __shfl_xor_sync(0xffffffffu, acc[j], off);
+            acc[j] = acc[j] * ca + ao * cb;
+        }
+        m = mn;
+    }
+    if (ks == 0) {
+        const float inv = 1.0f / l;
+        float4* op = reinterpret_cast<float4*>(out + ((long)n * L + t) * out_ld + h * D);
+#pragma unroll
+        for (int j = 0; j < D / 4; ++j)
+            op[j] = make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
+    }
 }
 
 }  // namespace
@@ -71,14 +95,14 @@ __global__ void __launch_bounds__(L) attention_kernel(const float* __restrict__ 
 void attention_forward(const View& qkv, int heads, const View& out, cudaStream_t s) {
     THA4_REQUIRE(qkv.H * qkv.W == L && out.C * 3 == qkv.C && out.C / heads == D, "attention: shape (L=256, head dim 32)");
     THA4_REQUIRE(qkv.ld % 4 == 0 && out.ld % 4 == 0, "attention: alignment");
-    const size_t smem = 2 * L * D * sizeof(float);
+    const size_t smem = 2 * L * DP * sizeof(float);
     static bool configured = false;
     if (!configured) {
         THA4_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     ProfScope prof(PROF_ATTN, s);
-    attention_kernel<<<qkv.N * heads, L, smem, s>>>(qkv.p, qkv.ld, out.C, heads, out.p, out.ld);
+    attention_kernel<<<qkv.N * heads * (L / QPB), QPB * KSPLIT, smem, s>>>(qkv.p, qkv.ld, out.C, heads, out.p, out.ld);
     THA4_LAUNCH_CHECK();
 }
 

@@ -17,6 +17,8 @@ struct tha4_ctx {
     int microbatch = 8;
     Pool persist, scratch;
     int* flag = nullptr;
+    double* stats_base = nullptr;          // zero-initialised statistics arena (Runtime::alloc_stats)
+    size_t stats_cap = 0, stats_off = 0;
     std::unique_ptr<EncDecNet> decomposer, combiner, face;
     std::unique_ptr<UNetNet> body, upscaler;
     std::unique_ptr<SirenFaceNet> sface;
@@ -46,6 +48,7 @@ int guarded(tha4_ctx* ctx, F&& f) {
 Runtime make_rt(tha4_ctx* ctx, void* stream) {
     Runtime rt;
     rt.persist = &ctx->persist; rt.scratch = &ctx->scratch; rt.stream = (cudaStream_t)stream; rt.strict = ctx->strict;
+    rt.stats_base = ctx->stats_base; rt.stats_cap = ctx->stats_cap; rt.stats_off = &ctx->stats_off;
     return rt;
 }
 
@@ -105,13 +108,21 @@ StateDict make_sd(int n, const char* const* keys, const void* const* ptrs, const
 }
 
 // Runs `fn(chunk offset n0, chunk size b)` over micro-batches; resets the workspace per chunk.
+// Start of one pass over the workspace: every pool block becomes reusable and the part of the statistics arena the
+// previous pass dirtied is re-zeroed (the arena is all-zero at the start of every pass).
+void begin_pass(tha4_ctx* ctx, cudaStream_t stream) {
+    ctx->persist.reset();
+    ctx->scratch.reset();
+    if (ctx->stats_off > 0) THA4_CUDA_CHECK(cudaMemsetAsync(ctx->stats_base, 0, ctx->stats_off * sizeof(double), stream));
+    ctx->stats_off = 0;
+}
+
 template <typename F>
-void for_chunks(tha4_ctx* ctx, int B, F&& fn) {
+void for_chunks(tha4_ctx* ctx, int B, cudaStream_t stream, F&& fn) {
     THA4_REQUIRE(B >= 1, "batch must be >= 1");
     for (int n0 = 0; n0 < B; n0 += ctx->microbatch) {
         const int b = std::min(ctx->microbatch, B - n0);
-        ctx->persist.reset();
-        ctx->scratch.reset();
+        begin_pass(ctx, stream);
         fn(n0, b);
     }
 }
@@ -139,6 +150,9 @@ int tha4_ctx_create(int device, tha4_ctx** out) {
         auto* ctx = new tha4_ctx();
         ctx->device = device;
         THA4_CUDA_CHECK(cudaMalloc(&ctx->flag, sizeof(int)));
+        ctx->stats_cap = (size_t)8 << 20;                       // 8 Mi doubles = 64 MB
+        THA4_CUDA_CHECK(cudaMalloc(&ctx->stats_base, ctx->stats_cap * sizeof(double)));
+        THA4_CUDA_CHECK(cudaMemset(ctx->stats_base, 0, ctx->stats_cap * sizeof(double)));
         ctx->decomposer.reset(new EncDecNet(TAIL_DECOMPOSER, 128, 4, 0));
         ctx->combiner.reset(new EncDecNet(TAIL_COMBINER, 128, 8, 12));
         ctx->face.reset(new EncDecNet(TAIL_FACE, 192, 4, 27));
@@ -162,6 +176,7 @@ int tha4_ctx_destroy(tha4_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->flag) cudaFree(ctx->flag);
+    if (ctx->stats_base) cudaFree(ctx->stats_base);
     delete ctx;
     return THA4_OK;
 }
@@ -217,7 +232,7 @@ int tha4_load_net(tha4_ctx* ctx, int net, int n_tensors, const char* const* keys
 int tha4_eyebrow_decomposer_forward(tha4_ctx* ctx, const float* image, int B, float* const* outputs, void* stream) {
     return guarded(ctx, [&] {
         Runtime rt = make_rt(ctx, stream);
-        for_chunks(ctx, B, [&](int n0, int b) {
+        for_chunks(ctx, B, rt.stream, [&](int n0, int b) {
             float* o[6]; offset_outputs<6>(outputs, kEncDecDecomposer, n0, o);
             ctx->decomposer->forward(rt, make_img(image + (size_t)n0 * 4 * 128 * 128, b, 4, 128, 128), ImgView{}, nullptr, 0, o);
         });
@@ -228,7 +243,7 @@ int tha4_eyebrow_morphing_combiner_forward(tha4_ctx* ctx, const float* backgroun
                                            const float* pose, int pose_ld, int B, float* const* outputs, void* stream) {
     return guarded(ctx, [&] {
         Runtime rt = make_rt(ctx, stream);
-        for_chunks(ctx, B, [&](int n0, int b) {
+        for_chunks(ctx, B, rt.stream, [&](int n0, int b) {
             float* o[8]; offset_outputs<8>(outputs, kCombiner, n0, o);
             const size_t off = (size_t)n0 * 4 * 128 * 128;
             ctx->combiner->forward(rt, make_img(eyebrow_layer + off, b, 4, 128, 128), make_img(background_layer + off, b, 4, 128, 128),
@@ -241,7 +256,7 @@ int tha4_face_morpher_forward(tha4_ctx* ctx, const float* image, const float* po
                               float* const* outputs, void* stream) {
     return guarded(ctx, [&] {
         Runtime rt = make_rt(ctx, stream);
-        for_chunks(ctx, B, [&](int n0, int b) {
+        for_chunks(ctx, B, rt.stream, [&](int n0, int b) {
             float* o[8]; offset_outputs<8>(outputs, kFace, n0, o);
             ctx->face->forward(rt, make_img(image + (size_t)n0 * 4 * 192 * 192, b, 4, 192, 192), ImgView{},
                                pose + (size_t)n0 * pose_ld, pose_ld, o);
@@ -254,7 +269,7 @@ int tha4_morpher_forward(tha4_ctx* ctx, const float* image, const float* pose, i
     return guarded(ctx, [&] {
         Runtime rt = make_rt(ctx, stream);
         OutSpec spec[5]; fill_unet_spec(spec, 256);
-        for_chunks(ctx, B, [&](int n0, int b) {
+        for_chunks(ctx, B, rt.stream, [&](int n0, int b) {
             float* o[5]; offset_outputs<5>(outputs, spec, n0, o);
             ctx->body->forward(rt, make_img(image + (size_t)n0 * 4 * 256 * 256, b, 4, 256, 256), nullptr, nullptr, 0,
                                pose + (size_t)n0 * pose_ld, pose_ld, o);
@@ -268,7 +283,7 @@ int tha4_upscaler_forward(tha4_ctx* ctx, const float* rest_image, const float* c
     return guarded(ctx, [&] {
         Runtime rt = make_rt(ctx, stream);
         OutSpec spec[5]; fill_unet_spec(spec, 512);
-        for_chunks(ctx, B, [&](int n0, int b) {
+        for_chunks(ctx, B, rt.stream, [&](int n0, int b) {
             float* o[5]; offset_outputs<5>(outputs, spec, n0, o);
             ctx->upscaler->forward(rt, make_img(rest_image + (size_t)n0 * 4 * 512 * 512, b, 4, 512, 512),
                                    coarse_posed_image + (size_t)n0 * 4 * coarse_size * coarse_size,
@@ -280,7 +295,7 @@ int tha4_upscaler_forward(tha4_ctx* ctx, const float* rest_image, const float* c
 int tha4_siren_face_morpher_forward(tha4_ctx* ctx, const float* pose, int pose_ld, int B, float* output, void* stream) {
     return guarded(ctx, [&] {
         Runtime rt = make_rt(ctx, stream);
-        ctx->persist.reset(); ctx->scratch.reset();
+        begin_pass(ctx, (cudaStream_t)stream);
         ctx->sface->forward(rt, pose, pose_ld, B, output);
     });
 }
@@ -289,7 +304,7 @@ int tha4_siren_morpher_forward(tha4_ctx* ctx, const float* image, const float* p
                                float* const* outputs, void* stream) {
     return guarded(ctx, [&] {
         Runtime rt = make_rt(ctx, stream);
-        ctx->persist.reset(); ctx->scratch.reset();
+        begin_pass(ctx, (cudaStream_t)stream);
         ctx->sbody->forward(rt, make_img(image, B, 4, 512, 512), pose, pose_ld, outputs);
     });
 }
@@ -311,7 +326,7 @@ int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, const floa
         for (int i = 0; i < 8; ++i) spec[n++] = kCombiner[i];
         for (int i = 0; i < 6; ++i) spec[n++] = kEncDecDecomposer[i];
         const int nout = n;
-        for_chunks(ctx, B, [&](int n0, int b) {
+        for_chunks(ctx, B, rt.stream, [&](int n0, int b) {
             float* o[33];
             for (int i = 0; i < nout; ++i) o[i] = outputs[i] ? outputs[i] + (size_t)n0 * spec[i].c * spec[i].s * spec[i].s : nullptr;
             const float* cd[6];
@@ -327,7 +342,7 @@ int tha4_student_forward(tha4_ctx* ctx, const float* image, const float* pose, i
     return guarded(ctx, [&] {
         Runtime rt = make_rt(ctx, stream);
         cudaStream_t s = rt.stream;
-        ctx->persist.reset(); ctx->scratch.reset();
+        begin_pass(ctx, (cudaStream_t)stream);
         // face SIREN from pose[:, :39] (mode_14.py:64-71), pasted at rows 80:208, cols 192:320 (:72-78)
         ctx->sface->forward(rt, pose, 45, B, outputs[5]);
         float* body_in = ctx->persist.alloc((size_t)B * 4 * 512 * 512);
@@ -362,7 +377,7 @@ int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, cons
                    void* stream) {
     return guarded(ctx, [&] {
         cudaStream_t s = (cudaStream_t)stream;
-        ctx->persist.reset(); ctx->scratch.reset();
+        begin_pass(ctx, (cudaStream_t)stream);
         Pool* P = &ctx->persist;
         const int cin_k = round_up(Cin, 4);
         ConvWeights cw;
@@ -402,19 +417,18 @@ int tha4_test_norm(tha4_ctx* ctx, const float* x, int N, int C, int H, int W, in
                    const float* beta, const float* film0, const float* film1, int act, int pool, float* y, void* stream) {
     return guarded(ctx, [&] {
         cudaStream_t s = (cudaStream_t)stream;
-        ctx->persist.reset(); ctx->scratch.reset();
+        begin_pass(ctx, s);
+        Runtime rt = make_rt(ctx, stream);
         Pool* P = &ctx->persist;
         View xin; xin.N = N; xin.H = H; xin.W = W; xin.C = C; xin.ld = C; xin.p = P->alloc((size_t)N * H * W * C);
+        xin.stats_rep = 2; xin.stats_rep_stride = (long)N * C * 2;
+        xin.stats = rt.alloc_stats((size_t)2 * N * C * 2); xin.stats_ld = C;
         nchw_to_nhwc(make_img(x, N, C, H, W), xin, s);
-        double* sums = P->alloc_f64((size_t)N * C * 2);
-        THA4_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(double), s));
-        norm_stats(xin, sums, s);
-        float* coef = P->alloc((size_t)N * C * 2);
-        norm_finalize(sums, N, C, H * W, groups, gamma, beta, film0, film1, 2 * C, coef, s);
-        View yo = xin;
+        norm_stats(xin, s);
+        View yo = xin; yo.stats = nullptr;
         if (pool) { yo.H = H / 2; yo.W = W / 2; }
         yo.p = P->alloc((size_t)N * yo.H * yo.W * C);
-        norm_apply(xin, coef, act, pool, nullptr, yo, s);
+        norm_apply_fused(xin, groups, gamma, beta, film0, film1, 2 * C, act, pool, nullptr, yo, s, 0);
         nhwc_to_nchw(yo, y, s);
     });
 }
@@ -422,7 +436,7 @@ int tha4_test_norm(tha4_ctx* ctx, const float* x, int N, int C, int H, int W, in
 int tha4_test_attention(tha4_ctx* ctx, const float* qkv, int N, int C, int heads, float* out, void* stream) {
     return guarded(ctx, [&] {
         cudaStream_t s = (cudaStream_t)stream;
-        ctx->persist.reset(); ctx->scratch.reset();
+        begin_pass(ctx, (cudaStream_t)stream);
         Pool* P = &ctx->persist;
         View q; q.N = N; q.H = 16; q.W = 16; q.C = 3 * C; q.ld = 3 * C; q.p = P->alloc((size_t)N * 256 * 3 * C);
         nchw_to_nhwc(make_img(qkv, N, 3 * C, 16, 16), q, s);

@@ -17,8 +17,16 @@ extern std::atomic<long> g_kernel_launches;   // every kernel this library launc
 struct View {
     float* p = nullptr;
     int N = 0, H = 0, W = 0, C = 0, ld = 0;
+    // Optional per-(n,c) statistics of this tensor: stats[(n * stats_ld + c) * 2 + {0: sum, 1: sum of squares}] (doubles),
+    // zero-initialised by the owner and accumulated by whichever kernel produces the tensor (conv epilogues).
+    // Producers spread their atomics over `stats_rep` replicas (replica r at stats + r * stats_rep_stride) so that
+    // thousands of tiles do not serialise on a handful of L2 lines; consumers add the replicas up.
+    double* stats = nullptr;
+    int stats_ld = 0;
+    int stats_rep = 1;
+    long stats_rep_stride = 0;
     __host__ __device__ long pix(int n, int y, int x) const { return (((long)n * H + y) * W + x) * ld; }
-    View slice(int c0, int c) const { View v = *this; v.p = p + c0; v.C = c; return v; }
+    View slice(int c0, int c) const { View v = *this; v.p = p + c0; v.C = c; if (stats) v.stats = stats + 2 * c0; return v; }
     size_t pixels() const { return (size_t)N * H * W; }
 };
 

@@ -374,6 +374,10 @@ void conv_pack(const ConvWeights& cw, ConvKind kind, const float* w_ref, int w_c
 static bool g_use_tc = true;
 void conv_enable_tc(bool on) { g_use_tc = on; }
 
+bool conv_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
+    return a.out.stats != nullptr && g_use_tc && conv_tc_supported(cw, a) && conv_tc_fuses_stats(cw, a);
+}
+
 void conv_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     if (g_use_tc && conv_tc_supported(cw, a)) conv_tc_forward(cw, a, s);
     else conv_mma_forward(cw, a, s);

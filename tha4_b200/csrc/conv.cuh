@@ -65,6 +65,10 @@ void conv_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);
 void conv_mma_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);     // conv.cu (general shapes, strict mode)
 bool conv_tc_supported(const ConvWeights& cw, const ConvArgs& a);
 void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);      // conv_tc.cu (tcgen05 + TMA + TMEM)
+// True when conv_forward(cw, a) will itself accumulate a.out.stats (tcgen05 epilogue / split-K reduction); otherwise
+// the caller runs norm_stats on the output.
+bool conv_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
+bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
 void conv_enable_tc(bool on);                                                        // default: on
 
 }  // namespace tha4

@@ -34,6 +34,7 @@ struct TcParams {
     int N, MH, MW, tiles_x, tiles_y;
     int ntaps, cpt, ksplit, out_mul;
     float* ws; long ws_rows; int ws_ld;            // split-K partials: ws[z][tile*128 + row][cout_pad]
+    double* stats; int stats_ld; int stats_rep; long stats_rep_stride;   // per-(n,c) sum / sum-of-squares of the output (optional)
     signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
     signed char dx[CONV_MAX_PHASES][CONV_MAX_TAPS];
     signed char ph_oy[CONV_MAX_PHASES], ph_ox[CONV_MAX_PHASES];
@@ -175,50 +176,78 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
             float* orow = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld;
             const bool lead = (split == 0);
+            float* scratch = reinterpret_cast<float*>(smA) + q * (32 * 33);   // pipeline smem is idle once tmem_full fired
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                if (!valid) continue;
                 const int cbase = n0 + c0;
-                if (cbase >= p.outC) continue;
+                if (cbase >= p.outC) continue;                         // warp-uniform
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                 const int cn = min(32, p.outC - cbase);
-                if (lead && !(p.ksplit > 1 && p.ws)) {
-                    if (p.bias) {
+                const bool to_ws = p.ksplit > 1 && p.ws;
+                if (valid) {
+                    if (lead && !to_ws) {
+                        if (p.bias) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
+                            for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
+                        }
+                        if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
+                            const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
+                            const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + cbase;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (j < cn) v[j] += rr[j];
+                        } else if (p.res_mode == RES_DOWN2) {
+                            const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + cbase;
+                            const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < cn) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+                        }
                     }
-                    if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
-                        const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
-                        const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + cbase;
+                    if (to_ws) {
+                        float* wrow = p.ws + ((long)blockIdx.z * p.ws_rows + (long)blockIdx.x * 128 + row) * p.ws_ld + cbase;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += rr[j];
-                    } else if (p.res_mode == RES_DOWN2) {
-                        const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + cbase;
-                        const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(wrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else if (p.ksplit > 1) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < cn) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+                        for (int j = 0; j < 32; ++j) if (j < cn) atomicAdd(orow + cbase + j, v[j]);
+                    } else if (cn == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(orow + cbase + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) orow[cbase + j] = v[j];
                     }
                 }
-                if (p.ksplit > 1 && p.ws) {
-                    float* wrow = p.ws + ((long)blockIdx.z * p.ws_rows + (long)blockIdx.x * 128 + row) * p.ws_ld + cbase;
+                if (p.stats && p.ksplit == 1) {
+                    // per-channel sum / sum of squares over this warp's 32 pixels: transpose through shared memory,
+                    // then lane j reduces channel j; one double atomic pair per (warp, channel).
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(wrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else if (p.ksplit > 1) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (j < cn) atomicAdd(orow + cbase + j, v[j]);
-                } else if (cn == 32) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(orow + cbase + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (j < cn) orow[cbase + j] = v[j];
+                    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = valid ? v[j] : 0.0f;
+                    __syncwarp();
+                    float su = 0.0f, sq = 0.0f;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) { const float t = scratch[rr * 33 + lane]; su += t; sq += t * t; }
+                    __syncwarp();
+                    float2* part = reinterpret_cast<float2*>(reinterpret_cast<float*>(smA) + 4 * 32 * 33);   // [4 warps][BN]
+                    part[q * BN + c0 + lane] = make_float2(su, sq);
+                }
+            }
+            if (p.stats && p.ksplit == 1) {
+                // combine the four warps' partial sums: one double atomic pair per (tile, channel), spread over replicas
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                const float2* part = reinterpret_cast<const float2*>(reinterpret_cast<float*>(smA) + 4 * 32 * 33);
+                double* base = p.stats + (long)(blockIdx.x % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + n0) * 2;
+                for (int c = (warp - 2) * 32 + lane; c < BN; c += 128) {
+                    if (n0 + c >= p.outC) break;
+                    const float2 a = part[c], b = part[BN + c], cc = part[2 * BN + c], d = part[3 * BN + c];
+                    atomicAdd(base + 2 * c, (double)a.x + (double)b.x + (double)cc.x + (double)d.x);
+                    atomicAdd(base + 2 * c + 1, (double)a.y + (double)b.y + (double)cc.y + (double)d.y);
                 }
             }
         }
@@ -230,41 +259,64 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     }
 }
 
-// out = sum_splits ws + bias + res  (deterministic split-K reduction; replaces fp32 atomics)
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcParams p, int nphase, int cout_pad) {
+// out = sum_splits ws + bias + res  (deterministic split-K reduction; replaces fp32 atomics), plus the per-(n,c)
+// statistics of the result.  grid = (pixel slabs, N * nphase); thread (pl, q) walks pixels pl, pl + PL, ... of its slab.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcParams p, int nphase, int ppt) {
+    __shared__ float red[256][9];
     const int cq = (p.outC + 3) >> 2;
-    const long total = (long)nphase * p.N * p.MH * p.MW * cq;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int q = (int)(i % cq);
-        long r = i / cq;
-        const int mx = (int)(r % p.MW); r /= p.MW;
-        const int my = (int)(r % p.MH); r /= p.MH;
-        const int n = (int)(r % p.N);
-        const int phase = (int)(r / p.N);
-        const long tile = ((long)n * p.tiles_y + my / TILE_H) * p.tiles_x + mx / TILE_W;
-        const int row = (my % TILE_H) * TILE_W + mx % TILE_W;
-        const int c = 4 * q;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < p.ksplit; ++s) {
-            const float4 v = *reinterpret_cast<const float4*>(p.ws + ((long)(phase * p.ksplit + s) * p.ws_rows + tile * 128 + row) * p.ws_ld + c);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const int PL = 256 / cq;
+    const int tid = threadIdx.x;
+    const int pl = tid / cq, q = tid - pl * cq;
+    const int n = blockIdx.y / nphase, phase = blockIdx.y % nphase;
+    const bool active = pl < PL;
+    const int c = 4 * q;
+    const int cn = min(4, p.outC - c);
+    float su[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+    if (active) {
+        const long MHW = (long)p.MH * p.MW;
+        const long base = (long)blockIdx.x * PL * ppt;
+        for (int i = 0; i < ppt; ++i) {
+            const long m = base + (long)i * PL + pl;
+            if (m >= MHW) break;
+            const int my = (int)(m / p.MW), mx = (int)(m - (long)my * p.MW);
+            const long tile = ((long)n * p.tiles_y + my / TILE_H) * p.tiles_x + mx / TILE_W;
+            const int row = (my % TILE_H) * TILE_W + mx % TILE_W;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < p.ksplit; ++s) {
+                const float4 v = *reinterpret_cast<const float4*>(p.ws + ((long)(phase * p.ksplit + s) * p.ws_rows + tile * 128 + row) * p.ws_ld + c);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
+            float v[4] = {acc.x, acc.y, acc.z, acc.w};
+            if (p.bias) for (int j = 0; j < cn; ++j) v[j] += __ldg(p.bias + c + j);
+            if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
+                const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
+                const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + c;
+                for (int j = 0; j < cn; ++j) v[j] += rr[j];
+            } else if (p.res_mode == RES_DOWN2) {
+                const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + c;
+                const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
+                for (int j = 0; j < cn; ++j) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+            }
+            float* o = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld + c;
+            if (cn == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            else for (int j = 0; j < cn; ++j) o[j] = v[j];
+            for (int j = 0; j < cn; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
         }
-        const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
-        float v[4] = {acc.x, acc.y, acc.z, acc.w};
-        const int cn = min(4, p.outC - c);
-        if (p.bias) for (int j = 0; j < cn; ++j) v[j] += __ldg(p.bias + c + j);
-        if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
-            const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
-            const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + c;
-            for (int j = 0; j < cn; ++j) v[j] += rr[j];
-        } else if (p.res_mode == RES_DOWN2) {
-            const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + c;
-            const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
-            for (int j = 0; j < cn; ++j) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
-        }
-        float* o = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld + c;
-        if (cn == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        else for (int j = 0; j < cn; ++j) o[j] = v[j];
+    }
+    if (!p.stats) return;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { red[tid][k] = su[k]; red[tid][4 + k] = sq[k]; }
+    __syncthreads();
+    if (active && pl == 0) {
+        double acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+        for (int j = 0; j < PL; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += (double)red[j * cq + q][k];
+        double* d = p.stats + (long)(blockIdx.x % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + c) * 2;
+        for (int k = 0; k < cn; ++k) { atomicAdd(d + 2 * k, acc[k]); atomicAdd(d + 2 * k + 1, acc[4 + k]); }
     }
 }
 
@@ -366,6 +418,12 @@ size_t conv_workspace_floats(const ConvWeights& cw, const ConvArgs& a) {
     return (size_t)cw.nphase * pl.ksplit * pl.tiles_m * 128 * cw.cout_pad;
 }
 
+bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
+    const TcPlan pl = tc_plan(cw, a);
+    if (pl.ksplit == 1) return true;
+    return a.ws && a.ws_floats >= (size_t)cw.nphase * pl.ksplit * pl.tiles_m * 128 * cw.cout_pad;
+}
+
 bool conv_tc_supported(const ConvWeights& cw, const ConvArgs& a) {
     if (a.in_up || cw.stride != 1 || a.strict) return false;
     if (a.in.ld % 4 != 0 || (((uintptr_t)a.in.p) & 15) != 0) return false;
@@ -398,6 +456,9 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     const size_t ws_need = (size_t)cw.nphase * ksplit * tiles_m * 128 * cw.cout_pad;
     const bool use_ws = ksplit > 1 && a.ws && a.ws_floats >= ws_need;
     p.ws = use_ws ? a.ws : nullptr; p.ws_rows = (long)tiles_m * 128; p.ws_ld = cw.cout_pad;
+    // statistics: fused when the result is final in this launch sequence (single pass, or split-K with workspace)
+    p.stats = (ksplit == 1 || use_ws) ? a.out.stats : nullptr; p.stats_ld = a.out.stats_ld;
+    p.stats_rep = std::max(1, a.out.stats_rep); p.stats_rep_stride = a.out.stats_rep_stride;
     ProfScope prof(PROF_CONV, s);
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
     if (ksplit > 1 && !use_ws)
@@ -427,9 +488,14 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
         else launch_tc<32, 3>(ma, mb, p, grid, s);
     }
     if (use_ws) {
-        const long total = (long)cw.nphase * p.N * p.MH * p.MW * ((p.outC + 3) / 4);
-        const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 8);
-        splitk_reduce_kernel<<<blocks, 256, 0, s>>>(p, cw.nphase, cw.cout_pad);
+        const int cq = (p.outC + 3) / 4;
+        THA4_REQUIRE(cq <= 256, "split-K reduce: Cout <= 1024");
+        const int PL = 256 / cq;
+        const long MHW = (long)p.MH * p.MW;
+        // pixels per thread: enough CTAs to fill the GPU on the small layers split-K exists for
+        const int ppt = (int)std::max<long>(1, std::min<long>(16, MHW * p.N * cw.nphase / ((long)PL * 296)));
+        dim3 rgrid(ceil_div(MHW, (long)PL * ppt), p.N * cw.nphase);
+        splitk_reduce_kernel<<<rgrid, 256, 0, s>>>(p, cw.nphase, ppt);
         THA4_LAUNCH_CHECK();
     }
 }

@@ -24,6 +24,14 @@ void Pool::reset() { for (auto& b : blocks_) b.used = false; }
 
 long TensorRef::numel() const { long n = 1; for (long d : shape) n *= d; return n; }
 
+double* Runtime::alloc_stats(size_t n) {
+    THA4_REQUIRE(stats_base != nullptr && stats_off != nullptr, "statistics arena not set up");
+    const size_t off = *stats_off;
+    THA4_REQUIRE(off + n <= stats_cap, "statistics arena exhausted (lower the micro-batch)");
+    *stats_off = off + n;
+    return stats_base + off;
+}
+
 // ------------------------------------------------------------------------------------------------ helpers
 namespace {
 
@@ -109,23 +117,35 @@ __global__ void vec_add_kernel(float* dst, const float* a, const float* b, int n
     if (i < n) dst[i] = a[i] + b[i];
 }
 
-View make_view(Pool* pool, int N, int H, int W, int C) {
+// rt != nullptr: the view also gets a (zeroed) statistics slot, to be filled by the conv that produces the tensor
+View make_view(Pool* pool, int N, int H, int W, int C, Runtime* rt = nullptr) {
     View v; v.N = N; v.H = H; v.W = W; v.C = C; v.ld = C;
     v.p = pool->alloc((size_t)N * H * W * C);
+    if (rt) {   // replicas ~ tiles/16 (128-pixel conv tiles per sample), power of two in [1, 16]
+        const int tiles = ((W + 15) / 16) * ((H + 7) / 8);
+        int rep = 1;
+        while (rep < 16 && rep * 32 <= tiles) rep *= 2;
+        v.stats_rep = rep;
+        v.stats_rep_stride = (long)N * C * 2;
+        v.stats = rt->alloc_stats((size_t)rep * N * C * 2);
+        v.stats_ld = C;
+    }
     return v;
 }
 
-// statistics -> per-(n,c) affine (InstanceNorm when groups == 0, GroupNorm otherwise), from the scratch pool
-float* norm_coef(Runtime& rt, const View& x, const NormW& nw, int groups, const float* film0, const float* film1,
-                 int film1_ld) {
+// per-(n,c) affine for the fused tail kernels (InstanceNorm when groups == 0, GroupNorm otherwise)
+float* tail_coef(Runtime& rt, const View& x, const NormW& nw, int groups) {
     THA4_REQUIRE(nw.C == x.C, "norm: channel mismatch");
-    const size_t n = (size_t)x.N * x.C * 2;
-    double* sums = rt.scratch->alloc_f64(n);
-    THA4_CUDA_CHECK(cudaMemsetAsync(sums, 0, n * sizeof(double), rt.stream));
-    norm_stats(x, sums, rt.stream);
-    float* coef = rt.scratch->alloc(n);
-    norm_finalize(sums, x.N, x.C, x.H * x.W, groups, nw.gamma, nw.beta, film0, film1, film1_ld, coef, rt.stream);
+    float* coef = rt.scratch->alloc((size_t)x.N * x.C * 2);
+    norm_finalize(x, groups, nw.gamma, nw.beta, nullptr, nullptr, 0, coef, rt.stream);
     return coef;
+}
+
+// normalisation layer = one elementwise pass: affine from x.stats rebuilt per CTA, activation / pool / residual fused
+void run_norm(Runtime& rt, const View& x, const NormW& nw, int groups, const float* film0, const float* film1,
+              int film1_ld, int act, int pool, const View* res, const View& y) {
+    THA4_REQUIRE(nw.C == x.C, "norm: channel mismatch");
+    norm_apply_fused(x, groups, nw.gamma, nw.beta, film0, film1, film1_ld, act, pool, res, y, rt.stream, !rt.strict);
 }
 
 void run_conv(Runtime& rt, const ConvWeights& cw, const View& in, const View& out, int in_up = 0,
@@ -135,7 +155,9 @@ void run_conv(Runtime& rt, const ConvWeights& cw, const View& in, const View& ou
     if (res) { a.res = *res; a.res_mode = res_mode; }
     const size_t ws = conv_workspace_floats(cw, a);
     if (ws) { a.ws = rt.scratch->alloc(ws); a.ws_floats = ws; }
+    const bool fused = conv_fuses_stats(cw, a);
     conv_forward(cw, a, rt.stream);
+    if (out.stats && !fused) norm_stats(out, rt.stream);      // mma.sync path (strict mode, stride-2 convs)
 }
 
 }  // namespace
@@ -205,11 +227,10 @@ void EncDecNet::forward(Runtime& rt, const ImgView& image0, const ImgView& image
     }
     // conv -> InstanceNorm -> ReLU; the activated tensor goes to `dst`
     auto conv_in_relu = [&](const ConvWeights& cw, const NormW& nw, const View& in, int oh, const View* dst) -> View {
-        View raw = make_view(P, B, oh, oh, cw.cout);
+        View raw = make_view(P, B, oh, oh, cw.cout, &rt);
         run_conv(rt, cw, in, raw);
-        float* coef = norm_coef(rt, raw, nw, 0, nullptr, nullptr, 0);
         const View& y = dst ? *dst : raw;
-        norm_apply(raw, coef, ACT_RELU, 0, nullptr, y, s, !rt.strict);
+        run_norm(rt, raw, nw, 0, nullptr, nullptr, 0, ACT_RELU, 0, nullptr, y);
         return y;
     };
     View f = conv_in_relu(down_[0], down_n_[0], x0, S_, nullptr);
@@ -223,18 +244,17 @@ void EncDecNet::forward(Runtime& rt, const ImgView& image0, const ImgView& image
     View x = conv_in_relu(bott0_, bott0_n_, bin, b, nullptr);
     for (int i = 0; i < 5; ++i) {   // ResnetBlock: x + IN(conv(relu(IN(conv(x)))))  (resnet_block.py:52-67)
         View h = conv_in_relu(res_[i][0], res_n_[i][0], x, b, nullptr);
-        View raw = make_view(P, B, b, b, 512);
+        View raw = make_view(P, B, b, b, 512, &rt);
         run_conv(rt, res_[i][1], h, raw);
-        float* coef = norm_coef(rt, raw, res_n_[i][1], 0, nullptr, nullptr, 0);
-        norm_apply(raw, coef, ACT_NONE, 0, &x, raw, s, !rt.strict);
+        run_norm(rt, raw, res_n_[i][1], 0, nullptr, nullptr, 0, ACT_NONE, 0, &x, raw);
         x = raw;
     }
     x = conv_in_relu(up_[0], up_n_[0], x, b * 2, nullptr);
     x = conv_in_relu(up_[1], up_n_[1], x, b * 4, nullptr);
     // last block: leave InstanceNorm + ReLU pending; the tail kernel applies them while staging its halo tile
-    View raw = make_view(P, B, S_, S_, 64);
+    View raw = make_view(P, B, S_, S_, 64, &rt);
     run_conv(rt, up_[2], x, raw);
-    float* coef = norm_coef(rt, raw, up_n_[2], 0, nullptr, nullptr, 0);
+    float* coef = tail_coef(rt, raw, up_n_[2], 0);
     tail_forward(kind_, tail_, raw, coef, ACT_RELU, image0, image1, outputs, s);
 }
 
@@ -369,15 +389,13 @@ void UNetNet::res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode
     THA4_REQUIRE(x.C == w.cin && out.C == w.cout, "res_block: channels");
     const int B = x.N;
     // norm0 -> SiLU -> (avg-pool) ; the nearest-upsample is folded into conv0's gather
-    float* coef0 = norm_coef(rt, x, w.norm0, 32, nullptr, nullptr, 0);
     const int th = (mode == 2) ? x.H / 2 : x.H;
     View t0 = make_view(rt.scratch, B, th, th, w.cin);
-    norm_apply(x, coef0, ACT_SILU, mode == 2 ? 1 : 0, nullptr, t0, s, !rt.strict);
-    View h = make_view(rt.scratch, B, out.H, out.W, w.cout);
+    run_norm(rt, x, w.norm0, 32, nullptr, nullptr, 0, ACT_SILU, mode == 2 ? 1 : 0, nullptr, t0);
+    View h = make_view(rt.scratch, B, out.H, out.W, w.cout, &rt);
     run_conv(rt, w.conv0, t0, h);      // mode 1: conv0 was packed as CONV_UP2_3x3 (upsample folded into 4 phases)
     // norm1 -> FiLM(time) -> FiLM(pose) -> SiLU, folded into one per-(n,c) affine
-    float* coef1 = norm_coef(rt, h, w.norm1, 32, w.film0, film1 + w.film1_off, film1_total_);
-    norm_apply(h, coef1, ACT_SILU, 0, nullptr, h, s, !rt.strict);
+    run_norm(rt, h, w.norm1, 32, w.film0, film1 + w.film1_off, film1_total_, ACT_SILU, 0, nullptr, h);
     if (w.has_skip) {
         THA4_REQUIRE(mode == 0, "res_block: skip conv only on same-resolution blocks");
         View sk = make_view(rt.scratch, B, x.H, x.W, w.cout);
@@ -392,9 +410,8 @@ void UNetNet::res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode
 void UNetNet::attn_block(Runtime& rt, const AttnW& w, const View& x, const View& out) {
     cudaStream_t s = rt.stream;
     rt.scratch->reset();
-    float* coef = norm_coef(rt, x, w.norm, 32, nullptr, nullptr, 0);
     View t = make_view(rt.scratch, x.N, x.H, x.W, x.C);
-    norm_apply(x, coef, ACT_NONE, 0, nullptr, t, s, !rt.strict);
+    run_norm(rt, x, w.norm, 32, nullptr, nullptr, 0, ACT_NONE, 0, nullptr, t);
     View qkv = make_view(rt.scratch, x.N, x.H, x.W, 3 * x.C);
     run_conv(rt, w.qkv, t, qkv);
     View a = make_view(rt.scratch, x.N, x.H, x.W, x.C);
@@ -444,7 +461,7 @@ void UNetNet::forward(Runtime& rt, const ImgView& image, const float* coarse_pos
         ch_h[j] = (j == 0) ? mc_ * mults_[L_ - 1] : ((j & 1) ? mc_ * mults_[lvl] : mc_ * mults_[lvl + 1]);
         const int cs = hs_ch[NH - 1 - j];
         THA4_REQUIRE(ch_h[j] + cs == up_res_[j].cin, "unet: concat plan does not match weights");
-        cat[j] = make_view(P, B, sp, sp, ch_h[j] + cs);
+        cat[j] = make_view(P, B, sp, sp, ch_h[j] + cs, &rt);
         hs[NH - 1 - j] = cat[j].slice(ch_h[j], cs);
     }
 
@@ -453,7 +470,7 @@ void UNetNet::forward(Runtime& rt, const ImgView& image, const float* coarse_pos
     View cur = hs[0];
     for (int i = 0; i < L_; ++i) {
         if (i == L_ - 1) {
-            View tmp = make_view(P, B, cur.H, cur.W, down_res_[i].cout);
+            View tmp = make_view(P, B, cur.H, cur.W, down_res_[i].cout, &rt);
             res_block(rt, down_res_[i], cur, 0, film1, tmp);
             attn_block(rt, down_attn_, tmp, hs[2 * i + 1]);
         } else {
@@ -468,11 +485,11 @@ void UNetNet::forward(Runtime& rt, const ImgView& image, const float* coarse_pos
     // ---- middle: Res, Attn, Res, Attn, Res, Attn, Res (unet.py:481-498) ----
     for (int j = 0; j < 4; ++j) {
         const bool last = (j == 3);
-        View r = last ? cat[0].slice(0, ch_h[0]) : make_view(P, B, cur.H, cur.W, cur.C);
+        View r = last ? cat[0].slice(0, ch_h[0]) : make_view(P, B, cur.H, cur.W, cur.C, &rt);
         res_block(rt, mid_res_[j], cur, 0, film1, r);
         cur = r;
         if (!last) {
-            View a = make_view(P, B, cur.H, cur.W, cur.C);
+            View a = make_view(P, B, cur.H, cur.W, cur.C, &rt);
             attn_block(rt, mid_attn_[j], cur, a);
             cur = a;
         }
@@ -485,9 +502,9 @@ void UNetNet::forward(Runtime& rt, const ImgView& image, const float* coarse_pos
         const int co = up_res_[j].cout;
         View dst;
         if (!second) dst = cat[j + 1].slice(0, ch_h[j + 1]);
-        else dst = make_view(P, B, cat[j].H, cat[j].W, co);      // goes to the upsampler or is the final feature
+        else dst = make_view(P, B, cat[j].H, cat[j].W, co, &rt);      // goes to the upsampler or is the final feature
         if (lvl == L_ - 1) {
-            View tmp = make_view(P, B, cat[j].H, cat[j].W, co);
+            View tmp = make_view(P, B, cat[j].H, cat[j].W, co, &rt);
             res_block(rt, up_res_[j], cat[j], 0, film1, tmp);
             attn_block(rt, up_attn_[second ? 1 : 0], tmp, dst);
         } else {
@@ -500,7 +517,7 @@ void UNetNet::forward(Runtime& rt, const ImgView& image, const float* coarse_pos
     }
     // ---- last: GroupNorm + SiLU pending, applied inside the fused tail (unet.py:526-529; morpher_00.py:53-58) ----
     rt.scratch->reset();
-    float* coef = norm_coef(rt, feat, last_n_, 32, nullptr, nullptr, 0);
+    float* coef = tail_coef(rt, feat, last_n_, 32);
     ImgView none{};
     tail_forward(TAIL_UNET, tail_, feat, coef, ACT_SILU, image, none, outputs, s);
 }

@@ -36,6 +36,11 @@ struct Runtime {                      // per-call execution context
     Pool* scratch;
     cudaStream_t stream;
     int strict;
+    // zero-initialised arena for per-(n,c) statistics (View::stats); bump-allocated, re-zeroed by the caller per pass
+    double* stats_base = nullptr;
+    size_t stats_cap = 0;
+    size_t* stats_off = nullptr;
+    double* alloc_stats(size_t n);
 };
 
 // ------------------------------------------------------------------ encoder-decoder networks

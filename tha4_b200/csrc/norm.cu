@@ -1,5 +1,7 @@
 // InstanceNorm2d / GroupNorm32 (+FiLM, +activation, +2x2 mean pool, +residual) on NHWC fp32 activations.
-// Three small HBM-bound kernels: per-(n,c) sum / sum-of-squares -> per-(n,c) affine -> elementwise apply.
+// Statistics are per-(n,c) sum / sum-of-squares in double precision, normally accumulated by the producing conv's
+// epilogue (conv_tc.cu); norm_stats is the stand-alone fallback.  norm_apply_fused turns them into the per-(n,c)
+// affine inside the apply kernel, so a normalisation layer costs exactly one elementwise pass over the tensor.
 #include "ops.cuh"
 #include "profiler.cuh"
 
@@ -9,7 +11,7 @@ namespace {
 constexpr int STAT_PIX_PER_THREAD = 32;
 
 __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict__ x, int HW, int C, int ld,
-                                                         double* __restrict__ sums) {
+                                                         double* __restrict__ sums, int stats_ld, int rep, long rep_stride) {
     __shared__ float red[256][9];
     const int cq = C >> 2;
     const int PL = 256 / cq;
@@ -41,7 +43,7 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict
         for (int j = 0; j < PL; ++j)
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] += (double)red[j * cq + q][k];
-        double* dst = sums + ((long)n * C + 4 * q) * 2;
+        double* dst = sums + (long)(blockIdx.x % rep) * rep_stride + ((long)n * stats_ld + 4 * q) * 2;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             atomicAdd(dst + 2 * k, acc[k]);
@@ -50,47 +52,99 @@ __global__ void __launch_bounds__(256) norm_stats_kernel(const float* __restrict
     }
 }
 
-__global__ void norm_finalize_kernel(const double* __restrict__ sums, int C, int HW, int groups,
+// per-(n,c) affine from the statistics (shared by the finalize kernel and the fused apply kernel)
+__device__ __forceinline__ float2 norm_affine(const double* __restrict__ sums, int stats_ld, int rep, long rep_stride,
+                                              int n, int c, int C, int HW, int groups, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                              const float* __restrict__ film0, const float* __restrict__ film1, int film1_ld) {
+    double su = 0.0, sq = 0.0, cnt;
+    const int cpg = groups == 0 ? 1 : C / groups, g0 = (c / cpg) * cpg;
+    for (int r = 0; r < rep; ++r) {
+        const double* sn = sums + r * rep_stride + (long)n * stats_ld * 2;
+        for (int j = 0; j < cpg; ++j) { su += sn[2 * (g0 + j)]; sq += sn[2 * (g0 + j) + 1]; }
+    }
+    cnt = (double)HW * cpg;
+    const double mean = su / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    float A = rstd * gamma[c];
+    float B = beta[c] - (float)mean * A;
+    if (film0) { const float sc = 1.0f + film0[c], sh = film0[C + c]; A *= sc; B = B * sc + sh; }
+    if (film1) { const float* f = film1 + (long)n * film1_ld; const float sc = 1.0f + f[c], sh = f[C + c]; A *= sc; B = B * sc + sh; }
+    return make_float2(A, B);
+}
+
+__global__ void norm_finalize_kernel(const double* __restrict__ sums, int stats_ld, int rep, long rep_stride, int C, int HW, int groups,
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      const float* __restrict__ film0, const float* __restrict__ film1, int film1_ld,
                                      float* __restrict__ coef) {
     const int n = blockIdx.x;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double su = 0.0, sq = 0.0, cnt;
-        if (groups == 0) {
-            su = sums[((long)n * C + c) * 2]; sq = sums[((long)n * C + c) * 2 + 1]; cnt = (double)HW;
-        } else {
-            const int cpg = C / groups, g0 = (c / cpg) * cpg;
-            for (int j = 0; j < cpg; ++j) { su += sums[((long)n * C + g0 + j) * 2]; sq += sums[((long)n * C + g0 + j) * 2 + 1]; }
-            cnt = (double)HW * cpg;
-        }
-        const double mean = su / cnt;
-        double var = sq / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-        float A = rstd * gamma[c];
-        float B = beta[c] - (float)mean * A;
-        if (film0) { const float sc = 1.0f + film0[c], sh = film0[C + c]; A *= sc; B = B * sc + sh; }
-        if (film1) { const float* f = film1 + (long)n * film1_ld; const float sc = 1.0f + f[c], sh = f[C + c]; A *= sc; B = B * sc + sh; }
-        coef[((long)n * C + c) * 2] = A;
-        coef[((long)n * C + c) * 2 + 1] = B;
+        const float2 ab = norm_affine(sums, stats_ld, rep, rep_stride, n, c, C, HW, groups, gamma, beta, film0, film1, film1_ld);
+        coef[((long)n * C + c) * 2] = ab.x;
+        coef[((long)n * C + c) * 2 + 1] = ab.y;
     }
 }
 
+// FUSED == true: coefficients come from shared memory (computed from the statistics by this CTA, grid.y = sample);
+// FUSED == false: from the coef array in global memory (grid.y == 1, samples flattened).
+template <bool FUSED>
 __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ x, int xH, int xW, int x_ld,
                                                          const float* __restrict__ coef, int act, int pool,
                                                          const float* __restrict__ res, int res_ld,
                                                          float* __restrict__ y, int yH, int yW, int y_ld, int C, long total,
-                                                         int round_out) {
+                                                         int round_out,
+                                                         const double* __restrict__ sums, int stats_ld, int rep, long rep_stride,
+                                                         int HW, int groups,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ film0, const float* __restrict__ film1,
+                                                         int film1_ld) {
+    extern __shared__ float2 sm_coef[];
     const int cq = C >> 2;
+    int n_fixed = 0;
+    if (FUSED) {
+        // two-step prologue: (1) mean / rstd per statistics group (channel for InstanceNorm, channel group for GroupNorm)
+        // into shared memory, (2) per-channel affine incl. gamma/beta and the FiLM scale-shifts.
+        n_fixed = blockIdx.y;
+        float2* sm_grp = sm_coef + C;                          // [ngroups] (mean, rstd)
+        const int ng = groups == 0 ? C : groups, cpg = C / ng;
+        for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+            double su = 0.0, sq = 0.0;
+            for (int r = 0; r < rep; ++r) {
+                const double* sn = sums + r * rep_stride + ((long)n_fixed * stats_ld + (long)g * cpg) * 2;
+                for (int j = 0; j < cpg; ++j) { su += sn[2 * j]; sq += sn[2 * j + 1]; }
+            }
+            const double cnt = (double)HW * cpg;
+            const double mean = su / cnt;
+            double var = sq / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            sm_grp[g] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float2 mr = sm_grp[c / cpg];
+            float A = mr.y * gamma[c];
+            float B = beta[c] - mr.x * A;
+            if (film0) { const float sc = 1.0f + film0[c], sh = film0[C + c]; A *= sc; B = B * sc + sh; }
+            if (film1) { const float* f = film1 + (long)n_fixed * film1_ld; const float sc = 1.0f + f[c], sh = f[C + c]; A *= sc; B = B * sc + sh; }
+            sm_coef[c] = make_float2(A, B);
+        }
+        __syncthreads();
+    }
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int q = (int)(i % cq);
         long pix = i / cq;
         const int ox = (int)(pix % yW); pix /= yW;
         const int oy = (int)(pix % yH);
-        const int n = (int)(pix / yH);
-        const float4 c0 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2);
-        const float4 c1 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2 + 4);
+        const int n = FUSED ? n_fixed : (int)(pix / yH);
+        float4 c0, c1;
+        if (FUSED) {
+            const float2 a = sm_coef[4 * q], b = sm_coef[4 * q + 1], c = sm_coef[4 * q + 2], d = sm_coef[4 * q + 3];
+            c0 = make_float4(a.x, a.y, b.x, b.y); c1 = make_float4(c.x, c.y, d.x, d.y);
+        } else {
+            c0 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2);
+            c1 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2 + 4);
+        }
         float4 r;
         if (!pool) {
             const float4 v = *reinterpret_cast<const float4*>(x + (((long)n * xH + oy) * xW + ox) * x_ld + 4 * q);
@@ -118,38 +172,63 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
     }
 }
 
+void check_apply(const View& x, int pool, const View* res, const View& y) {
+    THA4_REQUIRE(x.C == y.C && x.C % 4 == 0 && x.ld % 4 == 0 && y.ld % 4 == 0, "norm_apply: channels");
+    if (pool) THA4_REQUIRE(y.H * 2 == x.H && y.W * 2 == x.W, "norm_apply: pool dims");
+    else THA4_REQUIRE(y.H == x.H && y.W == x.W, "norm_apply: dims");
+    if (res) THA4_REQUIRE(res->H == y.H && res->W == y.W && res->C == y.C && res->ld % 4 == 0, "norm_apply: res dims");
+}
+
 }  // namespace
 
-void norm_stats(const View& x, double* sums, cudaStream_t s) {
+void norm_stats(const View& x, cudaStream_t s) {
+    THA4_REQUIRE(x.stats != nullptr, "norm_stats: view has no statistics buffer");
     THA4_REQUIRE(x.C % 4 == 0 && x.C <= 1024 && x.ld % 4 == 0, "norm_stats: channels");
     const int cq = x.C / 4, PL = 256 / cq;
     const int HW = x.H * x.W;
     dim3 grid(ceil_div(HW, PL * STAT_PIX_PER_THREAD), x.N);
     ProfScope prof(PROF_NORM, s);
     prof_add_work(PROF_NORM, 0.0, (double)x.pixels() * x.C * 4);
-    norm_stats_kernel<<<grid, 256, 0, s>>>(x.p, HW, x.C, x.ld, sums);
+    norm_stats_kernel<<<grid, 256, 0, s>>>(x.p, HW, x.C, x.ld, x.stats, x.stats_ld, x.stats_rep, x.stats_rep_stride);
     THA4_LAUNCH_CHECK();
 }
 
-void norm_finalize(const double* sums, int N, int C, int HW, int groups, const float* gamma, const float* beta,
+void norm_finalize(const View& x, int groups, const float* gamma, const float* beta,
                    const float* film0, const float* film1, int film1_ld, float* coef, cudaStream_t s) {
-    THA4_REQUIRE(groups == 0 || C % groups == 0, "norm_finalize: groups");
-    norm_finalize_kernel<<<N, 256, 0, s>>>(sums, C, HW, groups, gamma, beta, film0, film1, film1_ld, coef);
+    THA4_REQUIRE(x.stats != nullptr, "norm_finalize: view has no statistics");
+    THA4_REQUIRE(groups == 0 || x.C % groups == 0, "norm_finalize: groups");
+    norm_finalize_kernel<<<x.N, 256, 0, s>>>(x.stats, x.stats_ld, x.stats_rep, x.stats_rep_stride, x.C, x.H * x.W, groups, gamma, beta, film0, film1, film1_ld, coef);
     THA4_LAUNCH_CHECK();
 }
 
 void norm_apply(const View& x, const float* coef, int act, int pool, const View* res, const View& y, cudaStream_t s,
                 int round_out) {
-    THA4_REQUIRE(x.C == y.C && x.C % 4 == 0 && x.ld % 4 == 0 && y.ld % 4 == 0, "norm_apply: channels");
-    if (pool) THA4_REQUIRE(y.H * 2 == x.H && y.W * 2 == x.W, "norm_apply: pool dims");
-    else THA4_REQUIRE(y.H == x.H && y.W == x.W, "norm_apply: dims");
-    if (res) THA4_REQUIRE(res->H == y.H && res->W == y.W && res->C == y.C && res->ld % 4 == 0, "norm_apply: res dims");
+    check_apply(x, pool, res, y);
     const long total = (long)y.N * y.H * y.W * (y.C / 4);
     const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
     ProfScope prof(PROF_NORM, s);
     prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() + y.pixels() + (res ? y.pixels() : 0)) * x.C * 4);
-    norm_apply_kernel<<<blocks, 256, 0, s>>>(x.p, x.H, x.W, x.ld, coef, act, pool, res ? res->p : nullptr,
-                                             res ? res->ld : 0, y.p, y.H, y.W, y.ld, x.C, total, round_out);
+    norm_apply_kernel<false><<<blocks, 256, 0, s>>>(x.p, x.H, x.W, x.ld, coef, act, pool, res ? res->p : nullptr,
+                                                    res ? res->ld : 0, y.p, y.H, y.W, y.ld, x.C, total, round_out,
+                                                    nullptr, 0, 1, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0);
+    THA4_LAUNCH_CHECK();
+}
+
+void norm_apply_fused(const View& x, int groups, const float* gamma, const float* beta, const float* film0,
+                      const float* film1, int film1_ld, int act, int pool, const View* res, const View& y, cudaStream_t s,
+                      int round_out) {
+    check_apply(x, pool, res, y);
+    THA4_REQUIRE(x.stats != nullptr, "norm_apply_fused: view has no statistics");
+    THA4_REQUIRE(groups == 0 || x.C % groups == 0, "norm_apply_fused: groups");
+    const long per_sample = (long)y.H * y.W * (y.C / 4);
+    const int bx = (int)std::max<long>(1, std::min<long>((per_sample + 255) / 256, std::max(1, 148 * 16 / y.N)));
+    ProfScope prof(PROF_NORM, s);
+    prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() + y.pixels() + (res ? y.pixels() : 0)) * x.C * 4);
+    // per-sample pointers: grid.y selects the sample, the kernel indexes within it
+    dim3 grid(bx, y.N);
+    norm_apply_kernel<true><<<grid, 256, 2 * x.C * sizeof(float2), s>>>(
+        x.p, x.H, x.W, x.ld, nullptr, act, pool, res ? res->p : nullptr, res ? res->ld : 0, y.p, y.H, y.W, y.ld, x.C, per_sample,
+        round_out, x.stats, x.stats_ld, x.stats_rep, x.stats_rep_stride, x.H * x.W, groups, gamma, beta, film0, film1, film1_ld);
     THA4_LAUNCH_CHECK();
 }
 

@@ -6,16 +6,21 @@
 namespace tha4 {
 
 // ---------------------------------------------------------------- normalisation (norm.cu)
-// sums: [N][C][2] doubles (sum, sum of squares), must be zero on entry.
-void norm_stats(const View& x, double* sums, cudaStream_t s);
+// Accumulates per-(n,c) sum / sum of squares of x into x.stats (must be zero on entry).  Only needed for tensors whose
+// producer did not already do it (the tcgen05 conv epilogue and the split-K reduction accumulate them for free).
+void norm_stats(const View& x, cudaStream_t s);
 
 // Turns the statistics into a per-(n,c) affine  y = x * A + B  that folds InstanceNorm2d / GroupNorm (eps 1e-5,
 // biased variance; nn/normalization.py:94-95, unet.py:65-66) with gamma/beta and up to two FiLM scale-shifts
 // h*(1+s)+b (unet.py:90-97,159-163).  coef: [N][C][2] floats.
 //   groups == 0: instance norm (one group per channel).  film0: [2C] shared by all samples (the t=0 time embedding
 //   is a constant); film1: [N][film1_ld] with this block's 2C vector at film1 + n*film1_ld.
-void norm_finalize(const double* sums, int N, int C, int HW, int groups, const float* gamma, const float* beta,
+void norm_finalize(const View& x, int groups, const float* gamma, const float* beta,
                    const float* film0, const float* film1, int film1_ld, float* coef, cudaStream_t s);
+// norm_finalize + norm_apply in one launch: every CTA rebuilds the affine of its sample in shared memory from x.stats.
+void norm_apply_fused(const View& x, int groups, const float* gamma, const float* beta, const float* film0,
+                      const float* film1, int film1_ld, int act, int pool, const View* res, const View& y, cudaStream_t s,
+                      int round_out);
 
 // y = act(x * A + B) (+ res).  pool == 1: y has half the resolution and is the 2x2 mean of the activated values
 // (AvgPool2d(2) after SiLU, unet.py:58,158).  x and y may alias when pool == 0.
