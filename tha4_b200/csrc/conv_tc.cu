@@ -466,11 +466,16 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     const CUtensorMap& ma = activation_map(a.in);
     const CUtensorMap& mb = weight_map(cw, bn);
     dim3 grid(tiles_m, tiles_n, cw.nphase * ksplit);
-    static int stages_mode = -1;     // experiment knob: THA4_TC_STAGES=deep|mid|shallow
-    if (stages_mode < 0) {
+    // Pipeline depth: grids that cannot even fill the GPU once (the B=1 bottleneck layers, which stream their weights
+    // from HBM with one CTA per SM) get a deep TMA ring to hide DRAM latency; large grids get a shallow ring so that
+    // 2-3 CTAs share an SM and overlap each other's prologue / epilogue.  THA4_TC_STAGES=deep|mid|shallow overrides.
+    static int forced = -2;
+    if (forced == -2) {
         const char* e = getenv("THA4_TC_STAGES");
-        stages_mode = (e && !strcmp(e, "deep")) ? 0 : ((e && !strcmp(e, "mid")) ? 1 : 2);   // default: shallow (2-3 CTAs/SM)
+        forced = !e ? -1 : (!strcmp(e, "deep") ? 0 : (!strcmp(e, "mid") ? 1 : 2));
     }
+    const long total_ctas = (long)grid.x * grid.y * grid.z;
+    const int stages_mode = forced >= 0 ? forced : (total_ctas <= 160 ? 0 : 2);
     if (stages_mode == 0) {
         if (bn == 256) launch_tc<256, 4>(ma, mb, p, grid, s);
         else if (bn == 128) launch_tc<128, 6>(ma, mb, p, grid, s);

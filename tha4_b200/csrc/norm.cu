@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ film0, const float* __restrict__ film1,
                                                          int film1_ld) {
-    extern __shared__ float2 sm_coef[];
+    extern __shared__ __align__(16) float2 sm_coef[];
     const int cq = C >> 2;
     int n_fixed = 0;
     if (FUSED) {
@@ -131,26 +131,29 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
         }
         __syncthreads();
     }
+    const unsigned ucq = (unsigned)cq;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        const int q = (int)(i % cq);
-        long pix = i / cq;
-        const int ox = (int)(pix % yW); pix /= yW;
-        const int oy = (int)(pix % yH);
-        const int n = FUSED ? n_fixed : (int)(pix / yH);
+        // i enumerates (pixel, channel quad) of the output; samples are folded into `pix` (FUSED: offset by n_fixed)
+        const long pix0 = (long)((unsigned long long)i / ucq);
+        const int q = (int)(i - pix0 * ucq);
+        const long pix = FUSED ? pix0 + (long)n_fixed * yH * yW : pix0;
+        const int n = FUSED ? n_fixed : (int)(pix0 / ((long)yH * yW));
         float4 c0, c1;
         if (FUSED) {
-            const float2 a = sm_coef[4 * q], b = sm_coef[4 * q + 1], c = sm_coef[4 * q + 2], d = sm_coef[4 * q + 3];
-            c0 = make_float4(a.x, a.y, b.x, b.y); c1 = make_float4(c.x, c.y, d.x, d.y);
+            const float4* sc = reinterpret_cast<const float4*>(sm_coef + 4 * q);
+            c0 = sc[0]; c1 = sc[1];
         } else {
             c0 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2);
             c1 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2 + 4);
         }
         float4 r;
         if (!pool) {
-            const float4 v = *reinterpret_cast<const float4*>(x + (((long)n * xH + oy) * xW + ox) * x_ld + 4 * q);
+            const float4 v = *reinterpret_cast<const float4*>(x + pix * x_ld + 4 * q);
             r.x = act_apply(v.x * c0.x + c0.y, act); r.y = act_apply(v.y * c0.z + c0.w, act);
             r.z = act_apply(v.z * c1.x + c1.y, act); r.w = act_apply(v.w * c1.z + c1.w, act);
         } else {
+            const long pin = pix0 - (long)(FUSED ? 0 : n) * yH * yW;       // pixel index within the sample
+            const int oy = (int)(pin / yW), ox = (int)(pin - (long)oy * yW);
             r = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy)
@@ -164,11 +167,11 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
             r.x *= 0.25f; r.y *= 0.25f; r.z *= 0.25f; r.w *= 0.25f;
         }
         if (res) {
-            const float4 v = *reinterpret_cast<const float4*>(res + (((long)n * yH + oy) * yW + ox) * res_ld + 4 * q);
+            const float4 v = *reinterpret_cast<const float4*>(res + pix * res_ld + 4 * q);
             r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
         }
         if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-        *reinterpret_cast<float4*>(y + (((long)n * yH + oy) * yW + ox) * y_ld + 4 * q) = r;
+        *reinterpret_cast<float4*>(y + pix * y_ld + 4 * q) = r;
     }
 }
 

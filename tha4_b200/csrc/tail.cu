@@ -6,7 +6,10 @@
 //   coalesced NCHW stores of all outputs.
 // Reference: eyebrow_decomposer_00.py:46-64, eyebrow_morphing_combiner_00.py:51-72, face_morpher_08.py:170-193,
 // morpher_00.py:53-66, upscaler_02.py:84-96.
-// v1: CUDA-core FFMA head conv from a shared-memory halo tile (16x16 output pixels per CTA).
+// The 3x3 head conv runs on tensor cores (mma.sync m16n8k8 TF32, M = 16 pixels of one tile row, N = 8 / 16 head
+// channels, K = 9 taps x C) straight from the shared-memory halo tile; accumulators are transposed through shared
+// memory so that one thread owns all head channels of one pixel for the warp / blend epilogue.  The kernel is
+// HBM-bound by design: feature map + image read once, every returned tensor written once.
 #include "ops.cuh"
 #include "gridsample.cuh"
 #include "profiler.cuh"
@@ -16,13 +19,29 @@ namespace {
 
 constexpr int TILE = 16, HALO = TILE + 2;
 constexpr int CO_PAD = TAIL_CO_PAD;
+constexpr int WPITCH = 24;      // floats per (tap, channel) row of the staged weights: conflict-free B-fragment loads
+constexpr int OPITCH = 17;      // floats per pixel of the transposed accumulators
 
 __device__ __forceinline__ void store4(float* out, long plane, long pix, const float (&v)[4]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[c * plane + pix] = v[c];
 }
 
-template <int KIND>
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// 3xTF32 split of an fp32 value (hi + lo), so that the head conv keeps fp32 accuracy on the tensor cores
+__device__ __forceinline__ void split_tf32(float v, unsigned& hi, unsigned& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(hi) : "f"(v));
+    const float r = v - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(lo) : "f"(r));
+}
+
+template <int KIND, int NT>
 __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ feat, int S, int C, int ld,
                                                    const float* __restrict__ coef, int act,
                                                    const float* __restrict__ wg, const float* __restrict__ bg,
@@ -30,15 +49,21 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea
                                                    float* o0, float* o1, float* o2, float* o3, float* o4, float* o5,
                                                    float* o6, float* o7) {
     extern __shared__ __align__(16) float sm[];
-    const int CP = C + 1;
-    float* wsm = sm;                          // [9*C][CO_PAD]
-    float* fsm = sm + 9 * C * CO_PAD;         // [HALO*HALO][CP]
-    const int tid = threadIdx.x;
+    const int CP = C + 4;                     // halo pixel pitch: (4*g + t) mod 32 distinct for the A fragments
+    float* wsm = sm;                          // [9*C][WPITCH]
+    float* fsm = sm + 9 * C * WPITCH;         // [HALO*HALO][CP]
+    float* osm = fsm;                         // [256][OPITCH], reuses the halo tile after the MMAs
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
     const int n = blockIdx.z;
     const int by0 = blockIdx.y * TILE, bx0 = blockIdx.x * TILE;
 
-    for (int i = tid; i < 9 * C * CO_PAD / 4; i += 256)
-        reinterpret_cast<float4*>(wsm)[i] = reinterpret_cast<const float4*>(wg)[i];
+    for (int i = tid; i < 9 * C * (CO_PAD / 4); i += 256) {
+        const int row = i / (CO_PAD / 4), part = i - row * (CO_PAD / 4);
+        *reinterpret_cast<float4*>(wsm + row * WPITCH + 4 * part) = *reinterpret_cast<const float4*>(wg + row * CO_PAD + 4 * part);
+    }
+    if (CO_PAD < 16)
+        for (int i = tid; i < 9 * C; i += 256) *reinterpret_cast<float4*>(wsm + i * WPITCH + 12) = make_float4(0.f, 0.f, 0.f, 0.f);
     const int cq = C >> 2;
     for (int i = tid; i < HALO * HALO * cq; i += 256) {
         const int q = i % cq, hp = i / cq;
@@ -52,30 +77,64 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea
             v.x = act_apply(v.x * c0.x + c0.y, act); v.y = act_apply(v.y * c0.z + c0.w, act);
             v.z = act_apply(v.z * c1.x + c1.y, act); v.w = act_apply(v.w * c1.z + c1.w, act);
         }
-        float* d = fsm + hp * CP + 4 * q;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        *reinterpret_cast<float4*>(fsm + hp * CP + 4 * q) = v;
     }
+    __syncthreads();
+
+    // ---- head conv on tensor cores: warp w owns tile rows 2w and 2w+1 (16 pixels each = one m16 tile) ----
+    float acc[2][NT][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[r][nt][k] = 0.0f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap % 3;
+        const float* wt = wsm + tap * C * WPITCH;
+#pragma unroll 2
+        for (int kc = 0; kc < C; kc += 8) {
+            unsigned bh[NT][2], bl[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                split_tf32(wt[(kc + t) * WPITCH + nt * 8 + g], bh[nt][0], bl[nt][0]);
+                split_tf32(wt[(kc + t + 4) * WPITCH + nt * 8 + g], bh[nt][1], bl[nt][1]);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float* ap = fsm + ((2 * warp + r + dy) * HALO + dx + g) * CP + kc + t;
+                unsigned ah[4], al[4];
+                split_tf32(ap[0], ah[0], al[0]);
+                split_tf32(ap[8 * CP], ah[1], al[1]);
+                split_tf32(ap[4], ah[2], al[2]);
+                split_tf32(ap[8 * CP + 4], ah[3], al[3]);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma_tf32_16x8x8(acc[r][nt], al, bh[nt][0], bh[nt][1]);
+                    mma_tf32_16x8x8(acc[r][nt], ah, bl[nt][0], bl[nt][1]);
+                    mma_tf32_16x8x8(acc[r][nt], ah, bh[nt][0], bh[nt][1]);
+                }
+            }
+        }
+    }
+    __syncthreads();                          // all warps are done reading the halo tile: reuse it for the transpose
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int px0 = (2 * warp + r) * TILE + g;
+            osm[px0 * OPITCH + nt * 8 + 2 * t] = acc[r][nt][0];
+            osm[px0 * OPITCH + nt * 8 + 2 * t + 1] = acc[r][nt][1];
+            osm[(px0 + 8) * OPITCH + nt * 8 + 2 * t] = acc[r][nt][2];
+            osm[(px0 + 8) * OPITCH + nt * 8 + 2 * t + 1] = acc[r][nt][3];
+        }
     __syncthreads();
 
     const int ty = tid / TILE, tx = tid % TILE;
     float o[CO_PAD];
 #pragma unroll
-    for (int j = 0; j < CO_PAD; ++j) o[j] = bg[j];
-#pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-        const float* fp = fsm + ((ty + tap / 3) * HALO + tx + tap % 3) * CP;
-        const float* wp = wsm + tap * C * CO_PAD;
-#pragma unroll 4
-        for (int c = 0; c < C; ++c) {
-            const float f = fp[c];
-            const float4 w0 = *reinterpret_cast<const float4*>(wp + c * CO_PAD);
-            const float4 w1 = *reinterpret_cast<const float4*>(wp + c * CO_PAD + 4);
-            const float4 w2 = *reinterpret_cast<const float4*>(wp + c * CO_PAD + 8);
-            o[0] = fmaf(f, w0.x, o[0]); o[1] = fmaf(f, w0.y, o[1]); o[2] = fmaf(f, w0.z, o[2]); o[3] = fmaf(f, w0.w, o[3]);
-            o[4] = fmaf(f, w1.x, o[4]); o[5] = fmaf(f, w1.y, o[5]); o[6] = fmaf(f, w1.z, o[6]); o[7] = fmaf(f, w1.w, o[7]);
-            o[8] = fmaf(f, w2.x, o[8]); o[9] = fmaf(f, w2.y, o[9]); o[10] = fmaf(f, w2.z, o[10]); o[11] = fmaf(f, w2.w, o[11]);
-        }
-    }
+    for (int j = 0; j < CO_PAD; ++j) o[j] = (j < NT * 8) ? osm[tid * OPITCH + j] + bg[j] : 0.0f;
 
     const int y = by0 + ty, x = bx0 + tx;
     const long plane = (long)S * S, pix = (long)y * S + x;
@@ -165,13 +224,15 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea
     }
 }
 
-template <int KIND>
+template <int KIND, int NT>
 void launch_tail(const TailWeights& tw, const View& f, const float* coef, int act, const ImgView& i0, const ImgView& i1,
                  float* const* o, int nout, cudaStream_t s) {
-    const size_t smem = ((size_t)9 * tw.C * CO_PAD + (size_t)HALO * HALO * (tw.C + 1)) * sizeof(float);
+    THA4_REQUIRE(tw.C % 8 == 0 && tw.CO <= NT * 8, "tail: head channel layout");
+    const size_t halo = (size_t)HALO * HALO * (tw.C + 4), outs = (size_t)TILE * TILE * OPITCH;
+    const size_t smem = ((size_t)9 * tw.C * WPITCH + std::max(halo, outs)) * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel<KIND, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     float* op[8];
@@ -183,7 +244,7 @@ void launch_tail(const TailWeights& tw, const View& f, const float* coef, int ac
         const int img_ch = (KIND == TAIL_COMBINER) ? 8 : 4;
         prof_add_work(PROF_TAIL, 2.0 * f.pixels() * 9 * tw.C * tw.CO, (double)f.pixels() * (f.C + img_ch + out_ch[KIND]) * 4);
     }
-    tail_kernel<KIND><<<grid, 256, smem, s>>>(f.p, f.H, f.C, f.ld, coef, act, tw.w, tw.bias, i0, i1,
+    tail_kernel<KIND, NT><<<grid, 256, smem, s>>>(f.p, f.H, f.C, f.ld, coef, act, tw.w, tw.bias, i0, i1,
                                              base_grid_table(f.H), op[0], op[1], op[2], op[3], op[4], op[5], op[6], op[7]);
     THA4_LAUNCH_CHECK();
 }
@@ -195,10 +256,10 @@ void tail_forward(TailKind kind, const TailWeights& tw, const View& feature, con
     THA4_REQUIRE(feature.H == feature.W && feature.H % TILE == 0 && feature.C == tw.C && tw.C % 4 == 0, "tail: feature dims");
     THA4_REQUIRE(image0.H == feature.H && image0.W == feature.W && image0.C == 4, "tail: image dims");
     switch (kind) {
-        case TAIL_UNET: launch_tail<TAIL_UNET>(tw, feature, coef, act, image0, image1, outputs, 5, s); break;
-        case TAIL_DECOMPOSER: launch_tail<TAIL_DECOMPOSER>(tw, feature, coef, act, image0, image1, outputs, 6, s); break;
-        case TAIL_COMBINER: launch_tail<TAIL_COMBINER>(tw, feature, coef, act, image0, image1, outputs, 8, s); break;
-        case TAIL_FACE: launch_tail<TAIL_FACE>(tw, feature, coef, act, image0, image1, outputs, 8, s); break;
+        case TAIL_UNET: launch_tail<TAIL_UNET, 1>(tw, feature, coef, act, image0, image1, outputs, 5, s); break;
+        case TAIL_DECOMPOSER: launch_tail<TAIL_DECOMPOSER, 2>(tw, feature, coef, act, image0, image1, outputs, 6, s); break;
+        case TAIL_COMBINER: launch_tail<TAIL_COMBINER, 1>(tw, feature, coef, act, image0, image1, outputs, 8, s); break;
+        case TAIL_FACE: launch_tail<TAIL_FACE, 2>(tw, feature, coef, act, image0, image1, outputs, 8, s); break;
     }
 }
 
