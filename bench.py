@@ -99,7 +99,13 @@ def load_state_dicts(mode):
     return synthetic.student_state_dicts(0), 'random-init (seeded) student weights'
 
 
-def cpu_port_fps(mode, sds, image, poses, batch, frames_budget, threads):
+def cpu_threads():
+    """Host threads for the CPU arm.  PyTorch-CPU convs on these 128-core boxes get *slower* past a few dozen threads
+    (measured: 128 threads are 40x slower than 8 on the teacher), so the arm uses min(cores, 32) and says so."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get('THA4_CPU_THREADS', '32'))))
+
+
+def cpu_port_fps(mode, sds, image, poses, batch, frames_budget, threads, seconds_budget=20.0):
     """Times the CPU oracle (PyTorch-CPU port of the reference path).  Returns (fps, frames, seconds)."""
     from oracle import tha4_oracle
     torch.set_num_threads(threads)
@@ -114,7 +120,7 @@ def cpu_port_fps(mode, sds, image, poses, batch, frames_budget, threads):
         fn(sds, img_b, poses[:b], **kw)            # warm-up
         t0 = time.perf_counter()
         done = 0
-        while done < frames_budget:
+        while done < frames_budget and (done == 0 or time.perf_counter() - t0 < seconds_budget):
             fn(sds, img_b, poses[done % 8:done % 8 + b] if poses.shape[0] >= 8 + b else poses[:b], **kw)
             done += b
         dt = time.perf_counter() - t0
@@ -130,7 +136,7 @@ def run_reference(args, rank, world):
     sds, _ = load_state_dicts(wl['mode'])
     image = load_inputs(wl)
     poses = synthetic.random_poses(64, seed=1234)
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     per_step_frames = 1 if wl['mode'] == 'mode_07' else 2
     from oracle import tha4_oracle
     torch.set_num_threads(threads)
@@ -143,11 +149,14 @@ def run_reference(args, rank, world):
         if wl['mode'] == 'mode_07':     # eyebrow cache hot, as in the GPU arm (mode_07.py:56-68)
             dec = tha4_oracle.eyebrow_decomposer(sds['eyebrow_decomposer'], img_b[:, :, 64:192, 192:320])
             kw = dict(cached_decomposer_output=dec)
+        t_start = time.perf_counter()
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
             fn(sds, img_b, poses[(i * b) % 32:(i * b) % 32 + b], **kw)
             if i >= args.warmup:
                 times.append((time.perf_counter() - t0) / b)
+            if times and time.perf_counter() - t_start > 150.0:     # bounded sample: keep the arm within minutes
+                break
     spf = sum(times) / len(times)
     line = {
         'impl': 'reference', 'metric': '512x512 RGBA frames/sec', 'value': 1.0 / spf, 'unit': 'frames/s', 'n_gpus': args.gpus,
@@ -155,8 +164,8 @@ def run_reference(args, rank, world):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': wl['desc'], 'batch': wl['batch']},
         'cpu_baseline': {'value': 1.0 / spf, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                         'sample': '%d timed steps of %d frame(s) each of the same workload (PyTorch-CPU port of the reference path, '
-                                   'all host threads)' % (args.steps, per_step_frames)},
+                         'sample': '%d timed steps (of %d requested) of %d frame(s) each of the same workload (PyTorch-CPU port of the reference path, '
+                                   '%d of %d host threads)' % (len(times), args.steps, per_step_frames, threads, os.cpu_count() or 1)},
         'e2e': {'value': 1.0 / spf, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -327,12 +336,12 @@ def main():
             line['roofline'].update(achieved=ach, frac=ach / peaks['tflops'])
 
     if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         budget = 6 if wl['mode'] == 'mode_07' else 12
         fps, nfr, dt = cpu_port_fps(wl['mode'], sds, image, poses, B, budget, threads)
         line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                                 'sample': '%d frames of the same workload in %.1f s (PyTorch-CPU port of the reference path in oracle/, '
-                                          'all host threads; /root/reference itself is pure Python and does not exist on the GPU box)' % (nfr, dt)}
+                                          '%d of %d host threads; /root/reference itself is pure Python and does not exist on the GPU box)' % (nfr, dt, threads, os.cpu_count() or 1)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
