@@ -103,6 +103,23 @@ int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, const floa
                          int eyebrow_morphed_image_index, const float* const* cached_decomposer, void* stream);
 /* mode 14: TwoStepPoserComputationProtocol (src/tha4/poser/modes/mode_14.py:40-90): body(5) + face(1) */
 int tha4_student_forward(tha4_ctx* ctx, const float* image, const float* pose, int B, float* const* outputs, void* stream);
+/* ---- distillation inner loop of the body student (replaces the autograd part of
+ * SirenMorpherTrainingProtocol03.run_training_iteration, src/tha4/nn/siren/morpher/siren_morpher_protocols_03.py:178-214) ---- */
+/* number of fp32 parameters of SirenMorpher03 in state_dict order (331 567) */
+int64_t tha4_siren_morpher_param_count(void);
+/* student forward + the four L1 terms (siren_morpher_03_trainer.py:32-50: blended vs target_posed, warped vs
+ * target_warped, grid_change vs target_grid_change, color_change vs target_posed; mean reduction, weights
+ * loss_weights[4] on the host) + full backward.  image = the teacher's face_morphed_full (output 5 of mode 7),
+ * pose [B,45]; params / grads: flat device buffers in state_dict order (grads is overwritten);
+ * host_loss_means (optional): the four unweighted means (synchronises).  B <= 8 per GPU as in the reference. */
+int tha4_siren_morpher_train_step(tha4_ctx* ctx, const float* image, const float* pose, const float* target_posed,
+                                  const float* target_warped, const float* target_grid_change, const float* loss_weights,
+                                  const float* params, float* grads, double* host_loss_means, int B, void* stream);
+/* torch.optim.Adam step on flat buffers (shion/base/optimizer_factories.py:9-17); grads are scaled by grad_scale first
+ * (1/world_size after a summing all-reduce = DDP's gradient averaging) */
+int tha4_adam_step(tha4_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
 /* max|a-b| > 0 ?  -- the cache-validity test of mode_07.py:61 (synchronises the stream); result written to *differ */
 int tha4_images_differ(tha4_ctx* ctx, const float* a, const float* b, int64_t n, int* differ, void* stream);
 

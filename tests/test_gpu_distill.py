@@ -1,0 +1,92 @@
+"""Distillation inner loop on the B200 (-m gpu): losses, flat gradient and post-Adam weights of the CUDA step against
+CPU autograd on the oracle (same student weights, same targets).
+
+Tolerances: the dense layers run TF32 products (as the reference's own CUDA path would for 1x1 convs) and L1 has a
+discontinuous derivative (sign), so the gradient is compared as a whole: relative L2 error <= 3e-2 and cosine
+similarity >= 0.999; the four loss means agree to 2e-3 relative."""
+import pytest
+import torch
+
+import gpu_util as G
+from oracle import distill_oracle, synth, tha4_oracle as O
+from tha4_b200.distill import BodyMorpherDistiller, flatten_parameters
+from tha4_b200.poser.modes import mode_07, mode_14
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+def _smooth(seed, n, c, amp=1.0):
+    return (synth.synthetic_image(seed, n)[:, :c] * amp).contiguous()
+
+
+def test_student_train_step_vs_autograd(student_sds):
+    sd = student_sds['body_morpher']
+    n = 2
+    image = synth.synthetic_image(11, n)
+    pose = synth.random_poses(n, seed=4)
+    t_posed, t_warped = _smooth(12, n, 4), _smooth(13, n, 4)
+    t_grid = _smooth(14, n, 2, 0.05)
+    weights = [1.0, 0.5, 2.0, 0.25]
+    ref_losses, ref_grad = distill_oracle.body_losses_and_grads(sd, image, pose, t_posed, t_warped, t_grid, weights)
+
+    student = mode_14.load_body_morpher(None, sd).to(DEV)
+    flat = flatten_parameters(student)
+    assert torch.equal(flat.cpu(), torch.cat([v.reshape(-1) for v in sd.values()]))
+    grad = torch.zeros_like(flat)
+    ctx = G.ctx()
+    losses = ctx.siren_morpher_train_step(image.to(DEV), pose.to(DEV), t_posed.to(DEV), t_warped.to(DEV), t_grid.to(DEV),
+                                          weights, flat, grad)
+    torch.cuda.synchronize()
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 2e-3 * max(abs(b), 1e-3), (losses, ref_losses)
+    g = grad.cpu()
+    rel = ((g - ref_grad).norm() / ref_grad.norm()).item()
+    cos = torch.nn.functional.cosine_similarity(g, ref_grad, dim=0).item()
+    print('\ndistill grad: rel L2 err %.3e cosine %.6f |g| %.3e' % (rel, cos, ref_grad.norm().item()))
+    # per-tensor report (layer gradients differ by orders of magnitude)
+    off = 0
+    for k, v in sd.items():
+        m = v.numel()
+        a, b = g[off:off + m], ref_grad[off:off + m]
+        print('  %-40s rel %.3e' % (k, ((a - b).norm() / (b.norm() + 1e-20)).item()))
+        assert ((a - b).norm() / (b.norm() + 1e-20)).item() <= 6e-2, k
+        off += m
+    assert rel <= 3e-2 and cos >= 0.999
+
+    # Adam: two steps with the reference gradient fed to both implementations
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    gdev = ref_grad.to(DEV)
+    p0 = flat.clone()
+    ctx.adam_step(flat, gdev, m, v, 1e-4, 1)
+    ctx.adam_step(flat, gdev * 0.5, m, v, 1e-4, 2)
+    ref_p = distill_oracle.adam_reference(p0.cpu(), [ref_grad, ref_grad * 0.5], 1e-4)
+    assert (flat.cpu() - ref_p).abs().max().item() <= 2e-7
+
+
+def test_full_distill_step_with_teacher(teacher_sds, student_sds):
+    """teacher forward (strict) -> student step: losses against the oracle teacher + oracle student."""
+    teacher = mode_07.create_poser(DEV, state_dicts=teacher_sds)
+    teacher.get_context().set_option('strict', 1)
+    student = mode_14.load_body_morpher(None, student_sds['body_morpher'])
+    d = BodyMorpherDistiller(teacher, student)
+    image = synth.synthetic_image(0, 1)
+    pose = synth.random_poses(1, seed=21)
+    weights = [1.0, 1.0, 1.0, 1.0]
+    before = d.flat.clone()
+    out = d.train_step(image.to(DEV), pose.to(DEV), weights, lr=1e-4)
+    with torch.no_grad():
+        t = O.mode_07_outputs(teacher_sds, image, pose)
+    ref_losses, ref_grad = distill_oracle.body_losses_and_grads(student_sds['body_morpher'], t[5], pose, t[0], t[2], t[3], weights)
+    for name, b in zip(('full_blended', 'full_warped', 'full_grid_change', 'full_color_change'), ref_losses):
+        assert abs(out[name] - b) <= 3e-3 * max(abs(b), 1e-3), (name, out[name], b)
+    g = d.grad.cpu()
+    assert ((g - ref_grad).norm() / ref_grad.norm()).item() <= 4e-2
+    ref_p = distill_oracle.adam_reference(before.cpu(), [ref_grad], 1e-4)
+    # first Adam step moves every weight by ~lr * sign(g): compare the update direction where the gradient is not tiny
+    upd, ref_upd = (d.flat.cpu() - before.cpu()), (ref_p - before.cpu())
+    big = ref_grad.abs() > 1e-3 * ref_grad.abs().max()
+    assert (torch.sign(upd[big]) == torch.sign(ref_upd[big])).float().mean().item() >= 0.995
+    # the updated student is what the inference path now uses
+    outs = student.to(DEV)(t[5].to(DEV), pose.to(DEV))
+    assert len(outs) == 5 and torch.isfinite(outs[0]).all()

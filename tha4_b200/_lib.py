@@ -24,7 +24,8 @@ EXPORTED_SYMBOLS = [
     'tha4_ctx_create', 'tha4_ctx_destroy', 'tha4_last_error', 'tha4_set_option', 'tha4_get_counter', 'tha4_load_net',
     'tha4_eyebrow_decomposer_forward', 'tha4_eyebrow_morphing_combiner_forward', 'tha4_face_morpher_forward',
     'tha4_morpher_forward', 'tha4_upscaler_forward', 'tha4_siren_face_morpher_forward', 'tha4_siren_morpher_forward',
-    'tha4_teacher_forward', 'tha4_student_forward', 'tha4_images_differ', 'tha4_grid_sample', 'tha4_resize_bilinear',
+    'tha4_teacher_forward', 'tha4_student_forward', 'tha4_siren_morpher_param_count', 'tha4_siren_morpher_train_step',
+    'tha4_adam_step', 'tha4_images_differ', 'tha4_grid_sample', 'tha4_resize_bilinear',
     'tha4_base_grid', 'tha4_test_conv', 'tha4_test_norm', 'tha4_test_attention', 'tha4_test_linear',
 ]
 
@@ -49,6 +50,10 @@ def load_library() -> ctypes.CDLL:
     lib.tha4_get_counter.restype = ctypes.c_int64
     lib.tha4_get_counter.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
     lib.tha4_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]
+    lib.tha4_siren_morpher_param_count.restype = ctypes.c_int64
+    lib.tha4_adam_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                   ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_float,
+                                   ctypes.c_void_p]
     lib.tha4_images_differ.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                        ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
     _lib = lib
@@ -243,6 +248,27 @@ class Context:
         outs = self._empty([(4, 512), (1, 512), (4, 512), (4, 512), (2, 512), (4, 128)], B)
         self._call('tha4_student_forward', _ptr(image), _ptr(pose), B, _ptr_array(outs), self._stream())
         return outs
+
+    # ------------------------------------------------------------------ distillation
+    def siren_morpher_train_step(self, image: Tensor, pose: Tensor, target_posed: Tensor, target_warped: Tensor,
+                                 target_grid_change: Tensor, loss_weights: Sequence[float], params: Tensor, grads: Tensor,
+                                 want_losses: bool = True):
+        tensors = [_check_input(t, self.device, n) for t, n in ((image, 'image'), (pose, 'pose'), (target_posed, 'target_posed'),
+                                                                (target_warped, 'target_warped'), (target_grid_change, 'target_grid_change'))]
+        B = image.shape[0]
+        assert params.is_contiguous() and grads.is_contiguous() and params.dtype == torch.float32 and grads.dtype == torch.float32
+        w = (ctypes.c_float * 4)(*[float(x) for x in loss_weights])
+        losses = (ctypes.c_double * 4)()
+        self._call('tha4_siren_morpher_train_step', *[_ptr(t) for t in tensors], w, _ptr(params), _ptr(grads),
+                   losses if want_losses else None, B, self._stream())
+        return list(losses) if want_losses else None
+
+    def adam_step(self, params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, step: int,
+                  betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
+        rc = self.lib.tha4_adam_step(self.handle, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(), lr,
+                                     betas[0], betas[1], eps, step, grad_scale, self._stream())
+        if rc != 0:
+            raise Tha4Error('tha4_adam_step failed: %s' % self.lib.tha4_last_error(self.handle).decode())
 
     def images_differ(self, a: Tensor, b: Tensor) -> bool:
         a = _check_input(a, self.device, 'a')

@@ -3,6 +3,7 @@
 #include "nets.cuh"
 #include "siren.cuh"
 #include "profiler.cuh"
+#include "distill.cuh"
 #include <atomic>
 #include <cstring>
 
@@ -17,6 +18,7 @@ struct tha4_ctx {
     int microbatch = 8;
     Pool persist, scratch;
     int* flag = nullptr;
+    double* loss_acc = nullptr;            // 4 doubles: L1 sums of the distillation step
     double* stats_base = nullptr;          // zero-initialised statistics arena (Runtime::alloc_stats)
     size_t stats_cap = 0, stats_off = 0;
     std::unique_ptr<EncDecNet> decomposer, combiner, face;
@@ -150,6 +152,7 @@ int tha4_ctx_create(int device, tha4_ctx** out) {
         auto* ctx = new tha4_ctx();
         ctx->device = device;
         THA4_CUDA_CHECK(cudaMalloc(&ctx->flag, sizeof(int)));
+        THA4_CUDA_CHECK(cudaMalloc(&ctx->loss_acc, 4 * sizeof(double)));
         ctx->stats_cap = (size_t)8 << 20;                       // 8 Mi doubles = 64 MB
         THA4_CUDA_CHECK(cudaMalloc(&ctx->stats_base, ctx->stats_cap * sizeof(double)));
         THA4_CUDA_CHECK(cudaMemset(ctx->stats_base, 0, ctx->stats_cap * sizeof(double)));
@@ -176,6 +179,7 @@ int tha4_ctx_destroy(tha4_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->flag) cudaFree(ctx->flag);
+    if (ctx->loss_acc) cudaFree(ctx->loss_acc);
     if (ctx->stats_base) cudaFree(ctx->stats_base);
     delete ctx;
     return THA4_OK;
@@ -350,6 +354,33 @@ int tha4_student_forward(tha4_ctx* ctx, const float* image, const float* pose, i
         copy_window(make_img(outputs[5], B, 4, 128, 128), body_in + 80 * 512 + 192, 4L * 512 * 512, 512L * 512, 512, s);
         ctx->sbody->forward(rt, make_img(body_in, B, 4, 512, 512), pose, 45, outputs);
     });
+}
+
+int64_t tha4_siren_morpher_param_count(void) { return (int64_t)siren_body_param_count(); }
+
+int tha4_siren_morpher_train_step(tha4_ctx* ctx, const float* image, const float* pose, const float* target_posed,
+                                  const float* target_warped, const float* target_grid_change, const float* loss_weights,
+                                  const float* params, float* grads, double* host_loss_means, int B, void* stream) {
+    return guarded(ctx, [&] {
+        THA4_REQUIRE(B >= 1 && B <= 8, "distill step: per-GPU batch must be 1..8 (distiller_config.py:100-104)");
+        cudaStream_t s = (cudaStream_t)stream;
+        begin_pass(ctx, s);
+        Runtime rt = make_rt(ctx, stream);
+        siren_body_train_step(rt, make_img(image, B, 4, 512, 512), pose, 45, target_posed, target_warped, target_grid_change,
+                              loss_weights, params, grads, ctx->loss_acc);
+        if (host_loss_means) {
+            double h[4];
+            THA4_CUDA_CHECK(cudaMemcpyAsync(h, ctx->loss_acc, sizeof(h), cudaMemcpyDeviceToHost, s));
+            THA4_CUDA_CHECK(cudaStreamSynchronize(s));
+            const double nb = (double)B * 4 * 512 * 512, ng = (double)B * 2 * 512 * 512;
+            host_loss_means[0] = h[0] / nb; host_loss_means[1] = h[1] / nb; host_loss_means[2] = h[2] / ng; host_loss_means[3] = h[3] / nb;
+        }
+    });
+}
+
+int tha4_adam_step(tha4_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+    return guarded(ctx, [&] { adam_step(params, grads, exp_avg, exp_avg_sq, (long)n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream); });
 }
 
 int tha4_images_differ(tha4_ctx* ctx, const float* a, const float* b, int64_t n, int* differ, void* stream) {

@@ -68,11 +68,12 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_SILU_FAST = 3 };   // FAST: ex2.approx / rcp.approx (default mode)
 
 __device__ __forceinline__ float act_apply(float v, int act) {
     if (act == ACT_RELU) return fmaxf(v, 0.0f);
     if (act == ACT_SILU) return v / (1.0f + expf(-v));
+    if (act == ACT_SILU_FAST) return __fdividef(v, 1.0f + __expf(-v));
     return v;
 }
 // round-to-nearest TF32 (10-bit mantissa) as the tensor cores would ideally see it; tcgen05 kind::tf32 truncates the

@@ -255,7 +255,7 @@ void EncDecNet::forward(Runtime& rt, const ImgView& image0, const ImgView& image
     View raw = make_view(P, B, S_, S_, 64, &rt);
     run_conv(rt, up_[2], x, raw);
     float* coef = tail_coef(rt, raw, up_n_[2], 0);
-    tail_forward(kind_, tail_, raw, coef, ACT_RELU, image0, image1, outputs, s);
+    tail_forward(kind_, tail_, raw, coef, ACT_RELU, image0, image1, outputs, s, rt.strict);
 }
 
 // ------------------------------------------------------------------------------------------------ UNetNet
@@ -391,11 +391,11 @@ void UNetNet::res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode
     // norm0 -> SiLU -> (avg-pool) ; the nearest-upsample is folded into conv0's gather
     const int th = (mode == 2) ? x.H / 2 : x.H;
     View t0 = make_view(rt.scratch, B, th, th, w.cin);
-    run_norm(rt, x, w.norm0, 32, nullptr, nullptr, 0, ACT_SILU, mode == 2 ? 1 : 0, nullptr, t0);
+    run_norm(rt, x, w.norm0, 32, nullptr, nullptr, 0, rt.strict ? ACT_SILU : ACT_SILU_FAST, mode == 2 ? 1 : 0, nullptr, t0);
     View h = make_view(rt.scratch, B, out.H, out.W, w.cout, &rt);
     run_conv(rt, w.conv0, t0, h);      // mode 1: conv0 was packed as CONV_UP2_3x3 (upsample folded into 4 phases)
     // norm1 -> FiLM(time) -> FiLM(pose) -> SiLU, folded into one per-(n,c) affine
-    run_norm(rt, h, w.norm1, 32, w.film0, film1 + w.film1_off, film1_total_, ACT_SILU, 0, nullptr, h);
+    run_norm(rt, h, w.norm1, 32, w.film0, film1 + w.film1_off, film1_total_, rt.strict ? ACT_SILU : ACT_SILU_FAST, 0, nullptr, h);
     if (w.has_skip) {
         THA4_REQUIRE(mode == 0, "res_block: skip conv only on same-resolution blocks");
         View sk = make_view(rt.scratch, B, x.H, x.W, w.cout);
@@ -519,7 +519,7 @@ void UNetNet::forward(Runtime& rt, const ImgView& image, const float* coarse_pos
     rt.scratch->reset();
     float* coef = tail_coef(rt, feat, last_n_, 32);
     ImgView none{};
-    tail_forward(TAIL_UNET, tail_, feat, coef, ACT_SILU, image, none, outputs, s);
+    tail_forward(TAIL_UNET, tail_, feat, coef, rt.strict ? ACT_SILU : ACT_SILU_FAST, image, none, outputs, s, rt.strict);
 }
 
 }  // namespace tha4

@@ -70,6 +70,6 @@ constexpr int TAIL_CO_PAD = 12;
 // image0: the image that is warped / blended (NCHW view); image1: second image (combiner: background layer).
 // outputs: NCHW contiguous, order/meaning per kind (see tail.cu).
 void tail_forward(TailKind kind, const TailWeights& tw, const View& feature, const float* coef, int act,
-                  const ImgView& image0, const ImgView& image1, float* const* outputs, cudaStream_t s);
+                  const ImgView& image0, const ImgView& image1, float* const* outputs, cudaStream_t s, int strict);
 
 }  // namespace tha4

@@ -41,7 +41,7 @@ __device__ __forceinline__ void split_tf32(float v, unsigned& hi, unsigned& lo) 
     asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(lo) : "f"(r));
 }
 
-template <int KIND, int NT>
+template <int KIND, int NT, bool STRICT>
 __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ feat, int S, int C, int ld,
                                                    const float* __restrict__ coef, int act,
                                                    const float* __restrict__ wg, const float* __restrict__ bg,
@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea
 
     for (int i = tid; i < 9 * C * (CO_PAD / 4); i += 256) {
         const int row = i / (CO_PAD / 4), part = i - row * (CO_PAD / 4);
-        *reinterpret_cast<float4*>(wsm + row * WPITCH + 4 * part) = *reinterpret_cast<const float4*>(wg + row * CO_PAD + 4 * part);
+        float4 wv = *reinterpret_cast<const float4*>(wg + row * CO_PAD + 4 * part);
+        if (!STRICT) { wv.x = round_tf32(wv.x); wv.y = round_tf32(wv.y); wv.z = round_tf32(wv.z); wv.w = round_tf32(wv.w); }
+        *reinterpret_cast<float4*>(wsm + row * WPITCH + 4 * part) = wv;
     }
     if (CO_PAD < 16)
         for (int i = tid; i < 9 * C; i += 256) *reinterpret_cast<float4*>(wsm + i * WPITCH + 12) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea
             v.x = act_apply(v.x * c0.x + c0.y, act); v.y = act_apply(v.y * c0.z + c0.w, act);
             v.z = act_apply(v.z * c1.x + c1.y, act); v.w = act_apply(v.w * c1.z + c1.w, act);
         }
+        if (!STRICT) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
         *reinterpret_cast<float4*>(fsm + hp * CP + 4 * q) = v;
     }
     __syncthreads();
@@ -95,25 +98,41 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea
         const float* wt = wsm + tap * C * WPITCH;
 #pragma unroll 2
         for (int kc = 0; kc < C; kc += 8) {
-            unsigned bh[NT][2], bl[NT][2];
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                split_tf32(wt[(kc + t) * WPITCH + nt * 8 + g], bh[nt][0], bl[nt][0]);
-                split_tf32(wt[(kc + t + 4) * WPITCH + nt * 8 + g], bh[nt][1], bl[nt][1]);
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const float* ap = fsm + ((2 * warp + r + dy) * HALO + dx + g) * CP + kc + t;
-                unsigned ah[4], al[4];
-                split_tf32(ap[0], ah[0], al[0]);
-                split_tf32(ap[8 * CP], ah[1], al[1]);
-                split_tf32(ap[4], ah[2], al[2]);
-                split_tf32(ap[8 * CP + 4], ah[3], al[3]);
+            if (STRICT) {     // 3xTF32: hi/lo split of both operands, fp32-equivalent products
+                unsigned bh[NT][2], bl[NT][2];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    mma_tf32_16x8x8(acc[r][nt], al, bh[nt][0], bh[nt][1]);
-                    mma_tf32_16x8x8(acc[r][nt], ah, bl[nt][0], bl[nt][1]);
-                    mma_tf32_16x8x8(acc[r][nt], ah, bh[nt][0], bh[nt][1]);
+                    split_tf32(wt[(kc + t) * WPITCH + nt * 8 + g], bh[nt][0], bl[nt][0]);
+                    split_tf32(wt[(kc + t + 4) * WPITCH + nt * 8 + g], bh[nt][1], bl[nt][1]);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float* ap = fsm + ((2 * warp + r + dy) * HALO + dx + g) * CP + kc + t;
+                    unsigned ah[4], al[4];
+                    split_tf32(ap[0], ah[0], al[0]);
+                    split_tf32(ap[8 * CP], ah[1], al[1]);
+                    split_tf32(ap[4], ah[2], al[2]);
+                    split_tf32(ap[8 * CP + 4], ah[3], al[3]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        mma_tf32_16x8x8(acc[r][nt], al, bh[nt][0], bh[nt][1]);
+                        mma_tf32_16x8x8(acc[r][nt], ah, bl[nt][0], bl[nt][1]);
+                        mma_tf32_16x8x8(acc[r][nt], ah, bh[nt][0], bh[nt][1]);
+                    }
+                }
+            } else {          // single TF32: the halo tile and the staged weights were rounded (RNA) when written
+                unsigned b[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    b[nt][0] = __float_as_uint(wt[(kc + t) * WPITCH + nt * 8 + g]);
+                    b[nt][1] = __float_as_uint(wt[(kc + t + 4) * WPITCH + nt * 8 + g]);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float* ap = fsm + ((2 * warp + r + dy) * HALO + dx + g) * CP + kc + t;
+                    unsigned a[4] = {__float_as_uint(ap[0]), __float_as_uint(ap[8 * CP]), __float_as_uint(ap[4]), __float_as_uint(ap[8 * CP + 4])};
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32_16x8x8(acc[r][nt], a, b[nt][0], b[nt][1]);
                 }
             }
         }
@@ -224,7 +243,7 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea
     }
 }
 
-template <int KIND, int NT>
+template <int KIND, int NT, bool STRICT>
 void launch_tail(const TailWeights& tw, const View& f, const float* coef, int act, const ImgView& i0, const ImgView& i1,
                  float* const* o, int nout, cudaStream_t s) {
     THA4_REQUIRE(tw.C % 8 == 0 && tw.CO <= NT * 8, "tail: head channel layout");
@@ -232,7 +251,7 @@ void launch_tail(const TailWeights& tw, const View& f, const float* coef, int ac
     const size_t smem = ((size_t)9 * tw.C * WPITCH + std::max(halo, outs)) * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel<KIND, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel<KIND, NT, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     float* op[8];
@@ -244,7 +263,7 @@ void launch_tail(const TailWeights& tw, const View& f, const float* coef, int ac
         const int img_ch = (KIND == TAIL_COMBINER) ? 8 : 4;
         prof_add_work(PROF_TAIL, 2.0 * f.pixels() * 9 * tw.C * tw.CO, (double)f.pixels() * (f.C + img_ch + out_ch[KIND]) * 4);
     }
-    tail_kernel<KIND, NT><<<grid, 256, smem, s>>>(f.p, f.H, f.C, f.ld, coef, act, tw.w, tw.bias, i0, i1,
+    tail_kernel<KIND, NT, STRICT><<<grid, 256, smem, s>>>(f.p, f.H, f.C, f.ld, coef, act, tw.w, tw.bias, i0, i1,
                                              base_grid_table(f.H), op[0], op[1], op[2], op[3], op[4], op[5], op[6], op[7]);
     THA4_LAUNCH_CHECK();
 }
@@ -252,14 +271,26 @@ void launch_tail(const TailWeights& tw, const View& f, const float* coef, int ac
 }  // namespace
 
 void tail_forward(TailKind kind, const TailWeights& tw, const View& feature, const float* coef, int act,
-                  const ImgView& image0, const ImgView& image1, float* const* outputs, cudaStream_t s) {
+                  const ImgView& image0, const ImgView& image1, float* const* outputs, cudaStream_t s, int strict) {
     THA4_REQUIRE(feature.H == feature.W && feature.H % TILE == 0 && feature.C == tw.C && tw.C % 4 == 0, "tail: feature dims");
     THA4_REQUIRE(image0.H == feature.H && image0.W == feature.W && image0.C == 4, "tail: image dims");
     switch (kind) {
-        case TAIL_UNET: launch_tail<TAIL_UNET, 1>(tw, feature, coef, act, image0, image1, outputs, 5, s); break;
-        case TAIL_DECOMPOSER: launch_tail<TAIL_DECOMPOSER, 2>(tw, feature, coef, act, image0, image1, outputs, 6, s); break;
-        case TAIL_COMBINER: launch_tail<TAIL_COMBINER, 1>(tw, feature, coef, act, image0, image1, outputs, 8, s); break;
-        case TAIL_FACE: launch_tail<TAIL_FACE, 2>(tw, feature, coef, act, image0, image1, outputs, 8, s); break;
+        case TAIL_UNET:
+            if (strict) launch_tail<TAIL_UNET, 1, true>(tw, feature, coef, act, image0, image1, outputs, 5, s);
+            else launch_tail<TAIL_UNET, 1, false>(tw, feature, coef, act, image0, image1, outputs, 5, s);
+            break;
+        case TAIL_DECOMPOSER:
+            if (strict) launch_tail<TAIL_DECOMPOSER, 2, true>(tw, feature, coef, act, image0, image1, outputs, 6, s);
+            else launch_tail<TAIL_DECOMPOSER, 2, false>(tw, feature, coef, act, image0, image1, outputs, 6, s);
+            break;
+        case TAIL_COMBINER:
+            if (strict) launch_tail<TAIL_COMBINER, 1, true>(tw, feature, coef, act, image0, image1, outputs, 8, s);
+            else launch_tail<TAIL_COMBINER, 1, false>(tw, feature, coef, act, image0, image1, outputs, 8, s);
+            break;
+        case TAIL_FACE:
+            if (strict) launch_tail<TAIL_FACE, 2, true>(tw, feature, coef, act, image0, image1, outputs, 8, s);
+            else launch_tail<TAIL_FACE, 2, false>(tw, feature, coef, act, image0, image1, outputs, 8, s);
+            break;
     }
 }
 
