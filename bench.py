@@ -203,15 +203,23 @@ def main():
 
     from tha4_b200 import synthetic
     from tha4_b200.poser.modes import mode_07, mode_14
-    sds, weights_desc = load_state_dicts(wl['mode'])
+    distill = wl['mode'] == 'distill'
+    sds, weights_desc = load_state_dicts('mode_07' if distill else wl['mode'])
     image = load_inputs(wl)
     nposes = (args.warmup + args.steps) * B
     poses = synthetic.random_poses(nposes, seed=1234 + rank)
-    poser = (mode_07 if wl['mode'] == 'mode_07' else mode_14).create_poser(device, state_dicts=sds)
+    poser = (mode_14 if wl['mode'] == 'mode_14' else mode_07).create_poser(device, state_dicts=sds)
     poser.get_modules()
     ctx = poser.get_context()
     ctx.set_option('strict', args.strict)
     ctx.set_option('microbatch', 8)
+    distiller = None
+    if distill:
+        from tha4_b200.distill import BodyMorpherDistiller
+        student_sds, sdesc = load_state_dicts('mode_14')
+        distiller = BodyMorpherDistiller(poser, mode_14.load_body_morpher(None, student_sds['body_morpher']))
+        weights_desc += '; student: ' + sdesc
+    DISTILL_W, DISTILL_LR = [0.0, 1.0, 1.0, 0.0], 1e-4        # phase 1 of the body schedule: warp + grid-change terms
 
     img_dev = image.unsqueeze(0).expand(B, -1, -1, -1).contiguous().to(device)
     poses_dev = poses.to(device)
@@ -222,6 +230,8 @@ def main():
         torch.cuda.synchronize()
 
     def step_resident(i):
+        if distiller is not None:
+            return distiller.train_step(img_dev, poses_dev[i * B:(i + 1) * B], DISTILL_W, DISTILL_LR, want_losses=False)
         return poser.get_posing_outputs(img_dev, poses_dev[i * B:(i + 1) * B])
 
     # ---------------- device-resident timing ----------------
@@ -252,6 +262,9 @@ def main():
         def step_e2e(i):
             img_in.copy_(img_host, non_blocking=True)
             pose_in.copy_(poses_host[i * B:(i + 1) * B], non_blocking=True)
+            if distiller is not None:        # result of a training step = its loss terms, read back on the host
+                distiller.train_step(img_in, pose_in, DISTILL_W, DISTILL_LR, want_losses=True)
+                return
             out = poser.pose(img_in, pose_in)
             out_host.copy_(out, non_blocking=True)
             torch.cuda.current_stream().synchronize()      # the caller consumes the frame on the host
@@ -296,15 +309,16 @@ def main():
     value = frames / (ms / 1000.0)
     e2e_value = frames / (ms_e2e / 1000.0)
     line = {
-        'metric': '512x512 RGBA frames/sec', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+        'metric': 'distillation examples/sec' if distill else '512x512 RGBA frames/sec', 'value': value,
+        'unit': 'examples/s' if distill else 'frames/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'tf32 products, f32 accumulate/storage' if wl['mode'] == 'mode_07' and not args.strict else
+        'dtype': 'tf32 products, f32 accumulate/storage' if wl['mode'] in ('mode_07', 'distill') and not args.strict else
                  ('f32 (3xTF32)' if wl['mode'] == 'mode_07' else 'f16 products, f32 accumulate'),
         'data': 'synthetic poses; ' + weights_desc + '; lambda_00.png character image',
-        'config': {'workload': wl['desc'], 'batch_per_gpu': B, 'parallelism': 'frames sharded, no collective (dp%d)' % world,
+        'config': {'workload': wl['desc'], 'batch_per_gpu': B, 'parallelism': ('data parallel, one NCCL all-reduce of the 1.33 MB flat gradient per step (dp%d)' if distill else 'frames sharded, no collective (dp%d)') % world,
                    'l2': 'packed weights (657 MB teacher) and activations exceed the 126 MB L2; no explicit flush'},
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': B * (4 * 512 * 512 * 4 + 45 * 4),
-                'd2h_bytes_per_step': B * 4 * 512 * 512 * 4, 'ms_per_step': ms_e2e / args.steps},
+                'd2h_bytes_per_step': 32 if distill else B * 4 * 512 * 512 * 4, 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
         'clocks': clocks,
     }
@@ -336,7 +350,7 @@ def main():
             ach = 37.89e9 * B * args.steps / (s['us'] * 1e-6) / 1e12
             line['roofline'].update(achieved=ach, frac=ach / peaks['tflops'])
 
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not distill:
         threads = cpu_threads()
         budget = 6 if wl['mode'] == 'mode_07' else 12
         fps, nfr, dt = cpu_port_fps(wl['mode'], sds, image, poses, B, budget, threads)

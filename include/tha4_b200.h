@@ -49,6 +49,7 @@ const char* tha4_last_error(const tha4_ctx* ctx);
  *                    1: 3xTF32 error-compensated products == fp32 convolution),
  *          "microbatch" (frames processed per pass of the teacher pipeline; bounds the workspace),
  *          "tcgen05" (1, default: stride-1 convs run on the tcgen05/TMA/TMEM kernel; 0: everything on mma.sync),
+ *          "cluster_splitk" (1, default: K-split convs reduce through a thread-block cluster / DSMEM; 0: workspace + reduce kernel),
  *          "profile" (1: time every kernel class with CUDA events on the launching stream, 2: same + reset, 0: off) */
 int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value);
 /* counters: "kernel_launches" (kernels this library has launched so far), "workspace_bytes",

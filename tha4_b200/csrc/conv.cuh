@@ -69,6 +69,7 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s); 
 // the caller runs norm_stats on the output.
 bool conv_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
 bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
-void conv_enable_tc(bool on);                                                        // default: on
+void conv_enable_tc(bool on);
+void conv_tc_enable_cluster(bool on);   // split-K through a thread-block cluster + DSMEM (default) vs workspace + reduce kernel                                                        // default: on
 
 }  // namespace tha4

@@ -92,7 +92,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-template <int BN, int STAGES>
+// CS > 1: the K dimension is split over a thread-block cluster of CS CTAs (cluster dims {1,1,CS} along blockIdx.z); the
+// partial accumulators are exchanged through distributed shared memory and every CTA finishes 1/CS of the columns.
+template <int BN, int STAGES, int CS>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     constexpr int B_BYTES = BN * KCH * 4;
@@ -165,6 +167,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     umma_commit(smem_u32(bars + STAGES + s));          // frees the smem slot when these MMAs retire
                 }
                 umma_commit(smem_u32(bars + 2 * STAGES));              // accumulator complete -> epilogue
+            }
+        } else if (CS > 1) {   // ===== epilogue warps, cluster split-K: TMEM -> own shared-memory partial tile =====
+            const int q = warp & 3;
+            mbar_wait(smem_u32(bars + 2 * STAGES), 0);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const int row = q * 32 + lane;
+            float* Pt = reinterpret_cast<float*>(smem);                // [128][BN] fp32, 16-byte chunks XOR-swizzled by row
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int chunk = (c0 >> 2) + j;
+                    *reinterpret_cast<float4*>(Pt + row * BN + ((chunk ^ (row & 7)) << 2)) =
+                        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                }
             }
         } else {               // ===== epilogue warps: TMEM -> registers -> global =====
             const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
@@ -251,6 +270,70 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 }
             }
         }
+    }
+    if (CS > 1) {
+        // ---- cluster split-K reduction through distributed shared memory ----
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if (warp >= 2) {
+            constexpr int SL = BN / CS, SC = SL / 4;                   // columns / 16-byte chunks finished by this CTA
+            static_assert(SL >= 4 && 128 % SC == 0, "cluster slice");
+            const int te = threadIdx.x - 64;                           // 0..127
+            const int cc = te % SC;
+            const int chunk = split * SC + cc;                         // split == rank in the cluster
+            const int col = n0 + chunk * 4;
+            const uint32_t p_local = smem_u32(smem);
+            float su[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+#pragma unroll 1
+            for (int row = te / SC; row < 128; row += 128 / SC) {
+                const uint32_t off = (uint32_t)(row * BN + ((chunk ^ (row & 7)) << 2)) * 4u;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int pr = 0; pr < CS; ++pr) {
+                    uint32_t remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(p_local + off), "r"(pr));
+                    float4 v;
+                    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+                const int my = y0 + row / TILE_W, mx = x0 + row % TILE_W;
+                if (my >= p.MH || mx >= p.MW || col >= p.outC) continue;
+                const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
+                float v[4] = {acc.x, acc.y, acc.z, acc.w};
+                const int cn = min(4, p.outC - col);
+                if (p.bias) for (int j = 0; j < cn; ++j) v[j] += __ldg(p.bias + col + j);
+                if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
+                    const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
+                    const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + col;
+                    for (int j = 0; j < cn; ++j) v[j] += rr[j];
+                } else if (p.res_mode == RES_DOWN2) {
+                    const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + col;
+                    const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
+                    for (int j = 0; j < cn; ++j) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+                }
+                float* o = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld + col;
+                if (cn == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                else for (int j = 0; j < cn; ++j) o[j] = v[j];
+                for (int j = 0; j < cn; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
+            }
+            if (p.stats) {
+                float* red = reinterpret_cast<float*>(smem) + 128 * BN;          // [128][8], behind the partial tile
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { red[te * 8 + k] = su[k]; red[te * 8 + 4 + k] = sq[k]; }
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                if (te < SC && col < p.outC) {
+                    double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int t2 = te; t2 < 128; t2 += SC)
+                        for (int k = 0; k < 8; ++k) a8[k] += (double)red[t2 * 8 + k];
+                    double* d = p.stats + (long)(blockIdx.x % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + col) * 2;
+                    const int cn = min(4, p.outC - col);
+                    for (int k = 0; k < cn; ++k) { atomicAdd(d + 2 * k, a8[k]); atomicAdd(d + 2 * k + 1, a8[4 + k]); }
+                }
+            }
+        }
+        // peers may still be reading this CTA's shared memory: leave together
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -370,22 +453,41 @@ const CUtensorMap& weight_map(const ConvWeights& cw, int bn) {
     return g_maps.emplace(key, m).first->second;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CS = 1>
 void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
     constexpr size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BN * KCH * 4) + (2 * STAGES + 1) * 8 + 16;
+    static_assert(CS == 1 || (size_t)STAGES * (A_BYTES + BN * KCH * 4) >= (size_t)128 * BN * 4 + 128 * 8 * 4, "partial tile must fit");
     static bool configured = false;
     if (!configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    conv_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
+    if (CS == 1) {
+        conv_tc_kernel<BN, STAGES, CS><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = CS;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        THA4_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, CS>, ma, mb, p));
+    }
     THA4_LAUNCH_CHECK();
+}
+
+template <int BN, int STAGES>
+void launch_tc_cluster(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
+    if (cs == 8) launch_tc<BN, STAGES, 8>(ma, mb, p, grid, s);
+    else if (cs == 4) launch_tc<BN, STAGES, 4>(ma, mb, p, grid, s);
+    else launch_tc<BN, STAGES, 2>(ma, mb, p, grid, s);
 }
 
 }  // namespace
 
 namespace {
-struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW; };
+struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW; bool cluster; };
+bool g_use_cluster = true;
 TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
     TcPlan pl;
     pl.MH = a.out.H / cw.out_mul; pl.MW = a.out.W / cw.out_mul;
@@ -407,6 +509,19 @@ TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
     ksplit = std::max(1, std::min(ksplit, KT));
     const int k_per = (KT + ksplit - 1) / ksplit;
     pl.ksplit = (KT + k_per - 1) / k_per;          // every split owns at least one k-block
+    pl.cluster = false;
+    if (g_use_cluster && pl.ksplit > 1 && KT >= 2) {
+        // Split K over a thread-block cluster instead (partials meet in distributed shared memory, no workspace, no
+        // second kernel).  Cluster size 2/4/8; narrower N tiles buy back the CTA count the smaller split gives up.
+        int cs = 2;
+        while (cs < 8 && cs * 2 <= pl.ksplit && cs * 2 <= KT) cs *= 2;
+        int bn = pl.bn;
+        while (bn > 32 && (long)pl.tiles_m * (cw.cout_pad / bn) * cw.nphase * cs < 96 && cw.cout_pad % (bn / 2) == 0) bn /= 2;
+        const int kp = (KT + cs - 1) / cs;
+        if ((KT + kp - 1) / kp == cs) {            // every rank of the cluster must own k-blocks
+            pl.cluster = true; pl.ksplit = cs; pl.bn = bn; pl.tiles_n = cw.cout_pad / bn;
+        }
+    }
     return pl;
 }
 }  // namespace
@@ -414,13 +529,15 @@ TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
 size_t conv_workspace_floats(const ConvWeights& cw, const ConvArgs& a) {
     if (!conv_tc_supported(cw, a)) return 0;
     const TcPlan pl = tc_plan(cw, a);
-    if (pl.ksplit <= 1) return 0;
+    if (pl.ksplit <= 1 || pl.cluster) return 0;
     return (size_t)cw.nphase * pl.ksplit * pl.tiles_m * 128 * cw.cout_pad;
 }
 
+void conv_tc_enable_cluster(bool on) { g_use_cluster = on; }
+
 bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
     const TcPlan pl = tc_plan(cw, a);
-    if (pl.ksplit == 1) return true;
+    if (pl.ksplit == 1 || pl.cluster) return true;
     return a.ws && a.ws_floats >= (size_t)cw.nphase * pl.ksplit * pl.tiles_m * 128 * cw.cout_pad;
 }
 
@@ -454,14 +571,14 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     const int bn = pl.bn, tiles_m = pl.tiles_m, tiles_n = pl.tiles_n, ksplit = pl.ksplit;
     p.ksplit = ksplit;
     const size_t ws_need = (size_t)cw.nphase * ksplit * tiles_m * 128 * cw.cout_pad;
-    const bool use_ws = ksplit > 1 && a.ws && a.ws_floats >= ws_need;
+    const bool use_ws = !pl.cluster && ksplit > 1 && a.ws && a.ws_floats >= ws_need;
     p.ws = use_ws ? a.ws : nullptr; p.ws_rows = (long)tiles_m * 128; p.ws_ld = cw.cout_pad;
     // statistics: fused when the result is final in this launch sequence (single pass, or split-K with workspace)
-    p.stats = (ksplit == 1 || use_ws) ? a.out.stats : nullptr; p.stats_ld = a.out.stats_ld;
+    p.stats = (ksplit == 1 || use_ws || pl.cluster) ? a.out.stats : nullptr; p.stats_ld = a.out.stats_ld;
     p.stats_rep = std::max(1, a.out.stats_rep); p.stats_rep_stride = a.out.stats_rep_stride;
     ProfScope prof(PROF_CONV, s);
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
-    if (ksplit > 1 && !use_ws)
+    if (ksplit > 1 && !use_ws && !pl.cluster)
         THA4_CUDA_CHECK(cudaMemset2DAsync(a.out.p, (size_t)a.out.ld * sizeof(float), 0, (size_t)a.out.C * sizeof(float), a.out.pixels(), s));
     const CUtensorMap& ma = activation_map(a.in);
     const CUtensorMap& mb = weight_map(cw, bn);
@@ -476,6 +593,13 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     }
     const long total_ctas = (long)grid.x * grid.y * grid.z;
     const int stages_mode = forced >= 0 ? forced : (total_ctas <= 160 ? 0 : 2);
+    if (pl.cluster) {
+        if (bn == 256) launch_tc_cluster<256, 4>(ksplit, ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc_cluster<128, 6>(ksplit, ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc_cluster<64, 8>(ksplit, ma, mb, p, grid, s);
+        else launch_tc_cluster<32, 8>(ksplit, ma, mb, p, grid, s);
+        return;
+    }
     if (stages_mode == 0) {
         if (bn == 256) launch_tc<256, 4>(ma, mb, p, grid, s);
         else if (bn == 128) launch_tc<128, 6>(ma, mb, p, grid, s);
