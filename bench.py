@@ -173,12 +173,53 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_torch_cuda(args, rank):
+    """Context number (not part of the contract): the oracle's PyTorch ops executed on the GPU = what the reference's own
+    PyTorch-CUDA eager path does on this box (same ops, cuDNN/cuBLAS kernels, TF32 convs allowed as by torch's default)."""
+    if rank != 0:
+        return
+    from oracle import tha4_oracle
+    from tha4_b200 import synthetic
+    wl = WORKLOADS[args.workload]
+    mode = 'mode_14' if wl['mode'] == 'mode_14' else 'mode_07'
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    sds, _ = load_state_dicts(mode)
+    sds = {k: {kk: vv.to(dev) for kk, vv in v.items()} for k, v in sds.items()}
+    B = wl['batch']
+    image = load_inputs(wl).to(dev).unsqueeze(0).expand(B, -1, -1, -1).contiguous()
+    poses = synthetic.random_poses((args.warmup + args.steps) * B, seed=1234).to(dev)
+    fn = getattr(tha4_oracle, mode + '_outputs')
+    _orig = tha4_oracle.base_grid
+    tha4_oracle.base_grid = lambda n, h, w, dtype=torch.float32: _orig(n, h, w, dtype).to(dev)
+    tha4_oracle._timestep_embedding_zero_orig = tha4_oracle._timestep_embedding_zero
+    tha4_oracle._timestep_embedding_zero = lambda n, c: tha4_oracle._timestep_embedding_zero_orig(n, c).to(dev)
+    kw = {}
+    with torch.no_grad():
+        if mode == 'mode_07':
+            kw = dict(cached_decomposer_output=tha4_oracle.eyebrow_decomposer(sds['eyebrow_decomposer'], image[:, :, 64:192, 192:320]))
+        for i in range(args.warmup):
+            fn(sds, image, poses[i * B:(i + 1) * B], **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            fn(sds, image, poses[(args.warmup + i) * B:(args.warmup + i + 1) * B], **kw)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({'impl': 'torch_cuda_eager', 'metric': '512x512 RGBA frames/sec', 'value': args.steps * B / (ms / 1000.0),
+                      'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'steps': args.steps, 'warmup': args.warmup,
+                      'config': {'workload': wl['desc']},
+                      'note': 'PyTorch eager on the same GPU running the oracle port (the ops the reference dispatches); context only'}),
+          flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='tha4_b200', choices=['tha4_b200', 'reference'])
+    ap.add_argument('--impl', default='tha4_b200', choices=['tha4_b200', 'reference', 'torch_cuda'])
     ap.add_argument('--workload', default='teacher_b1', choices=sorted(WORKLOADS))
     ap.add_argument('--strict', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -190,6 +231,9 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
         run_reference(args, rank, world)
+        return
+    if args.impl == 'torch_cuda':
+        run_torch_cuda(args, rank)
         return
 
     wl = WORKLOADS[args.workload]

@@ -50,6 +50,8 @@ const char* tha4_last_error(const tha4_ctx* ctx);
  *          "microbatch" (frames processed per pass of the teacher pipeline; bounds the workspace),
  *          "tcgen05" (1, default: stride-1 convs run on the tcgen05/TMA/TMEM kernel; 0: everything on mma.sync),
  *          "cluster_splitk" (1, default: K-split convs reduce through a thread-block cluster / DSMEM; 0: workspace + reduce kernel),
+ *          "persistent_conv" (0 default; 1: GPU-filling convs run on the persistent halo-reuse tcgen05 kernel),
+ *          "conv_mt2" (0 default; 1: GPU-filling convs use two 128-pixel tiles per CTA sharing each weight tile),
  *          "profile" (1: time every kernel class with CUDA events on the launching stream, 2: same + reset, 0: off) */
 int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value);
 /* counters: "kernel_launches" (kernels this library has launched so far), "workspace_bytes",

@@ -192,6 +192,8 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         if (!strcmp(name, "strict")) { ctx->strict = value ? 1 : 0; }
         else if (!strcmp(name, "tcgen05")) conv_enable_tc(value != 0);
         else if (!strcmp(name, "cluster_splitk")) conv_tc_enable_cluster(value != 0);
+        else if (!strcmp(name, "persistent_conv")) conv_tcp_enable(value != 0);
+        else if (!strcmp(name, "conv_mt2")) conv_tc_enable_mt2(value != 0);
         else if (!strcmp(name, "profile")) { prof_enable(value != 0); if (value == 2) prof_reset(); }
         else if (!strcmp(name, "microbatch")) { THA4_REQUIRE(value >= 1 && value <= 1024, "microbatch range"); ctx->microbatch = (int)value; }
         else throw std::runtime_error(std::string("tha4: unknown option ") + name);

@@ -69,7 +69,11 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s); 
 // the caller runs norm_stats on the output.
 bool conv_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
 bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
+bool conv_tcp_supported(const ConvWeights& cw, const ConvArgs& a);                    // conv_tcp.cu (persistent, halo reuse)
+void conv_tcp_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);
+void conv_tcp_enable(bool on);
 void conv_enable_tc(bool on);
-void conv_tc_enable_cluster(bool on);   // split-K through a thread-block cluster + DSMEM (default) vs workspace + reduce kernel                                                        // default: on
+void conv_tc_enable_cluster(bool on);
+void conv_tc_enable_mt2(bool on);       // two 128-pixel tiles per CTA sharing each weight tile (default on)   // split-K through a thread-block cluster + DSMEM (default) vs workspace + reduce kernel                                                        // default: on
 
 }  // namespace tha4

@@ -13,6 +13,7 @@
 // and the nearest-upsample-fused gather stay on the mma.sync kernel in conv.cu.
 #include "conv.cuh"
 #include "profiler.cuh"
+#include "tc_common.cuh"
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
@@ -22,9 +23,10 @@
 namespace tha4 {
 namespace {
 
+using namespace tc;
+
 constexpr int TILE_W = 16, TILE_H = 8;          // 128 output pixels per CTA
-constexpr int KCH = 32;                          // channels per k-block (128 bytes of fp32 = one swizzle row)
-constexpr int A_BYTES = 128 * KCH * 4;           // 16 KB
+constexpr int A_BYTES1 = 128 * KCH * 4;          // 16 KB per 128-pixel tile
 constexpr int TC_THREADS = 192;                  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
 struct TcParams {
@@ -40,65 +42,18 @@ struct TcParams {
     signed char ph_oy[CONV_MAX_PHASES], ph_ox[CONV_MAX_PHASES];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    const long long t0 = clock64();
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) break;
-        if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s watchdog: fail loudly instead of hanging the GPU
-    }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
-                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
-                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
-
-// K-major, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1 (Blackwell).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    const uint32_t lo = ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
-    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    return ((uint64_t)hi << 32) | lo;
-}
-
 // CS > 1: the K dimension is split over a thread-block cluster of CS CTAs (cluster dims {1,1,CS} along blockIdx.z); the
 // partial accumulators are exchanged through distributed shared memory and every CTA finishes 1/CS of the columns.
-template <int BN, int STAGES, int CS>
+// MT = 2: the CTA owns two vertically adjacent 16x8 pixel tiles (M = 256 as two M = 128 MMAs per k-step into two TMEM
+// accumulators) that SHARE every weight tile -- operand traffic per MAC drops by a third to a half, which is what
+// bounds these kernels (L2 -> shared memory at ~40 B/clk/SM).
+template <int BN, int STAGES, int CS, int MT>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    static_assert(MT == 1 || CS == 1, "the two-tile variant is for unsplit launches");
     constexpr int B_BYTES = BN * KCH * 4;
-    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr int A_BYTES = MT * A_BYTES1;
+    constexpr int TMEM_COLS = MT * BN < 32 ? 32 : MT * BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smA = smem;
@@ -112,7 +67,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int tx = tile % p.tiles_x; tile /= p.tiles_x;
     const int ty = tile % p.tiles_y;
     const int n = tile / p.tiles_y;
-    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+    const int x0 = tx * TILE_W, y0 = ty * TILE_H * MT;
     const int n0 = blockIdx.y * BN;
     const int phase = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
     const int KT = p.ntaps * p.cpt;
@@ -162,8 +117,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     const uint64_t adesc = make_smem_desc(smem_u32(smA + s * A_BYTES));
                     const uint64_t bdesc = make_smem_desc(smem_u32(smB + s * B_BYTES));
 #pragma unroll
-                    for (int k = 0; k < KCH / 8; ++k)     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (>>4)
-                        umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int h = 0; h < MT; ++h)
+#pragma unroll
+                        for (int k = 0; k < KCH / 8; ++k)     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (>>4)
+                            umma_tf32(tmem_base + (uint32_t)(h * BN), adesc + (uint64_t)(h * (A_BYTES1 >> 4)) + 2 * k, bdesc + 2 * k, idesc,
+                                      (i > 0 || k > 0) ? 1u : 0u);
                     umma_commit(smem_u32(bars + STAGES + s));          // frees the smem slot when these MMAs retire
                 }
                 umma_commit(smem_u32(bars + 2 * STAGES));              // accumulator complete -> epilogue
@@ -190,16 +148,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             mbar_wait(smem_u32(bars + 2 * STAGES), 0);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const int row = q * 32 + lane;
-            const int my = y0 + row / TILE_W, mx = x0 + row % TILE_W;
-            const bool valid = my < p.MH && mx < p.MW;
-            const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
-            float* orow = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld;
             const bool lead = (split == 0);
             float* scratch = reinterpret_cast<float*>(smA) + q * (32 * 33);   // pipeline smem is idle once tmem_full fired
 #pragma unroll 1
+            for (int h = 0; h < MT; ++h) {
+            const int my = y0 + h * TILE_H + row / TILE_W, mx = x0 + row % TILE_W;
+            const bool valid = my < p.MH && mx < p.MW;
+            const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
+            float* orow = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld;
+#pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + c0), r);
                 const int cbase = n0 + c0;
                 if (cbase >= p.outC) continue;                         // warp-uniform
                 float v[32];
@@ -268,7 +228,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     atomicAdd(base + 2 * c, (double)a.x + (double)b.x + (double)cc.x + (double)d.x);
                     atomicAdd(base + 2 * c + 1, (double)a.y + (double)b.y + (double)cc.y + (double)d.y);
                 }
+                if (MT > 1) asm volatile("bar.sync 1, 128;\n" ::: "memory");     // `part` is reused by the second tile
             }
+            }   // h
         }
     }
     if (CS > 1) {
@@ -423,14 +385,14 @@ EncodeTiledFn get_encode() {
 using MapKey = std::tuple<const void*, long, long, long, long, long, int>;
 std::map<MapKey, CUtensorMap> g_maps;
 
-const CUtensorMap& activation_map(const View& v) {
-    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -1};
+const CUtensorMap& activation_map(const View& v, int mt) {
+    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -mt};
     auto it = g_maps.find(key);
     if (it != g_maps.end()) return it->second;
     CUtensorMap m;
     cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
     cuuint64_t strides[3] = {(cuuint64_t)v.ld * 4, (cuuint64_t)v.W * v.ld * 4, (cuuint64_t)v.H * v.W * v.ld * 4};
-    cuuint32_t box[4] = {KCH, TILE_W, TILE_H, 1};
+    cuuint32_t box[4] = {KCH, TILE_W, (cuuint32_t)(TILE_H * mt), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -453,17 +415,19 @@ const CUtensorMap& weight_map(const ConvWeights& cw, int bn) {
     return g_maps.emplace(key, m).first->second;
 }
 
-template <int BN, int STAGES, int CS = 1>
+template <int BN, int STAGES, int CS = 1, int MT = 1>
 void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
+    constexpr int A_BYTES = MT * A_BYTES1;
     constexpr size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BN * KCH * 4) + (2 * STAGES + 1) * 8 + 16;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
     static_assert(CS == 1 || (size_t)STAGES * (A_BYTES + BN * KCH * 4) >= (size_t)128 * BN * 4 + 128 * 8 * 4, "partial tile must fit");
     static bool configured = false;
     if (!configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, CS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     if (CS == 1) {
-        conv_tc_kernel<BN, STAGES, CS><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
+        conv_tc_kernel<BN, STAGES, CS, MT><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
     } else {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -471,7 +435,7 @@ void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = CS;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        THA4_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, CS>, ma, mb, p));
+        THA4_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, CS, MT>, ma, mb, p));
     }
     THA4_LAUNCH_CHECK();
 }
@@ -486,15 +450,23 @@ void launch_tc_cluster(int cs, const CUtensorMap& ma, const CUtensorMap& mb, con
 }  // namespace
 
 namespace {
-struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW; bool cluster; };
+struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW, mt; bool cluster; };
+bool g_use_mt2 = false;    // measured: no gain (the narrow layers are bound by the MMA's own shared-memory operand reads, not by L2)
 bool g_use_cluster = true;
 TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
     TcPlan pl;
     pl.MH = a.out.H / cw.out_mul; pl.MW = a.out.W / cw.out_mul;
     pl.tiles_x = ceil_div(pl.MW, TILE_W); pl.tiles_y = ceil_div(pl.MH, TILE_H);
+    pl.mt = 1;
     pl.bn = (cw.cout_pad % 256 == 0) ? 256 : (cw.cout_pad % 128 == 0 ? 128 : (cw.cout_pad % 64 == 0 ? 64 : 32));
     pl.tiles_m = pl.tiles_x * pl.tiles_y * a.in.N;
     pl.tiles_n = cw.cout_pad / pl.bn;
+    // two-tile CTAs (M = 256) when that still fills the GPU about twice over
+    if (g_use_mt2 && a.ksplit <= 1 && (long)pl.tiles_x * ceil_div(pl.MH, 2 * TILE_H) * a.in.N * pl.tiles_n * cw.nphase >= 280) {
+        pl.mt = 2;
+        pl.tiles_y = ceil_div(pl.MH, 2 * TILE_H);
+        pl.tiles_m = pl.tiles_x * pl.tiles_y * a.in.N;
+    }
     const int KT = cw.ntaps * (cw.cin_pad / KCH);
     int ksplit = a.ksplit;
     if (ksplit <= 0) {
@@ -527,13 +499,14 @@ TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
 }  // namespace
 
 size_t conv_workspace_floats(const ConvWeights& cw, const ConvArgs& a) {
-    if (!conv_tc_supported(cw, a)) return 0;
+    if (!conv_tc_supported(cw, a) || conv_tcp_supported(cw, a)) return 0;
     const TcPlan pl = tc_plan(cw, a);
     if (pl.ksplit <= 1 || pl.cluster) return 0;
     return (size_t)cw.nphase * pl.ksplit * pl.tiles_m * 128 * cw.cout_pad;
 }
 
 void conv_tc_enable_cluster(bool on) { g_use_cluster = on; }
+void conv_tc_enable_mt2(bool on) { g_use_mt2 = on; }
 
 bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
     const TcPlan pl = tc_plan(cw, a);
@@ -580,7 +553,7 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
     if (ksplit > 1 && !use_ws && !pl.cluster)
         THA4_CUDA_CHECK(cudaMemset2DAsync(a.out.p, (size_t)a.out.ld * sizeof(float), 0, (size_t)a.out.C * sizeof(float), a.out.pixels(), s));
-    const CUtensorMap& ma = activation_map(a.in);
+    const CUtensorMap& ma = activation_map(a.in, pl.mt);
     const CUtensorMap& mb = weight_map(cw, bn);
     dim3 grid(tiles_m, tiles_n, cw.nphase * ksplit);
     // Pipeline depth: grids that cannot even fill the GPU once (the B=1 bottleneck layers, which stream their weights
@@ -590,6 +563,13 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     if (forced == -2) {
         const char* e = getenv("THA4_TC_STAGES");
         forced = !e ? -1 : (!strcmp(e, "deep") ? 0 : (!strcmp(e, "mid") ? 1 : 2));
+    }
+    if (pl.mt == 2) {          // M = 256 per CTA, accumulators MT x BN columns of TMEM
+        if (bn == 256) launch_tc<256, 3, 1, 2>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<128, 4, 1, 2>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<64, 2, 1, 2>(ma, mb, p, grid, s);
+        else launch_tc<32, 2, 1, 2>(ma, mb, p, grid, s);
+        return;
     }
     const long total_ctas = (long)grid.x * grid.y * grid.z;
     const int stages_mode = forced >= 0 ? forced : (total_ctas <= 160 ? 0 : 2);

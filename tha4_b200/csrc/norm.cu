@@ -132,8 +132,49 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
         __syncthreads();
     }
     const unsigned ucq = (unsigned)cq;
+    const unsigned utotal = (unsigned)total, stride = gridDim.x * blockDim.x;
+    if (!pool) {
+        // streaming path: 4 independent float4 items per thread in flight (32-bit index math; total < 2^31 float4s)
+        const long nbase = FUSED ? (long)n_fixed * yH * yW : 0;
+        for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < utotal; i0 += 4 * stride) {
+            float4 v[4], rv[4];
+            unsigned q[4]; long pix[4]; bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned i = i0 + u * stride;
+                ok[u] = i < utotal;
+                const unsigned p0 = ok[u] ? i / ucq : 0u;
+                q[u] = ok[u] ? i - p0 * ucq : 0u;
+                pix[u] = nbase + p0;
+                if (ok[u]) {
+                    v[u] = *reinterpret_cast<const float4*>(x + pix[u] * x_ld + 4 * q[u]);
+                    if (res) rv[u] = *reinterpret_cast<const float4*>(res + pix[u] * res_ld + 4 * q[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ok[u]) continue;
+                float4 c0, c1;
+                if (FUSED) {
+                    const float4* sc = reinterpret_cast<const float4*>(sm_coef + 4 * q[u]);
+                    c0 = sc[0]; c1 = sc[1];
+                } else {
+                    const int n = (int)(pix[u] / ((long)yH * yW));
+                    c0 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q[u]) * 2);
+                    c1 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q[u]) * 2 + 4);
+                }
+                float4 r;
+                r.x = act_apply(v[u].x * c0.x + c0.y, act); r.y = act_apply(v[u].y * c0.z + c0.w, act);
+                r.z = act_apply(v[u].z * c1.x + c1.y, act); r.w = act_apply(v[u].w * c1.z + c1.w, act);
+                if (res) { r.x += rv[u].x; r.y += rv[u].y; r.z += rv[u].z; r.w += rv[u].w; }
+                if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+                *reinterpret_cast<float4*>(y + pix[u] * y_ld + 4 * q[u]) = r;
+            }
+        }
+        return;
+    }
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-        // i enumerates (pixel, channel quad) of the output; samples are folded into `pix` (FUSED: offset by n_fixed)
+        // pooled path: i enumerates (output pixel, channel quad); samples are folded into `pix` (FUSED: offset by n_fixed)
         const long pix0 = (long)((unsigned long long)i / ucq);
         const int q = (int)(i - pix0 * ucq);
         const long pix = FUSED ? pix0 + (long)n_fixed * yH * yW : pix0;
@@ -146,26 +187,19 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
             c0 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2);
             c1 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2 + 4);
         }
-        float4 r;
-        if (!pool) {
-            const float4 v = *reinterpret_cast<const float4*>(x + pix * x_ld + 4 * q);
-            r.x = act_apply(v.x * c0.x + c0.y, act); r.y = act_apply(v.y * c0.z + c0.w, act);
-            r.z = act_apply(v.z * c1.x + c1.y, act); r.w = act_apply(v.w * c1.z + c1.w, act);
-        } else {
-            const long pin = pix0 - (long)(FUSED ? 0 : n) * yH * yW;       // pixel index within the sample
-            const int oy = (int)(pin / yW), ox = (int)(pin - (long)oy * yW);
-            r = make_float4(0.f, 0.f, 0.f, 0.f);
+        const long pin = pix0 - (long)(FUSED ? 0 : n) * yH * yW;       // pixel index within the sample
+        const int oy = (int)(pin / yW), ox = (int)(pin - (long)oy * yW);
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
+        for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const float4 v = *reinterpret_cast<const float4*>(
-                        x + (((long)n * xH + 2 * oy + dy) * xW + 2 * ox + dx) * x_ld + 4 * q);
-                    r.x += act_apply(v.x * c0.x + c0.y, act); r.y += act_apply(v.y * c0.z + c0.w, act);
-                    r.z += act_apply(v.z * c1.x + c1.y, act); r.w += act_apply(v.w * c1.z + c1.w, act);
-                }
-            r.x *= 0.25f; r.y *= 0.25f; r.z *= 0.25f; r.w *= 0.25f;
-        }
+            for (int dx = 0; dx < 2; ++dx) {
+                const float4 v = *reinterpret_cast<const float4*>(
+                    x + (((long)n * xH + 2 * oy + dy) * xW + 2 * ox + dx) * x_ld + 4 * q);
+                r.x += act_apply(v.x * c0.x + c0.y, act); r.y += act_apply(v.y * c0.z + c0.w, act);
+                r.z += act_apply(v.z * c1.x + c1.y, act); r.w += act_apply(v.w * c1.z + c1.w, act);
+            }
+        r.x *= 0.25f; r.y *= 0.25f; r.z *= 0.25f; r.w *= 0.25f;
         if (res) {
             const float4 v = *reinterpret_cast<const float4*>(res + pix * res_ld + 4 * q);
             r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
@@ -208,7 +242,8 @@ void norm_apply(const View& x, const float* coef, int act, int pool, const View*
                 int round_out) {
     check_apply(x, pool, res, y);
     const long total = (long)y.N * y.H * y.W * (y.C / 4);
-    const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    THA4_REQUIRE(total < (1L << 31), "norm_apply: tensor too large for 32-bit indexing");
+    const int blocks = (int)std::max<long>(1, std::min<long>((total + 1023) / 1024, 148L * 8));
     ProfScope prof(PROF_NORM, s);
     prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() + y.pixels() + (res ? y.pixels() : 0)) * x.C * 4);
     norm_apply_kernel<false><<<blocks, 256, 0, s>>>(x.p, x.H, x.W, x.ld, coef, act, pool, res ? res->p : nullptr,
@@ -224,7 +259,8 @@ void norm_apply_fused(const View& x, int groups, const float* gamma, const float
     THA4_REQUIRE(x.stats != nullptr, "norm_apply_fused: view has no statistics");
     THA4_REQUIRE(groups == 0 || x.C % groups == 0, "norm_apply_fused: groups");
     const long per_sample = (long)y.H * y.W * (y.C / 4);
-    const int bx = (int)std::max<long>(1, std::min<long>((per_sample + 255) / 256, std::max(1, 148 * 16 / y.N)));
+    THA4_REQUIRE(per_sample < (1L << 31), "norm_apply: tensor too large for 32-bit indexing");
+    const int bx = (int)std::max<long>(1, std::min<long>((per_sample + 1023) / 1024, std::max(1, 148 * 8 / y.N)));
     ProfScope prof(PROF_NORM, s);
     prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() + y.pixels() + (res ? y.pixels() : 0)) * x.C * 4);
     // per-sample pointers: grid.y selects the sample, the kernel indexes within it
