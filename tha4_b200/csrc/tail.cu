@@ -17,10 +17,12 @@
 namespace tha4 {
 namespace {
 
-constexpr int TILE = 16, HALO = TILE + 2;
+constexpr int TILE = 16, TILE_H = 8, HALO = TILE + 2, HALO_H = TILE_H + 2;    // 16 x 8 output pixels per CTA (4 warps x 2 rows)
+constexpr int TAIL_THREADS = 128;
 constexpr int CO_PAD = TAIL_CO_PAD;
-constexpr int WPITCH = 24;      // floats per (tap, channel) row of the staged weights: conflict-free B-fragment loads
 constexpr int OPITCH = 17;      // floats per pixel of the transposed accumulators
+// floats per (tap, channel) row of the staged weights, chosen for conflict-free B-fragment loads: bank = pitch*t + g
+__host__ __device__ constexpr int wpitch(int nt) { return nt == 1 ? 8 : 24; }
 
 __device__ __forceinline__ void store4(float* out, long plane, long pix, const float (&v)[4]) {
 #pragma unroll
@@ -42,32 +44,33 @@ __device__ __forceinline__ void split_tf32(float v, unsigned& hi, unsigned& lo) 
 }
 
 template <int KIND, int NT, bool STRICT>
-__global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ feat, int S, int C, int ld,
+__global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const float* __restrict__ feat, int S, int C, int ld,
                                                    const float* __restrict__ coef, int act,
                                                    const float* __restrict__ wg, const float* __restrict__ bg,
                                                    ImgView img0, ImgView img1, const float* __restrict__ base,
                                                    float* o0, float* o1, float* o2, float* o3, float* o4, float* o5,
                                                    float* o6, float* o7) {
     extern __shared__ __align__(16) float sm[];
+    constexpr int WPITCH = wpitch(NT);
     const int CP = C + 4;                     // halo pixel pitch: (4*g + t) mod 32 distinct for the A fragments
     float* wsm = sm;                          // [9*C][WPITCH]
-    float* fsm = sm + 9 * C * WPITCH;         // [HALO*HALO][CP]
-    float* osm = fsm;                         // [256][OPITCH], reuses the halo tile after the MMAs
+    float* fsm = sm + 9 * C * WPITCH;         // [HALO_H*HALO][CP]
+    float* osm = fsm;                         // [128][OPITCH], reuses the halo tile after the MMAs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int n = blockIdx.z;
-    const int by0 = blockIdx.y * TILE, bx0 = blockIdx.x * TILE;
+    const int by0 = blockIdx.y * TILE_H, bx0 = blockIdx.x * TILE;
 
-    for (int i = tid; i < 9 * C * (CO_PAD / 4); i += 256) {
-        const int row = i / (CO_PAD / 4), part = i - row * (CO_PAD / 4);
+    constexpr int WQ = NT * 2;                // float4 chunks of head weights actually used (8 or 16 columns; 12..15 are zero)
+    for (int i = tid; i < 9 * C * WQ; i += TAIL_THREADS) {
+        const int row = i / WQ, part = i - row * WQ;
+        if (4 * part >= CO_PAD) { *reinterpret_cast<float4*>(wsm + row * WPITCH + 4 * part) = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
         float4 wv = *reinterpret_cast<const float4*>(wg + row * CO_PAD + 4 * part);
         if (!STRICT) { wv.x = round_tf32(wv.x); wv.y = round_tf32(wv.y); wv.z = round_tf32(wv.z); wv.w = round_tf32(wv.w); }
         *reinterpret_cast<float4*>(wsm + row * WPITCH + 4 * part) = wv;
     }
-    if (CO_PAD < 16)
-        for (int i = tid; i < 9 * C; i += 256) *reinterpret_cast<float4*>(wsm + i * WPITCH + 12) = make_float4(0.f, 0.f, 0.f, 0.f);
     const int cq = C >> 2;
-    for (int i = tid; i < HALO * HALO * cq; i += 256) {
+    for (int i = tid; i < HALO_H * HALO * cq; i += TAIL_THREADS) {
         const int q = i % cq, hp = i / cq;
         const int hy = hp / HALO, hx = hp - hy * HALO;
         const int gy = by0 + hy - 1, gx = bx0 + hx - 1;
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea
     }
     __syncthreads();
 
-    // ---- head conv on tensor cores: warp w owns tile rows 2w and 2w+1 (16 pixels each = one m16 tile) ----
+    // ---- head conv on tensor cores: warp w (of 4) owns tile rows 2w and 2w+1 (16 pixels each = one m16 tile) ----
     float acc[2][NT][4];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(256) tail_kernel(const float* __restrict__ fea
     const int ty = tid / TILE, tx = tid % TILE;
     float o[CO_PAD];
 #pragma unroll
-    for (int j = 0; j < CO_PAD; ++j) o[j] = (j < NT * 8) ? osm[tid * OPITCH + j] + bg[j] : 0.0f;
+    for (int j = 0; j < CO_PAD; ++j) o[j] = (j < NT * 8) ? osm[tid * OPITCH + j] + bg[j] : 0.0f;     // 128 threads = 128 pixels
 
     const int y = by0 + ty, x = bx0 + tx;
     const long plane = (long)S * S, pix = (long)y * S + x;
@@ -247,8 +250,8 @@ template <int KIND, int NT, bool STRICT>
 void launch_tail(const TailWeights& tw, const View& f, const float* coef, int act, const ImgView& i0, const ImgView& i1,
                  float* const* o, int nout, cudaStream_t s) {
     THA4_REQUIRE(tw.C % 8 == 0 && tw.CO <= NT * 8, "tail: head channel layout");
-    const size_t halo = (size_t)HALO * HALO * (tw.C + 4), outs = (size_t)TILE * TILE * OPITCH;
-    const size_t smem = ((size_t)9 * tw.C * WPITCH + std::max(halo, outs)) * sizeof(float);
+    const size_t halo = (size_t)HALO_H * HALO * (tw.C + 4), outs = (size_t)TILE * TILE_H * OPITCH;
+    const size_t smem = ((size_t)9 * tw.C * wpitch(NT) + std::max(halo, outs)) * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {
         THA4_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel<KIND, NT, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -256,14 +259,14 @@ void launch_tail(const TailWeights& tw, const View& f, const float* coef, int ac
     }
     float* op[8];
     for (int i = 0; i < 8; ++i) op[i] = i < nout ? o[i] : nullptr;
-    dim3 grid(f.W / TILE, f.H / TILE, f.N);
+    dim3 grid(f.W / TILE, f.H / TILE_H, f.N);
     ProfScope prof(PROF_TAIL, s);
     {   // compulsory traffic: feature map + 4-channel image(s) read once, every returned tensor written once
         const int out_ch[4] = {15, 18, 24, 24};
         const int img_ch = (KIND == TAIL_COMBINER) ? 8 : 4;
         prof_add_work(PROF_TAIL, 2.0 * f.pixels() * 9 * tw.C * tw.CO, (double)f.pixels() * (f.C + img_ch + out_ch[KIND]) * 4);
     }
-    tail_kernel<KIND, NT, STRICT><<<grid, 256, smem, s>>>(f.p, f.H, f.C, f.ld, coef, act, tw.w, tw.bias, i0, i1,
+    tail_kernel<KIND, NT, STRICT><<<grid, TAIL_THREADS, smem, s>>>(f.p, f.H, f.C, f.ld, coef, act, tw.w, tw.bias, i0, i1,
                                              base_grid_table(f.H), op[0], op[1], op[2], op[3], op[4], op[5], op[6], op[7]);
     THA4_LAUNCH_CHECK();
 }
