@@ -11,8 +11,9 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import gpu_util as G  # noqa: E402
 
 
-def bench(kind, N, Cin, H, Cout, ksplit=0, cluster=1, reps=20, persistent=0, mt2=1):
+def bench(kind, N, Cin, H, Cout, ksplit=0, cluster=1, reps=20, persistent=0, mt2=0, half=0):
     c = G.ctx()
+    c.set_option('half_operands', half)
     c.set_option('cluster_splitk', cluster)
     c.set_option('persistent_conv', persistent)
     c.set_option('conv_mt2', mt2)
@@ -29,8 +30,9 @@ def bench(kind, N, Cin, H, Cout, ksplit=0, cluster=1, reps=20, persistent=0, mt2
     c.set_option('cluster_splitk', 1)
     gf = 2.0 * N * H * H * Cout * Cin * k * k / 1e9
     c.set_option('persistent_conv', 0)
-    c.set_option('conv_mt2', 1)
-    print('kind %d N%d Cin%4d H%3d Cout%4d ksplit %2d cluster %d persistent %d mt2 %d : %7.1f us  %7.1f TFLOP/s' % (kind, N, Cin, H, Cout, ksplit, cluster, persistent, mt2, us, gf / us * 1e3))
+    c.set_option('conv_mt2', 0)
+    c.set_option('half_operands', 1)
+    print('kind %d N%d Cin%4d H%3d Cout%4d ksplit %2d cluster %d persistent %d mt2 %d half %d : %7.1f us  %7.1f TFLOP/s' % (kind, N, Cin, H, Cout, ksplit, cluster, persistent, mt2, half, us, gf / us * 1e3))
 
 
 if __name__ == '__main__':

@@ -99,16 +99,24 @@ CONV_CASES = [
     (4, 2, 128, 16, 128, True, 2, 0, 0),         # phase-decomposed nearest-x2 + 3x3 (+ upsampled residual)
     (4, 1, 64, 24, 64, True, 0, 0, 0),
     (4, 1, 256, 16, 256, True, 0, 0, 4),
+    (0, 1, 32, 64, 32, True, 0, 0, 0),           # f16 operands: 64-byte rows (Cin % 64 == 32)
+    (0, 1, 160, 32, 64, True, 1, 0, 0),
+    (0, 1, 528, 16, 512, False, 0, 0, 0),        # pose-concat bottleneck as the f16 path sees it (pose padded to 16)
+    (0, 1, 544, 24, 512, False, 0, 0, 3),
+    (3, 1, 512, 16, 1536, True, 0, 0, 0),        # attention qkv
 ]
 
 
 @pytest.mark.parametrize('case', CONV_CASES)
-@pytest.mark.parametrize('path', ['strict_mma', 'tf32_tcgen05', 'tf32_mma'])
+@pytest.mark.parametrize('path', ['strict_mma', 'tf32_tcgen05', 'f16_tcgen05', 'tf32_mma'])
 def test_conv_vs_torch(case, path):
     """strict_mma: 3xTF32 mma.sync (== fp32); tf32_tcgen05: TMA + tcgen05.mma kind::tf32 where the configuration is
-    supported (stride-1 taps, no fused upsample), else mma.sync; tf32_mma: single-TF32 mma.sync everywhere."""
+    supported (stride-1 taps, no fused upsample), else mma.sync; f16_tcgen05: the same kernel with f16 operands
+    (kind::f16, 128- or 64-byte rows) where Cin % 8 == 0, as the networks run it behind a normalisation layer;
+    tf32_mma: single-TF32 mma.sync everywhere."""
     strict = 1 if path == 'strict_mma' else 0
     G.ctx().set_option('tcgen05', 0 if path == 'tf32_mma' else 1)
+    G.ctx().set_option('half_operands', 1 if path == 'f16_tcgen05' else 0)
     kind, N, Cin, H, Cout, has_bias, res_mode, in_up, ksplit = case
     g = _gen(hash(case) % 10000)
     k = {0: 3, 1: 4, 2: 4, 3: 1, 4: 3}[kind]
@@ -127,6 +135,7 @@ def test_conv_vs_torch(case, path):
     mx, mean = G.err(out, ref)
     tol = (6e-5 if kind == 4 else 2e-5) if strict else 6e-3     # kind 4 pre-sums weights: (a+b)x vs ax+bx rounding          # 3xTF32 == fp32; single TF32: 2^-11 relative per product
     G.ctx().set_option('tcgen05', 1)
+    G.ctx().set_option('half_operands', 1)
     assert mx < tol * max(1.0, ref.abs().max().item()), (case, path, mx, mean)
 
 

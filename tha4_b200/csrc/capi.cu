@@ -16,6 +16,7 @@ struct tha4_ctx {
     std::string err;
     int strict = 0;
     int microbatch = 8;
+    int half_operands = 1;                 // f16 conv operands between normalisation and tcgen05 conv (non-strict mode)
     Pool persist, scratch;
     int* flag = nullptr;
     double* loss_acc = nullptr;            // 4 doubles: L1 sums of the distillation step
@@ -50,6 +51,7 @@ int guarded(tha4_ctx* ctx, F&& f) {
 Runtime make_rt(tha4_ctx* ctx, void* stream) {
     Runtime rt;
     rt.persist = &ctx->persist; rt.scratch = &ctx->scratch; rt.stream = (cudaStream_t)stream; rt.strict = ctx->strict;
+    rt.f16 = ctx->half_operands && !ctx->strict && conv_tc_enabled();
     rt.stats_base = ctx->stats_base; rt.stats_cap = ctx->stats_cap; rt.stats_off = &ctx->stats_off;
     return rt;
 }
@@ -194,6 +196,7 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         else if (!strcmp(name, "cluster_splitk")) conv_tc_enable_cluster(value != 0);
         else if (!strcmp(name, "persistent_conv")) conv_tcp_enable(value != 0);
         else if (!strcmp(name, "conv_mt2")) conv_tc_enable_mt2(value != 0);
+        else if (!strcmp(name, "half_operands")) ctx->half_operands = value ? 1 : 0;
         else if (!strcmp(name, "profile")) { prof_enable(value != 0); if (value == 2) prof_reset(); }
         else if (!strcmp(name, "microbatch")) { THA4_REQUIRE(value >= 1 && value <= 1024, "microbatch range"); ctx->microbatch = (int)value; }
         else throw std::runtime_error(std::string("tha4: unknown option ") + name);
@@ -433,6 +436,12 @@ int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, cons
         View yo = mk(Ho, Wo, Cout);
         ConvArgs a;
         a.in = xin; a.in_up = in_up; a.out = yo; a.strict = strict; a.ksplit = ksplit;
+        if (ctx->half_operands && !strict && conv_tc_enabled() && cin_k % 8 == 0 && conv_tc_supported(cw, a)) {
+            // exercise the f16-operand variant the networks use between a normalisation layer and a conv
+            View x16 = xin; x16.f16 = 1; x16.p = P->alloc((xin.pixels() * cin_k + 1) / 2);
+            convert_f16(xin, x16, s);
+            a.in = x16;
+        }
         if (res) {
             const int rh = res_mode == RES_UP2 ? Ho / 2 : (res_mode == RES_DOWN2 ? Ho * 2 : Ho);
             const int rw = res_mode == RES_UP2 ? Wo / 2 : (res_mode == RES_DOWN2 ? Wo * 2 : Wo);

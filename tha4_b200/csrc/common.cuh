@@ -1,6 +1,7 @@
 // Shared declarations for the tha4_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -17,6 +18,10 @@ extern std::atomic<long> g_kernel_launches;   // every kernel this library launc
 struct View {
     float* p = nullptr;
     int N = 0, H = 0, W = 0, C = 0, ld = 0;
+    // f16 == 1: `p` really addresses __half elements (ld still counts elements).  Only the normalisation kernels write
+    // such tensors and only the tcgen05 conv reads them (kind::f16 operands: same 10-bit mantissa as TF32, half the
+    // operand bytes); everything else requires f16 == 0.
+    int f16 = 0;
     // Optional per-(n,c) statistics of this tensor: stats[(n * stats_ld + c) * 2 + {0: sum, 1: sum of squares}] (doubles),
     // zero-initialised by the owner and accumulated by whichever kernel produces the tensor (conv epilogues).
     // Producers spread their atomics over `stats_rep` replicas (replica r at stats + r * stats_rep_stride) so that
@@ -26,7 +31,12 @@ struct View {
     int stats_rep = 1;
     long stats_rep_stride = 0;
     __host__ __device__ long pix(int n, int y, int x) const { return (((long)n * H + y) * W + x) * ld; }
-    View slice(int c0, int c) const { View v = *this; v.p = p + c0; v.C = c; if (stats) v.stats = stats + 2 * c0; return v; }
+    View slice(int c0, int c) const {
+        View v = *this;
+        v.p = f16 ? reinterpret_cast<float*>(reinterpret_cast<__half*>(p) + c0) : p + c0;
+        v.C = c; if (stats) v.stats = stats + 2 * c0; return v;
+    }
+    __half* hp() const { return reinterpret_cast<__half*>(p); }
     size_t pixels() const { return (size_t)N * H * W; }
 };
 

@@ -373,6 +373,7 @@ void conv_pack(const ConvWeights& cw, ConvKind kind, const float* w_ref, int w_c
 
 static bool g_use_tc = true;
 void conv_enable_tc(bool on) { g_use_tc = on; }
+bool conv_tc_enabled() { return g_use_tc; }
 
 bool conv_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
     if (a.out.stats == nullptr || !g_use_tc) return false;
@@ -388,6 +389,7 @@ void conv_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
 
 void conv_mma_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     THA4_REQUIRE(!(a.strict && cw.tf32_rounded), "strict mode needs weights packed without TF32 rounding: set the option before loading");
+    THA4_REQUIRE(!a.in.f16 && !a.out.f16, "conv (mma.sync path): fp32 activations only");
     ConvKernelParams p{};
     THA4_REQUIRE(a.in.C == cw.cin, "conv: input channels");
     THA4_REQUIRE(a.out.C == cw.cout, "conv: output channels");

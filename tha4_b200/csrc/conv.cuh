@@ -17,6 +17,7 @@ enum ResMode { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2, RES_DOWN2 = 3 };
 // Packed weights: [phase][tap][cout_pad][cin_pad] fp32, cin_pad % 32 == 0, cout_pad % 32 == 0, zero padded.
 struct ConvWeights {
     float* w = nullptr;
+    mutable __half* w16 = nullptr;   // same layout in f16, made on first use with f16 activations (conv_tc.cu)
     float* bias = nullptr;      // [cout] or nullptr
     int cin = 0, cout = 0, cin_pad = 0, cout_pad = 0;
     int ntaps = 0, nphase = 1;
@@ -73,6 +74,7 @@ bool conv_tcp_supported(const ConvWeights& cw, const ConvArgs& a);              
 void conv_tcp_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);
 void conv_tcp_enable(bool on);
 void conv_enable_tc(bool on);
+bool conv_tc_enabled();
 void conv_tc_enable_cluster(bool on);
 void conv_tc_enable_mt2(bool on);       // two 128-pixel tiles per CTA sharing each weight tile (default on)   // split-K through a thread-block cluster + DSMEM (default) vs workspace + reduce kernel                                                        // default: on
 

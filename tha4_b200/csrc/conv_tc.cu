@@ -26,7 +26,6 @@ namespace {
 using namespace tc;
 
 constexpr int TILE_W = 16, TILE_H = 8;          // 128 output pixels per CTA
-constexpr int A_BYTES1 = 128 * KCH * 4;          // 16 KB per 128-pixel tile
 constexpr int TC_THREADS = 192;                  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
 struct TcParams {
@@ -47,11 +46,28 @@ struct TcParams {
 // MT = 2: the CTA owns two vertically adjacent 16x8 pixel tiles (M = 256 as two M = 128 MMAs per k-step into two TMEM
 // accumulators) that SHARE every weight tile -- operand traffic per MAC drops by a third to a half, which is what
 // bounds these kernels (L2 -> shared memory at ~40 B/clk/SM).
-template <int BN, int STAGES, int CS, int MT>
+//
+// OP selects the operand format of one k-block (one TMA box row per pixel / per cout):
+//   OP_TF32: 32 fp32 channels  = 128-byte rows, SWIZZLE_128B, kind::tf32 (4 MMAs of K = 8)
+//   OP_F16 : 64 f16 channels   = 128-byte rows, SWIZZLE_128B, kind::f16  (4 MMAs of K = 16)
+//   OP_F16N: 32 f16 channels   =  64-byte rows, SWIZZLE_64B,  kind::f16  (2 MMAs of K = 16)  -- Cin % 64 == 32 layers
+// f16 operands carry the same 10-bit mantissa as TF32 (the normalisation kernels that produce conv inputs write them),
+// so the products are as exact as the TF32 path's while every operand byte count -- HBM, L2 -> smem, smem -> tensor
+// core -- is halved, and the tensor pipe runs at twice the TF32 rate.
+enum { OP_TF32 = 0, OP_F16 = 1, OP_F16N = 2 };
+__host__ __device__ constexpr int op_row_bytes(int op) { return op == OP_F16N ? 64 : 128; }
+__host__ __device__ constexpr int op_kch(int op) { return op == OP_TF32 ? 32 : (op == OP_F16 ? 64 : 32); }   // channels per k-block
+__host__ __device__ constexpr int op_stages(int op, int stages) { return op == OP_F16N ? 2 * stages : stages; }
+
+template <int BN, int STAGES_, int CS, int MT, int OP>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     static_assert(MT == 1 || CS == 1, "the two-tile variant is for unsplit launches");
-    constexpr int B_BYTES = BN * KCH * 4;
+    constexpr int STAGES = op_stages(OP, STAGES_);
+    constexpr int ROWB = op_row_bytes(OP);
+    constexpr int KCE = op_kch(OP);
+    constexpr int A_BYTES1 = 128 * ROWB;
+    constexpr int B_BYTES = BN * ROWB;
     constexpr int A_BYTES = MT * A_BYTES1;
     constexpr int TMEM_COLS = MT * BN < 32 ? 32 : MT * BN;
     extern __shared__ uint8_t smem_raw[];
@@ -101,27 +117,33 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     mbar_expect_tx(full, A_BYTES + B_BYTES);
                     const int kt = kb + i;
                     const int tap = kt / p.cpt;
-                    const int c0 = (kt - tap * p.cpt) * KCH;
+                    const int c0 = (kt - tap * p.cpt) * KCE;
                     tma_load_4d(smem_u32(smA + s * A_BYTES), &tmA, c0, x0 + p.dx[phase][tap], y0 + p.dy[phase][tap], n, full);
                     tma_load_3d(smem_u32(smB + s * B_BYTES), &tmB, c0, n0, phase * p.ntaps + tap, full);
                 }
             }
         } else if (warp == 1) {
             if (lane == 0) {   // ===== MMA issuer (single thread) =====
-                // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
-                constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+                // instruction descriptor: D=f32, A=B=tf32 (format 2) or f16 (format 0), both K-major, N = BN, M = 128
+                constexpr uint32_t fmt = OP == OP_TF32 ? 2u : 0u;
+                constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
                 for (int i = 0; i < nk; ++i) {
                     const int s = i % STAGES;
                     mbar_wait(smem_u32(bars + s), (i / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const uint64_t adesc = make_smem_desc(smem_u32(smA + s * A_BYTES));
-                    const uint64_t bdesc = make_smem_desc(smem_u32(smB + s * B_BYTES));
+                    const uint64_t adesc = make_smem_desc_sw<ROWB>(smem_u32(smA + s * A_BYTES));
+                    const uint64_t bdesc = make_smem_desc_sw<ROWB>(smem_u32(smB + s * B_BYTES));
 #pragma unroll
                     for (int h = 0; h < MT; ++h)
 #pragma unroll
-                        for (int k = 0; k < KCH / 8; ++k)     // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (>>4)
-                            umma_tf32(tmem_base + (uint32_t)(h * BN), adesc + (uint64_t)(h * (A_BYTES1 >> 4)) + 2 * k, bdesc + 2 * k, idesc,
-                                      (i > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < ROWB / 32; ++k) {  // one MMA consumes 32 bytes of K per row (8 tf32 / 16 f16): advance the start address by 2 (>>4)
+                            if (OP == OP_TF32)
+                                umma_tf32(tmem_base + (uint32_t)(h * BN), adesc + (uint64_t)(h * (A_BYTES1 >> 4)) + 2 * k, bdesc + 2 * k, idesc,
+                                          (i > 0 || k > 0) ? 1u : 0u);
+                            else
+                                umma_f16(tmem_base + (uint32_t)(h * BN), adesc + (uint64_t)(h * (A_BYTES1 >> 4)) + 2 * k, bdesc + 2 * k, idesc,
+                                         (i > 0 || k > 0) ? 1u : 0u);
+                        }
                     umma_commit(smem_u32(bars + STAGES + s));          // frees the smem slot when these MMAs retire
                 }
                 umma_commit(smem_u32(bars + 2 * STAGES));              // accumulator complete -> epilogue
@@ -385,49 +407,57 @@ EncodeTiledFn get_encode() {
 using MapKey = std::tuple<const void*, long, long, long, long, long, int>;
 std::map<MapKey, CUtensorMap> g_maps;
 
-const CUtensorMap& activation_map(const View& v, int mt) {
-    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -mt};
+const CUtensorMap& activation_map(const View& v, int mt, int op) {
+    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -(mt + 4 * op)};
     auto it = g_maps.find(key);
     if (it != g_maps.end()) return it->second;
     CUtensorMap m;
     cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
-    cuuint64_t strides[3] = {(cuuint64_t)v.ld * 4, (cuuint64_t)v.W * v.ld * 4, (cuuint64_t)v.H * v.W * v.ld * 4};
-    cuuint32_t box[4] = {KCH, TILE_W, (cuuint32_t)(TILE_H * mt), 1};
+    const cuuint64_t eb = op == OP_TF32 ? 4 : 2;
+    THA4_REQUIRE((op != OP_TF32) == (v.f16 != 0), "conv_tc: operand format does not match the activation view");
+    cuuint64_t strides[3] = {(cuuint64_t)v.ld * eb, (cuuint64_t)v.W * v.ld * eb, (cuuint64_t)v.H * v.W * v.ld * eb};
+    cuuint32_t box[4] = {(cuuint32_t)op_kch(op), TILE_W, (cuuint32_t)(TILE_H * mt), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = get_encode()(&m, op == OP_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, v.p, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, op == OP_F16N ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     THA4_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
     return g_maps.emplace(key, m).first->second;
 }
 
-const CUtensorMap& weight_map(const ConvWeights& cw, int bn) {
-    MapKey key{cw.w, cw.cin_pad, cw.cout_pad, cw.ntaps, cw.nphase, 0, bn};
+const CUtensorMap& weight_map(const ConvWeights& cw, int bn, int op) {
+    const void* wp = op == OP_TF32 ? (const void*)cw.w : (const void*)cw.w16;
+    MapKey key{wp, cw.cin_pad, cw.cout_pad, cw.ntaps, cw.nphase, op, bn};
     auto it = g_maps.find(key);
     if (it != g_maps.end()) return it->second;
     CUtensorMap m;
     cuuint64_t dims[3] = {(cuuint64_t)cw.cin_pad, (cuuint64_t)cw.cout_pad, (cuuint64_t)cw.ntaps * cw.nphase};
-    cuuint64_t strides[2] = {(cuuint64_t)cw.cin_pad * 4, (cuuint64_t)cw.cout_pad * cw.cin_pad * 4};
-    cuuint32_t box[3] = {KCH, (cuuint32_t)bn, 1};
+    const cuuint64_t eb = op == OP_TF32 ? 4 : 2;
+    cuuint64_t strides[2] = {(cuuint64_t)cw.cin_pad * eb, (cuuint64_t)cw.cout_pad * cw.cin_pad * eb};
+    cuuint32_t box[3] = {(cuuint32_t)op_kch(op), (cuuint32_t)bn, 1};
     cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, cw.w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = get_encode()(&m, op == OP_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(wp), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, op == OP_F16N ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     THA4_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
     return g_maps.emplace(key, m).first->second;
 }
 
-template <int BN, int STAGES, int CS = 1, int MT = 1>
+template <int OP, int BN, int STAGES_, int CS = 1, int MT = 1>
 void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
-    constexpr int A_BYTES = MT * A_BYTES1;
-    constexpr size_t smem = 1024 + (size_t)STAGES * (A_BYTES + BN * KCH * 4) + (2 * STAGES + 1) * 8 + 16;
+    constexpr int STAGES = op_stages(OP, STAGES_);
+    constexpr int STAGE_BYTES = (MT * 128 + BN) * op_row_bytes(OP);
+    constexpr size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static_assert(CS == 1 || (size_t)STAGES * (A_BYTES + BN * KCH * 4) >= (size_t)128 * BN * 4 + 128 * 8 * 4, "partial tile must fit");
+    static_assert((size_t)STAGES * STAGE_BYTES >= (size_t)4 * 32 * 33 * 4 + 4 * BN * 8, "epilogue scratch must fit in the pipeline buffers");
+    static_assert(CS == 1 || (size_t)STAGES * STAGE_BYTES >= (size_t)128 * BN * 4 + 128 * 8 * 4, "partial tile must fit");
     static bool configured = false;
     if (!configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES, CS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES_, CS, MT, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     if (CS == 1) {
-        conv_tc_kernel<BN, STAGES, CS, MT><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
+        conv_tc_kernel<BN, STAGES_, CS, MT, OP><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
     } else {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -435,16 +465,53 @@ void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = CS;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        THA4_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES, CS, MT>, ma, mb, p));
+        THA4_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES_, CS, MT, OP>, ma, mb, p));
     }
     THA4_LAUNCH_CHECK();
 }
 
-template <int BN, int STAGES>
+template <int OP, int BN, int STAGES>
 void launch_tc_cluster(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
-    if (cs == 8) launch_tc<BN, STAGES, 8>(ma, mb, p, grid, s);
-    else if (cs == 4) launch_tc<BN, STAGES, 4>(ma, mb, p, grid, s);
-    else launch_tc<BN, STAGES, 2>(ma, mb, p, grid, s);
+    if (cs == 8) launch_tc<OP, BN, STAGES, 8>(ma, mb, p, grid, s);
+    else if (cs == 4) launch_tc<OP, BN, STAGES, 4>(ma, mb, p, grid, s);
+    else launch_tc<OP, BN, STAGES, 2>(ma, mb, p, grid, s);
+}
+
+// all launch shapes of one operand format: cluster split-K, deep / mid / shallow TMA rings
+template <int OP>
+void launch_variants(bool cluster, int stages_mode, int bn, int ksplit, const CUtensorMap& ma, const CUtensorMap& mb,
+                     const TcParams& p, dim3 grid, cudaStream_t s) {
+    if (cluster) {
+        if (bn == 256) launch_tc_cluster<OP, 256, 4>(ksplit, ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc_cluster<OP, 128, 6>(ksplit, ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc_cluster<OP, 64, 8>(ksplit, ma, mb, p, grid, s);
+        else launch_tc_cluster<OP, 32, 8>(ksplit, ma, mb, p, grid, s);
+    } else if (stages_mode == 0) {
+        if (bn == 256) launch_tc<OP, 256, 4>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<OP, 128, 6>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<OP, 64, 8>(ma, mb, p, grid, s);
+        else launch_tc<OP, 32, 8>(ma, mb, p, grid, s);
+    } else if (stages_mode == 1) {
+        if (bn == 256) launch_tc<OP, 256, 2>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<OP, 128, 3>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<OP, 64, 4>(ma, mb, p, grid, s);
+        else launch_tc<OP, 32, 5>(ma, mb, p, grid, s);
+    } else {
+        if (bn == 256) launch_tc<OP, 256, 2>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<OP, 128, 2>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<OP, 64, 2>(ma, mb, p, grid, s);
+        else launch_tc<OP, 32, 3>(ma, mb, p, grid, s);
+    }
+}
+
+// fp32 packed weights -> f16 (the packed values were already rounded to 10 mantissa bits, so this is exact in range)
+__global__ void pack_half_kernel(const float* __restrict__ w, __half* __restrict__ h, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) h[i] = __float2half_rn(w[i]);
+}
+
+int op_for(const ConvWeights& cw, const ConvArgs& a) {
+    if (!a.in.f16) return OP_TF32;
+    return cw.cin_pad % 64 == 0 ? OP_F16 : OP_F16N;
 }
 
 }  // namespace
@@ -462,12 +529,12 @@ TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
     pl.tiles_m = pl.tiles_x * pl.tiles_y * a.in.N;
     pl.tiles_n = cw.cout_pad / pl.bn;
     // two-tile CTAs (M = 256) when that still fills the GPU about twice over
-    if (g_use_mt2 && a.ksplit <= 1 && (long)pl.tiles_x * ceil_div(pl.MH, 2 * TILE_H) * a.in.N * pl.tiles_n * cw.nphase >= 280) {
+    if (g_use_mt2 && !a.in.f16 && a.ksplit <= 1 && (long)pl.tiles_x * ceil_div(pl.MH, 2 * TILE_H) * a.in.N * pl.tiles_n * cw.nphase >= 280) {
         pl.mt = 2;
         pl.tiles_y = ceil_div(pl.MH, 2 * TILE_H);
         pl.tiles_m = pl.tiles_x * pl.tiles_y * a.in.N;
     }
-    const int KT = cw.ntaps * (cw.cin_pad / KCH);
+    const int KT = cw.ntaps * (cw.cin_pad / op_kch(op_for(cw, a)));
     int ksplit = a.ksplit;
     if (ksplit <= 0) {
         const long ctas = (long)pl.tiles_m * pl.tiles_n * cw.nphase;
@@ -516,7 +583,7 @@ bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
 
 bool conv_tc_supported(const ConvWeights& cw, const ConvArgs& a) {
     if (a.in_up || cw.stride != 1 || a.strict) return false;
-    if (a.in.ld % 4 != 0 || (((uintptr_t)a.in.p) & 15) != 0) return false;
+    if (a.in.ld % (a.in.f16 ? 8 : 4) != 0 || (((uintptr_t)a.in.p) & 15) != 0) return false;
     if (a.out.ld % 4 != 0 || (((uintptr_t)a.out.p) & 15) != 0) return false;
     if (cw.cout_pad % 32 != 0) return false;
     return true;
@@ -536,7 +603,16 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     p.MH = pl.MH; p.MW = pl.MW;
     THA4_REQUIRE(p.MH == a.in.H && p.MW == a.in.W, "conv_tc: geometry");
     p.tiles_x = pl.tiles_x; p.tiles_y = pl.tiles_y;
-    p.ntaps = cw.ntaps; p.cpt = cw.cin_pad / KCH;
+    const int op = op_for(cw, a);
+    p.ntaps = cw.ntaps; p.cpt = cw.cin_pad / op_kch(op);
+    if (op != OP_TF32 && !cw.w16) {          // first use with f16 activations: make the f16 copy of the packed weights
+        const long nw = (long)conv_packed_floats(cw);
+        __half* h = nullptr;
+        THA4_CUDA_CHECK(cudaMalloc(&h, nw * sizeof(__half)));
+        pack_half_kernel<<<(int)std::min<long>((nw + 255) / 256, 1184), 256, 0, s>>>(cw.w, h, nw);
+        THA4_LAUNCH_CHECK();
+        cw.w16 = h;
+    }
     for (int ph = 0; ph < CONV_MAX_PHASES; ++ph) {
         p.ph_oy[ph] = cw.ph_oy[ph]; p.ph_ox[ph] = cw.ph_ox[ph];
         for (int t = 0; t < CONV_MAX_TAPS; ++t) { p.dy[ph][t] = cw.dy[ph][t]; p.dx[ph][t] = cw.dx[ph][t]; }
@@ -553,8 +629,8 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
     if (ksplit > 1 && !use_ws && !pl.cluster)
         THA4_CUDA_CHECK(cudaMemset2DAsync(a.out.p, (size_t)a.out.ld * sizeof(float), 0, (size_t)a.out.C * sizeof(float), a.out.pixels(), s));
-    const CUtensorMap& ma = activation_map(a.in, pl.mt);
-    const CUtensorMap& mb = weight_map(cw, bn);
+    const CUtensorMap& ma = activation_map(a.in, pl.mt, op);
+    const CUtensorMap& mb = weight_map(cw, bn, op);
     dim3 grid(tiles_m, tiles_n, cw.nphase * ksplit);
     // Pipeline depth: grids that cannot even fill the GPU once (the B=1 bottleneck layers, which stream their weights
     // from HBM with one CTA per SM) get a deep TMA ring to hide DRAM latency; large grids get a shallow ring so that
@@ -564,38 +640,18 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
         const char* e = getenv("THA4_TC_STAGES");
         forced = !e ? -1 : (!strcmp(e, "deep") ? 0 : (!strcmp(e, "mid") ? 1 : 2));
     }
-    if (pl.mt == 2) {          // M = 256 per CTA, accumulators MT x BN columns of TMEM
-        if (bn == 256) launch_tc<256, 3, 1, 2>(ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc<128, 4, 1, 2>(ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc<64, 2, 1, 2>(ma, mb, p, grid, s);
-        else launch_tc<32, 2, 1, 2>(ma, mb, p, grid, s);
-        return;
-    }
     const long total_ctas = (long)grid.x * grid.y * grid.z;
     const int stages_mode = forced >= 0 ? forced : (total_ctas <= 160 ? 0 : 2);
-    if (pl.cluster) {
-        if (bn == 256) launch_tc_cluster<256, 4>(ksplit, ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc_cluster<128, 6>(ksplit, ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc_cluster<64, 8>(ksplit, ma, mb, p, grid, s);
-        else launch_tc_cluster<32, 8>(ksplit, ma, mb, p, grid, s);
+    if (pl.mt == 2) {          // M = 256 per CTA, accumulators MT x BN columns of TMEM (tf32 operands only)
+        if (bn == 256) launch_tc<OP_TF32, 256, 3, 1, 2>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<OP_TF32, 128, 4, 1, 2>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<OP_TF32, 64, 2, 1, 2>(ma, mb, p, grid, s);
+        else launch_tc<OP_TF32, 32, 2, 1, 2>(ma, mb, p, grid, s);
         return;
     }
-    if (stages_mode == 0) {
-        if (bn == 256) launch_tc<256, 4>(ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc<128, 6>(ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc<64, 8>(ma, mb, p, grid, s);
-        else launch_tc<32, 8>(ma, mb, p, grid, s);
-    } else if (stages_mode == 1) {
-        if (bn == 256) launch_tc<256, 2>(ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc<128, 3>(ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc<64, 4>(ma, mb, p, grid, s);
-        else launch_tc<32, 5>(ma, mb, p, grid, s);
-    } else {
-        if (bn == 256) launch_tc<256, 2>(ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc<128, 2>(ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc<64, 2>(ma, mb, p, grid, s);
-        else launch_tc<32, 3>(ma, mb, p, grid, s);
-    }
+    if (op == OP_TF32) launch_variants<OP_TF32>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
+    else if (op == OP_F16) launch_variants<OP_F16>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
+    else launch_variants<OP_F16N>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
     if (use_ws) {
         const int cq = (p.outC + 3) / 4;
         THA4_REQUIRE(cq <= 256, "split-K reduce: Cout <= 1024");

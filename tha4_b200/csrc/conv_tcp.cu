@@ -319,7 +319,7 @@ void conv_tcp_enable(bool on) { g_use_persistent = on; }
 
 // persistent path: stride-1 taps, grid large enough that K never needs splitting
 bool conv_tcp_supported(const ConvWeights& cw, const ConvArgs& a) {
-    if (!g_use_persistent || !conv_tc_supported(cw, a) || a.ksplit > 1) return false;
+    if (!g_use_persistent || a.in.f16 || !conv_tc_supported(cw, a) || a.ksplit > 1) return false;
     const int MH = a.out.H / cw.out_mul, MW = a.out.W / cw.out_mul;
     const long tiles = (long)ceil_div(MW, PT_W) * ceil_div(MH, PT_H) * a.in.N * cw.nphase;
     const int bn = (cw.cout_pad % 128 == 0) ? 128 : (cw.cout_pad % 64 == 0 ? 64 : 32);

@@ -46,13 +46,22 @@ __global__ void copy_window_kernel(ImgView src, float* __restrict__ dst, long dn
     }
 }
 
-__global__ void tile_vector_kernel(const float* __restrict__ vec, int vec_ld, int P, float* __restrict__ dst, int H, int W,
+template <typename T>
+__global__ void tile_vector_kernel(const float* __restrict__ vec, int vec_ld, int P, T* __restrict__ dst, int H, int W,
                                    int C, int ld, long total) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         const long pix = i / C;
         const int n = (int)(pix / ((long)H * W));
-        dst[pix * ld + c] = (c < P) ? vec[(long)n * vec_ld + c] : 0.0f;
+        dst[pix * ld + c] = (T)((c < P) ? vec[(long)n * vec_ld + c] : 0.0f);
+    }
+}
+
+__global__ void convert_f16_kernel(const float* __restrict__ src, int src_ld, __half* __restrict__ dst, int dst_ld, int C, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long pix = i / C;
+        dst[pix * dst_ld + c] = __float2half_rn(src[pix * src_ld + c]);
     }
 }
 
@@ -180,7 +189,15 @@ void copy_window(const ImgView& src, float* dst, long dn, long dc, long dh, cuda
 
 void tile_vector(const float* vec, int vec_ld, int P, const View& dst, cudaStream_t s) {
     const long total = (long)dst.N * dst.H * dst.W * dst.C;
-    tile_vector_kernel<<<grid_for(total), 256, 0, s>>>(vec, vec_ld, P, dst.p, dst.H, dst.W, dst.C, dst.ld, total);
+    if (dst.f16) tile_vector_kernel<__half><<<grid_for(total), 256, 0, s>>>(vec, vec_ld, P, dst.hp(), dst.H, dst.W, dst.C, dst.ld, total);
+    else tile_vector_kernel<float><<<grid_for(total), 256, 0, s>>>(vec, vec_ld, P, dst.p, dst.H, dst.W, dst.C, dst.ld, total);
+    THA4_LAUNCH_CHECK();
+}
+
+void convert_f16(const View& src, const View& dst, cudaStream_t s) {
+    THA4_REQUIRE(!src.f16 && dst.f16 && src.C == dst.C && src.pixels() == dst.pixels(), "convert_f16: views");
+    const long total = (long)src.pixels() * src.C;
+    convert_f16_kernel<<<grid_for(total), 256, 0, s>>>(src.p, src.ld, dst.hp(), dst.ld, src.C, total);
     THA4_LAUNCH_CHECK();
 }
 

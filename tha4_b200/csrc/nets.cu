@@ -133,6 +133,14 @@ View make_view(Pool* pool, int N, int H, int W, int C, Runtime* rt = nullptr) {
     return v;
 }
 
+// f16 activation tensor (conv operand produced by a normalisation layer; see View::f16)
+View make_view16(Pool* pool, int N, int H, int W, int C) {
+    THA4_REQUIRE(C % 8 == 0, "f16 view: channels must be a multiple of 8");
+    View v; v.N = N; v.H = H; v.W = W; v.C = C; v.ld = C; v.f16 = 1;
+    v.p = pool->alloc(((size_t)N * H * W * C + 1) / 2);
+    return v;
+}
+
 // per-(n,c) affine for the fused tail kernels (InstanceNorm when groups == 0, GroupNorm otherwise)
 float* tail_coef(Runtime& rt, const View& x, const NormW& nw, int groups) {
     THA4_REQUIRE(nw.C == x.C, "norm: channel mismatch");
@@ -143,9 +151,9 @@ float* tail_coef(Runtime& rt, const View& x, const NormW& nw, int groups) {
 
 // normalisation layer = one elementwise pass: affine from x.stats rebuilt per CTA, activation / pool / residual fused
 void run_norm(Runtime& rt, const View& x, const NormW& nw, int groups, const float* film0, const float* film1,
-              int film1_ld, int act, int pool, const View* res, const View& y) {
+              int film1_ld, int act, int pool, const View* res, const View& y, const View* y16 = nullptr) {
     THA4_REQUIRE(nw.C == x.C, "norm: channel mismatch");
-    norm_apply_fused(x, groups, nw.gamma, nw.beta, film0, film1, film1_ld, act, pool, res, y, rt.stream, !rt.strict);
+    norm_apply_fused(x, groups, nw.gamma, nw.beta, film0, film1, film1_ld, act, pool, res, y, rt.stream, !rt.strict, y16);
 }
 
 void run_conv(Runtime& rt, const ConvWeights& cw, const View& in, const View& out, int in_up = 0,
@@ -164,7 +172,7 @@ void run_conv(Runtime& rt, const ConvWeights& cw, const View& in, const View& ou
 
 // ------------------------------------------------------------------------------------------------ EncDecNet
 EncDecNet::EncDecNet(TailKind kind, int size, int in_ch, int pose_ch)
-    : kind_(kind), S_(size), in_ch_(in_ch), pose_ch_(pose_ch), pose_pad_(round_up(pose_ch, 4)) {}
+    : kind_(kind), S_(size), in_ch_(in_ch), pose_ch_(pose_ch), pose_pad_(round_up(pose_ch, 8)) {}
 
 void EncDecNet::load(const StateDict& sd, cudaStream_t s) {
     const std::string p = (kind_ == TAIL_FACE) ? "" : "body.";
@@ -225,32 +233,39 @@ void EncDecNet::forward(Runtime& rt, const ImgView& image0, const ImgView& image
     } else {
         nchw_to_nhwc(image0, x0, s);
     }
-    // conv -> InstanceNorm -> ReLU; the activated tensor goes to `dst`
-    auto conv_in_relu = [&](const ConvWeights& cw, const NormW& nw, const View& in, int oh, const View* dst) -> View {
+    // conv -> InstanceNorm -> ReLU; the activated tensor goes to `dst`, or to a fresh f16 tensor when its only consumer is
+    // a tcgen05 conv (to16), or back in place
+    const bool h16 = rt.f16 != 0;
+    auto conv_in_relu = [&](const ConvWeights& cw, const NormW& nw, const View& in, int oh, const View* dst, bool to16) -> View {
         View raw = make_view(P, B, oh, oh, cw.cout, &rt);
         run_conv(rt, cw, in, raw);
-        const View& y = dst ? *dst : raw;
+        const View y = dst ? *dst : (to16 ? make_view16(P, B, oh, oh, cw.cout) : raw);
         run_norm(rt, raw, nw, 0, nullptr, nullptr, 0, ACT_RELU, 0, nullptr, y);
         return y;
     };
-    View f = conv_in_relu(down_[0], down_n_[0], x0, S_, nullptr);
-    f = conv_in_relu(down_[1], down_n_[1], f, S_ / 2, nullptr);
-    f = conv_in_relu(down_[2], down_n_[2], f, S_ / 4, nullptr);
+    View f = conv_in_relu(down_[0], down_n_[0], x0, S_, nullptr, false);       // the stride-2 convs read fp32
+    f = conv_in_relu(down_[1], down_n_[1], f, S_ / 2, nullptr, false);
+    f = conv_in_relu(down_[2], down_n_[2], f, S_ / 4, nullptr, false);
     const int b = S_ / 8;
-    View bin = make_view(P, B, b, b, 512 + pose_pad_);
+    View bin = h16 ? make_view16(P, B, b, b, 512 + pose_pad_) : make_view(P, B, b, b, 512 + pose_pad_);
     View bfeat = bin.slice(0, 512);
-    conv_in_relu(down_[3], down_n_[3], f, b, &bfeat);
+    conv_in_relu(down_[3], down_n_[3], f, b, &bfeat, false);
     if (pose_pad_ > 0) tile_vector(pose, pose_ld, pose_ch_, bin.slice(512, pose_pad_), s);   // poser_encoder_decoder_00.py:110-113
-    View x = conv_in_relu(bott0_, bott0_n_, bin, b, nullptr);
+    // the bottleneck stream x is both a residual (fp32) and a conv operand (f16 copy x16)
+    View x = make_view(P, B, b, b, bott0_.cout, &rt), x16;
+    run_conv(rt, bott0_, bin, x);
+    if (h16) x16 = make_view16(P, B, b, b, bott0_.cout);
+    run_norm(rt, x, bott0_n_, 0, nullptr, nullptr, 0, ACT_RELU, 0, nullptr, x, h16 ? &x16 : nullptr);
     for (int i = 0; i < 5; ++i) {   // ResnetBlock: x + IN(conv(relu(IN(conv(x)))))  (resnet_block.py:52-67)
-        View h = conv_in_relu(res_[i][0], res_n_[i][0], x, b, nullptr);
+        View h = conv_in_relu(res_[i][0], res_n_[i][0], h16 ? x16 : x, b, nullptr, h16);
         View raw = make_view(P, B, b, b, 512, &rt);
         run_conv(rt, res_[i][1], h, raw);
-        run_norm(rt, raw, res_n_[i][1], 0, nullptr, nullptr, 0, ACT_NONE, 0, &x, raw);
-        x = raw;
+        View n16; if (h16) n16 = make_view16(P, B, b, b, 512);
+        run_norm(rt, raw, res_n_[i][1], 0, nullptr, nullptr, 0, ACT_NONE, 0, &x, raw, h16 ? &n16 : nullptr);
+        x = raw; x16 = n16;
     }
-    x = conv_in_relu(up_[0], up_n_[0], x, b * 2, nullptr);
-    x = conv_in_relu(up_[1], up_n_[1], x, b * 4, nullptr);
+    x = conv_in_relu(up_[0], up_n_[0], h16 ? x16 : x, b * 2, nullptr, h16);
+    x = conv_in_relu(up_[1], up_n_[1], x, b * 4, nullptr, h16);
     // last block: leave InstanceNorm + ReLU pending; the tail kernel applies them while staging its halo tile
     View raw = make_view(P, B, S_, S_, 64, &rt);
     run_conv(rt, up_[2], x, raw);
@@ -390,19 +405,21 @@ void UNetNet::res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode
     const int B = x.N;
     // norm0 -> SiLU -> (avg-pool) ; the nearest-upsample is folded into conv0's gather
     const int th = (mode == 2) ? x.H / 2 : x.H;
-    View t0 = make_view(rt.scratch, B, th, th, w.cin);
+    const bool h16 = rt.f16 != 0;
+    View t0 = h16 ? make_view16(rt.scratch, B, th, th, w.cin) : make_view(rt.scratch, B, th, th, w.cin);
     run_norm(rt, x, w.norm0, 32, nullptr, nullptr, 0, rt.strict ? ACT_SILU : ACT_SILU_FAST, mode == 2 ? 1 : 0, nullptr, t0);
     View h = make_view(rt.scratch, B, out.H, out.W, w.cout, &rt);
     run_conv(rt, w.conv0, t0, h);      // mode 1: conv0 was packed as CONV_UP2_3x3 (upsample folded into 4 phases)
     // norm1 -> FiLM(time) -> FiLM(pose) -> SiLU, folded into one per-(n,c) affine
-    run_norm(rt, h, w.norm1, 32, w.film0, film1 + w.film1_off, film1_total_, rt.strict ? ACT_SILU : ACT_SILU_FAST, 0, nullptr, h);
+    const View h2 = h16 ? make_view16(rt.scratch, B, out.H, out.W, w.cout) : h;
+    run_norm(rt, h, w.norm1, 32, w.film0, film1 + w.film1_off, film1_total_, rt.strict ? ACT_SILU : ACT_SILU_FAST, 0, nullptr, h2);
     if (w.has_skip) {
         THA4_REQUIRE(mode == 0, "res_block: skip conv only on same-resolution blocks");
         View sk = make_view(rt.scratch, B, x.H, x.W, w.cout);
         run_conv(rt, w.skip, x, sk);
-        run_conv(rt, w.conv1, h, out, 0, &sk, RES_SAME);
+        run_conv(rt, w.conv1, h2, out, 0, &sk, RES_SAME);
     } else {
-        run_conv(rt, w.conv1, h, out, 0, &x, mode == 0 ? RES_SAME : (mode == 1 ? RES_UP2 : RES_DOWN2));
+        run_conv(rt, w.conv1, h2, out, 0, &x, mode == 0 ? RES_SAME : (mode == 1 ? RES_UP2 : RES_DOWN2));
     }
 }
 
@@ -410,7 +427,7 @@ void UNetNet::res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode
 void UNetNet::attn_block(Runtime& rt, const AttnW& w, const View& x, const View& out) {
     cudaStream_t s = rt.stream;
     rt.scratch->reset();
-    View t = make_view(rt.scratch, x.N, x.H, x.W, x.C);
+    View t = rt.f16 ? make_view16(rt.scratch, x.N, x.H, x.W, x.C) : make_view(rt.scratch, x.N, x.H, x.W, x.C);
     run_norm(rt, x, w.norm, 32, nullptr, nullptr, 0, ACT_NONE, 0, nullptr, t);
     View qkv = make_view(rt.scratch, x.N, x.H, x.W, 3 * x.C);
     run_conv(rt, w.qkv, t, qkv);

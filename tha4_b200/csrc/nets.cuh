@@ -36,6 +36,7 @@ struct Runtime {                      // per-call execution context
     Pool* scratch;
     cudaStream_t stream;
     int strict;
+    int f16 = 0;                      // normalisation layers hand f16 tensors to the tcgen05 convs (non-strict, tcgen05 on)
     // zero-initialised arena for per-(n,c) statistics (View::stats); bump-allocated, re-zeroed by the caller per pass
     double* stats_base = nullptr;
     size_t stats_cap = 0;

@@ -92,7 +92,8 @@ template <bool FUSED>
 __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict__ x, int xH, int xW, int x_ld,
                                                          const float* __restrict__ coef, int act, int pool,
                                                          const float* __restrict__ res, int res_ld,
-                                                         float* __restrict__ y, int yH, int yW, int y_ld, int C, long total,
+                                                         float* __restrict__ y, int yH, int yW, int y_ld,
+                                                         __half* __restrict__ yh, int yh_ld, int C, long total,
                                                          int round_out,
                                                          const double* __restrict__ sums, int stats_ld, int rep, long rep_stride,
                                                          int HW, int groups,
@@ -167,8 +168,15 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
                 r.x = act_apply(v[u].x * c0.x + c0.y, act); r.y = act_apply(v[u].y * c0.z + c0.w, act);
                 r.z = act_apply(v[u].z * c1.x + c1.y, act); r.w = act_apply(v[u].w * c1.z + c1.w, act);
                 if (res) { r.x += rv[u].x; r.y += rv[u].y; r.z += rv[u].z; r.w += rv[u].w; }
-                if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-                *reinterpret_cast<float4*>(y + pix[u] * y_ld + 4 * q[u]) = r;
+                if (yh) {     // f16 copy for the tensor-core consumer (round to nearest even; same mantissa width as TF32)
+                    const __half2 lo = __floats2half2_rn(r.x, r.y), hi = __floats2half2_rn(r.z, r.w);
+                    uint2 pk; pk.x = *reinterpret_cast<const unsigned*>(&lo); pk.y = *reinterpret_cast<const unsigned*>(&hi);
+                    *reinterpret_cast<uint2*>(yh + pix[u] * yh_ld + 4 * q[u]) = pk;
+                }
+                if (y) {
+                    if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+                    *reinterpret_cast<float4*>(y + pix[u] * y_ld + 4 * q[u]) = r;
+                }
             }
         }
         return;
@@ -204,13 +212,21 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
             const float4 v = *reinterpret_cast<const float4*>(res + pix * res_ld + 4 * q);
             r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
         }
-        if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
-        *reinterpret_cast<float4*>(y + pix * y_ld + 4 * q) = r;
+        if (yh) {
+            const __half2 lo = __floats2half2_rn(r.x, r.y), hi = __floats2half2_rn(r.z, r.w);
+            uint2 pk; pk.x = *reinterpret_cast<const unsigned*>(&lo); pk.y = *reinterpret_cast<const unsigned*>(&hi);
+            *reinterpret_cast<uint2*>(yh + pix * yh_ld + 4 * q) = pk;
+        }
+        if (y) {
+            if (round_out) { r.x = round_tf32(r.x); r.y = round_tf32(r.y); r.z = round_tf32(r.z); r.w = round_tf32(r.w); }
+            *reinterpret_cast<float4*>(y + pix * y_ld + 4 * q) = r;
+        }
     }
 }
 
 void check_apply(const View& x, int pool, const View* res, const View& y) {
     THA4_REQUIRE(x.C == y.C && x.C % 4 == 0 && x.ld % 4 == 0 && y.ld % 4 == 0, "norm_apply: channels");
+    THA4_REQUIRE(!x.f16 && (!res || !res->f16), "norm_apply: fp32 input / residual");
     if (pool) THA4_REQUIRE(y.H * 2 == x.H && y.W * 2 == x.W, "norm_apply: pool dims");
     else THA4_REQUIRE(y.H == x.H && y.W == x.W, "norm_apply: dims");
     if (res) THA4_REQUIRE(res->H == y.H && res->W == y.W && res->C == y.C && res->ld % 4 == 0, "norm_apply: res dims");
@@ -246,27 +262,33 @@ void norm_apply(const View& x, const float* coef, int act, int pool, const View*
     const int blocks = (int)std::max<long>(1, std::min<long>((total + 1023) / 1024, 148L * 8));
     ProfScope prof(PROF_NORM, s);
     prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() + y.pixels() + (res ? y.pixels() : 0)) * x.C * 4);
+    THA4_REQUIRE(!y.f16, "norm_apply: fp32 output");
     norm_apply_kernel<false><<<blocks, 256, 0, s>>>(x.p, x.H, x.W, x.ld, coef, act, pool, res ? res->p : nullptr,
-                                                    res ? res->ld : 0, y.p, y.H, y.W, y.ld, x.C, total, round_out,
+                                                    res ? res->ld : 0, y.p, y.H, y.W, y.ld, nullptr, 0, x.C, total, round_out,
                                                     nullptr, 0, 1, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0);
     THA4_LAUNCH_CHECK();
 }
 
 void norm_apply_fused(const View& x, int groups, const float* gamma, const float* beta, const float* film0,
                       const float* film1, int film1_ld, int act, int pool, const View* res, const View& y, cudaStream_t s,
-                      int round_out) {
+                      int round_out, const View* y16) {
     check_apply(x, pool, res, y);
     THA4_REQUIRE(x.stats != nullptr, "norm_apply_fused: view has no statistics");
+    // outputs: y fp32 (optionally with an extra f16 copy y16), or y itself f16
+    float* yf = y.f16 ? nullptr : y.p;
+    __half* yh = y.f16 ? y.hp() : (y16 ? y16->hp() : nullptr);
+    const int yh_ld = y.f16 ? y.ld : (y16 ? y16->ld : 0);
+    if (y16) THA4_REQUIRE(!y.f16 && y16->f16 && y16->C == y.C && y16->H == y.H && y16->W == y.W && y16->N == y.N && y16->ld % 4 == 0, "norm_apply_fused: f16 copy");
     THA4_REQUIRE(groups == 0 || x.C % groups == 0, "norm_apply_fused: groups");
     const long per_sample = (long)y.H * y.W * (y.C / 4);
     THA4_REQUIRE(per_sample < (1L << 31), "norm_apply: tensor too large for 32-bit indexing");
     const int bx = (int)std::max<long>(1, std::min<long>((per_sample + 1023) / 1024, std::max(1, 148 * 8 / y.N)));
     ProfScope prof(PROF_NORM, s);
-    prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() + y.pixels() + (res ? y.pixels() : 0)) * x.C * 4);
+    prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() * 4 + y.pixels() * (yf ? 4 : 0) + y.pixels() * (yh ? 2 : 0) + (res ? y.pixels() * 4 : 0)) * x.C);
     // per-sample pointers: grid.y selects the sample, the kernel indexes within it
     dim3 grid(bx, y.N);
     norm_apply_kernel<true><<<grid, 256, 2 * x.C * sizeof(float2), s>>>(
-        x.p, x.H, x.W, x.ld, nullptr, act, pool, res ? res->p : nullptr, res ? res->ld : 0, y.p, y.H, y.W, y.ld, x.C, per_sample,
+        x.p, x.H, x.W, x.ld, nullptr, act, pool, res ? res->p : nullptr, res ? res->ld : 0, yf, y.H, y.W, y.ld, yh, yh_ld, x.C, per_sample,
         round_out, x.stats, x.stats_ld, x.stats_rep, x.stats_rep_stride, x.H * x.W, groups, gamma, beta, film0, film1, film1_ld);
     THA4_LAUNCH_CHECK();
 }

@@ -20,7 +20,7 @@ void norm_finalize(const View& x, int groups, const float* gamma, const float* b
 // norm_finalize + norm_apply in one launch: every CTA rebuilds the affine of its sample in shared memory from x.stats.
 void norm_apply_fused(const View& x, int groups, const float* gamma, const float* beta, const float* film0,
                       const float* film1, int film1_ld, int act, int pool, const View* res, const View& y, cudaStream_t s,
-                      int round_out);
+                      int round_out, const View* y16 = nullptr);   // y may itself be an f16 view; y16: extra f16 copy of an fp32 y
 
 // y = act(x * A + B) (+ res).  pool == 1: y has half the resolution and is the 2x2 mean of the activated values
 // (AvgPool2d(2) after SiLU, unet.py:58,158).  x and y may alias when pool == 0.
@@ -42,7 +42,8 @@ void attention_forward(const View& qkv, int heads, const View& out, cudaStream_t
 void nchw_to_nhwc(const ImgView& src, const View& dst, cudaStream_t s);                 // dst.C == src.C
 void nhwc_to_nchw(const View& src, float* dst, cudaStream_t s);                          // dst contiguous NCHW
 void copy_window(const ImgView& src, float* dst, long dn, long dc, long dh, cudaStream_t s);  // strided NCHW copy
-void tile_vector(const float* vec, int vec_ld, int P, const View& dst, cudaStream_t s); // dst[n,y,x,c] = c<P ? vec[n][c] : 0
+void tile_vector(const float* vec, int vec_ld, int P, const View& dst, cudaStream_t s); // dst[n,y,x,c] = c<P ? vec[n][c] : 0  (dst fp32 or f16)
+void convert_f16(const View& src, const View& dst, cudaStream_t s);                      // fp32 view -> f16 view (tests)
 void resize_bilinear(const ImgView& src, float* dst, int Ho, int Wo, cudaStream_t s);   // align_corners=False
 void grid_sample(const ImgView& image, const float* grid_change, float* out, int* x0, int* y0, float* tx, float* ty,
                  cudaStream_t s);                                                        // any output may be null

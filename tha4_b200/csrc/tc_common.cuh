@@ -38,6 +38,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                  :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(bar) : "memory");
 }
@@ -59,7 +63,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
-
+// Same with the row width as a parameter: 128-byte rows / SWIZZLE_128B (layout 2, SBO 1024) or 64-byte rows /
+// SWIZZLE_64B (layout 4, SBO 512).
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_smem_desc_sw(uint32_t smem_addr) {
+    static_assert(ROWB == 128 || ROWB == 64, "row bytes");
+    const uint32_t lo = ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+    const uint32_t hi = ((8u * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
 
 }  // namespace tc
 }  // namespace tha4
