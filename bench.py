@@ -223,6 +223,7 @@ def main():
     ap.add_argument('--workload', default='teacher_b1', choices=sorted(WORKLOADS))
     ap.add_argument('--strict', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--option', action='append', default=[], help='library option name=value (developer A/B runs)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -257,6 +258,9 @@ def main():
     ctx = poser.get_context()
     ctx.set_option('strict', args.strict)
     ctx.set_option('microbatch', 8)
+    for kv in args.option:
+        k, v = kv.split('=')
+        ctx.set_option(k, int(v))
     distiller = None
     if distill:
         from tha4_b200.distill import BodyMorpherDistiller

@@ -7,7 +7,7 @@
 #include <atomic>
 #include <cstring>
 
-namespace tha4 { std::atomic<long> g_kernel_launches{0}; }
+namespace tha4 { std::atomic<long> g_kernel_launches{0}; bool g_use_pdl = true; }
 
 using namespace tha4;
 
@@ -197,6 +197,7 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         else if (!strcmp(name, "persistent_conv")) conv_tcp_enable(value != 0);
         else if (!strcmp(name, "conv_mt2")) conv_tc_enable_mt2(value != 0);
         else if (!strcmp(name, "half_operands")) ctx->half_operands = value ? 1 : 0;
+        else if (!strcmp(name, "pdl")) g_use_pdl = value != 0;
         else if (!strcmp(name, "profile")) { prof_enable(value != 0); if (value == 2) prof_reset(); }
         else if (!strcmp(name, "microbatch")) { THA4_REQUIRE(value >= 1 && value <= 1024, "microbatch range"); ctx->microbatch = (int)value; }
         else throw std::runtime_error(std::string("tha4: unknown option ") + name);

@@ -12,6 +12,7 @@
 namespace tha4 {
 
 extern std::atomic<long> g_kernel_launches;   // every kernel this library launches is counted (bench "gpu_launches")
+extern bool g_use_pdl;                        // programmatic dependent launch on the kernels that support it (option "pdl")
 
 // NHWC fp32 activation view.  `ld` is the pixel stride in floats (>= C) so that a tensor can live in a channel
 // slice of a wider buffer (U-Net skip concatenation is free: producers write into their slice).
@@ -74,6 +75,37 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
         if (!(cond)) throw std::runtime_error(std::string("tha4: ") + (msg) + " [" #cond "] at " + \
                                               __FILE__ + ":" + std::to_string(__LINE__));         \
     } while (0)
+
+// Programmatic dependent launch: a kernel launched through launch_pdl may start while its predecessor in the stream is
+// still running; it must execute pdl_wait() before touching global memory (blocks until every earlier grid has
+// completed and flushed) and should execute pdl_trigger() once it holds its resources (so that the NEXT kernel's
+// prologue -- barrier init, TMEM allocation, descriptor prefetch, launch latency -- overlaps this one's body).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_z, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_use_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (cluster_z > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = (unsigned)cluster_z;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (e != cudaSuccess)
+        throw CudaError(std::string("cudaLaunchKernelEx failed: ") + cudaGetErrorString(e));
+}
+#endif
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

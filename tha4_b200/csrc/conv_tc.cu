@@ -106,6 +106,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // resources are held: let the next kernel of the stream start its prologue, then wait for our own producers
+    pdl_trigger();
+    pdl_wait();
 
     if (nk > 0) {
         if (warp == 0) {
@@ -301,17 +304,43 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 for (int j = 0; j < cn; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
             }
             if (p.stats) {
+                // per-column sums of this CTA's slice: thread te holds partials of chunk te % SC; fold the 128 / SC row
+                // threads of each chunk in two short steps (8 floats per thread, then <= 16 doubles per output)
                 float* red = reinterpret_cast<float*>(smem) + 128 * BN;          // [128][8], behind the partial tile
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { red[te * 8 + k] = su[k]; red[te * 8 + 4 + k] = sq[k]; }
                 asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                if (te < SC && col < p.outC) {
-                    double a8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    for (int t2 = te; t2 < 128; t2 += SC)
-                        for (int k = 0; k < 8; ++k) a8[k] += (double)red[t2 * 8 + k];
-                    double* d = p.stats + (long)(blockIdx.x % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + col) * 2;
-                    const int cn = min(4, p.outC - col);
-                    for (int k = 0; k < cn; ++k) { atomicAdd(d + 2 * k, a8[k]); atomicAdd(d + 2 * k + 1, a8[4 + k]); }
+                constexpr int NOUT = SC * 8;                                     // (chunk, {4 sums, 4 sums of squares})
+                double* dbase = p.stats + (long)(blockIdx.x % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + n0 + split * SL) * 2;
+                if constexpr (NOUT <= 128) {
+                    constexpr int G = 128 / NOUT;                                // threads per output
+                    constexpr int PER = 128 / SC / G;                            // entries per thread (= 8)
+                    float* red2 = red + 128 * 8;                                 // [G][NOUT]
+                    const int o = te % NOUT, g = te / NOUT;
+                    const int oc = o >> 3, ok = o & 7;
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) acc += red[(oc + SC * (g * PER + i)) * 8 + ok];
+                    red2[g * NOUT + o] = acc;
+                    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                    if (te < NOUT) {
+                        const int c = n0 + split * SL + oc * 4 + (ok & 3);
+                        if (c < p.outC) {
+                            double a = 0.0;
+#pragma unroll
+                            for (int gg = 0; gg < G; ++gg) a += (double)red2[gg * NOUT + o];
+                            atomicAdd(dbase + 2 * (oc * 4 + (ok & 3)) + (ok >> 2), a);
+                        }
+                    }
+                } else {
+                    for (int o = te; o < NOUT; o += 128) {
+                        const int oc = o >> 3, ok = o & 7;
+                        const int c = n0 + split * SL + oc * 4 + (ok & 3);
+                        if (c >= p.outC) continue;
+                        double a = 0.0;
+                        for (int t2 = oc; t2 < 128; t2 += SC) a += (double)red[t2 * 8 + ok];
+                        atomicAdd(dbase + 2 * (oc * 4 + (ok & 3)) + (ok >> 2), a);
+                    }
                 }
             }
         }
@@ -450,23 +479,13 @@ void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
     constexpr size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static_assert((size_t)STAGES * STAGE_BYTES >= (size_t)4 * 32 * 33 * 4 + 4 * BN * 8, "epilogue scratch must fit in the pipeline buffers");
-    static_assert(CS == 1 || (size_t)STAGES * STAGE_BYTES >= (size_t)128 * BN * 4 + 128 * 8 * 4, "partial tile must fit");
+    static_assert(CS == 1 || (size_t)STAGES * STAGE_BYTES >= (size_t)128 * BN * 4 + 128 * 8 * 4 + 128 * 4, "partial tile + statistics scratch must fit");
     static bool configured = false;
     if (!configured) {
         THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES_, CS, MT, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    if (CS == 1) {
-        conv_tc_kernel<BN, STAGES_, CS, MT, OP><<<grid, TC_THREADS, smem, s>>>(ma, mb, p);
-    } else {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = CS;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        THA4_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES_, CS, MT, OP>, ma, mb, p));
-    }
+    launch_pdl(conv_tc_kernel<BN, STAGES_, CS, MT, OP>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, p);
     THA4_LAUNCH_CHECK();
 }
 

@@ -104,16 +104,34 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
     const int cq = C >> 2;
     int n_fixed = 0;
     if (FUSED) {
+        pdl_trigger();      // launched with programmatic stream serialization: the statistics come from the previous kernel
+        pdl_wait();
         // two-step prologue: (1) mean / rstd per statistics group (channel for InstanceNorm, channel group for GroupNorm)
         // into shared memory, (2) per-channel affine incl. gamma/beta and the FiLM scale-shifts.
         n_fixed = blockIdx.y;
         float2* sm_grp = sm_coef + C;                          // [ngroups] (mean, rstd)
         const int ng = groups == 0 ? C : groups, cpg = C / ng;
+        double2* sm_ch = reinterpret_cast<double2*>(sm_coef + 2 * C);   // [C] per-channel (sum, sum of squares) over the replicas
+        if (cpg > 1) {                                         // GroupNorm: all threads fold the replicas, then one thread per group
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                double su = 0.0, sq = 0.0;
+                for (int r = 0; r < rep; ++r) {
+                    const double2 v = *reinterpret_cast<const double2*>(sums + r * rep_stride + ((long)n_fixed * stats_ld + c) * 2);
+                    su += v.x; sq += v.y;
+                }
+                sm_ch[c] = make_double2(su, sq);
+            }
+            __syncthreads();
+        }
         for (int g = threadIdx.x; g < ng; g += blockDim.x) {
             double su = 0.0, sq = 0.0;
-            for (int r = 0; r < rep; ++r) {
-                const double* sn = sums + r * rep_stride + ((long)n_fixed * stats_ld + (long)g * cpg) * 2;
-                for (int j = 0; j < cpg; ++j) { su += sn[2 * j]; sq += sn[2 * j + 1]; }
+            if (cpg > 1) {
+                for (int j = 0; j < cpg; ++j) { const double2 v = sm_ch[g * cpg + j]; su += v.x; sq += v.y; }
+            } else {
+                for (int r = 0; r < rep; ++r) {
+                    const double2 v = *reinterpret_cast<const double2*>(sums + r * rep_stride + ((long)n_fixed * stats_ld + g) * 2);
+                    su += v.x; sq += v.y;
+                }
             }
             const double cnt = (double)HW * cpg;
             const double mean = su / cnt;
@@ -287,9 +305,9 @@ void norm_apply_fused(const View& x, int groups, const float* gamma, const float
     prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() * 4 + y.pixels() * (yf ? 4 : 0) + y.pixels() * (yh ? 2 : 0) + (res ? y.pixels() * 4 : 0)) * x.C);
     // per-sample pointers: grid.y selects the sample, the kernel indexes within it
     dim3 grid(bx, y.N);
-    norm_apply_kernel<true><<<grid, 256, 2 * x.C * sizeof(float2), s>>>(
-        x.p, x.H, x.W, x.ld, nullptr, act, pool, res ? res->p : nullptr, res ? res->ld : 0, yf, y.H, y.W, y.ld, yh, yh_ld, x.C, per_sample,
-        round_out, x.stats, x.stats_ld, x.stats_rep, x.stats_rep_stride, x.H * x.W, groups, gamma, beta, film0, film1, film1_ld);
+    launch_pdl(norm_apply_kernel<true>, grid, dim3(256), 2 * x.C * sizeof(float2) + x.C * sizeof(double2), s, 1,
+               (const float*)x.p, x.H, x.W, x.ld, (const float*)nullptr, act, pool, (const float*)(res ? res->p : nullptr), res ? res->ld : 0, yf, y.H, y.W, y.ld, yh, yh_ld, x.C, per_sample,
+               round_out, (const double*)x.stats, x.stats_ld, x.stats_rep, x.stats_rep_stride, x.H * x.W, groups, gamma, beta, film0, film1, film1_ld);
     THA4_LAUNCH_CHECK();
 }
 
