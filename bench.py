@@ -360,7 +360,7 @@ def main():
         'metric': 'distillation examples/sec' if distill else '512x512 RGBA frames/sec', 'value': value,
         'unit': 'examples/s' if distill else 'frames/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'tf32 products, f32 accumulate/storage' if wl['mode'] in ('mode_07', 'distill') and not args.strict else
+        'dtype': 'f16/tf32 operands (10-bit mantissa), f32 accumulate, f32 storage outside conv operands' if wl['mode'] in ('mode_07', 'distill') and not args.strict else
                  ('f32 (3xTF32)' if wl['mode'] == 'mode_07' else 'f16 products, f32 accumulate'),
         'data': 'synthetic poses; ' + weights_desc + '; lambda_00.png character image',
         'config': {'workload': wl['desc'], 'batch_per_gpu': B, 'parallelism': ('data parallel, one NCCL all-reduce of the 1.33 MB flat gradient per step (dp%d)' if distill else 'frames sharded, no collective (dp%d)') % world,
@@ -376,9 +376,9 @@ def main():
     if prof.get('conv', {}).get('us', 0) > 0:
         c = prof['conv']
         ach = c['flops'] / (c['us'] * 1e-6) / 1e12
-        line['roofline'] = {'kernel': 'conv_igemm_kernel (implicit-GEMM conv, TF32 mma.sync)', 'bound': 'tensor', 'achieved': ach,
+        line['roofline'] = {'kernel': 'conv_tc_kernel (implicit-GEMM conv: TMA + tcgen05.mma kind::f16/tf32, TMEM accumulator; all conv launches of the step)', 'bound': 'tensor', 'achieved': ach,
                             'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
-                            'peak_source': peaks['source'] + ' dense bf16 burst; TF32 nominal peak is half of it',
+                            'peak_source': peaks['source'] + ' dense bf16 burst (= the f16 operand rate; kind::tf32 layers peak at half of it)',
                             'avg_launch_us': c['us'] / max(1, c['launches']), 'launches_per_step': c['launches'] / args.steps,
                             'share_of_profiled_kernel_time': c['us'] / max(1.0, sum(v['us'] for v in prof.values()))}
     if prof.get('tail', {}).get('us', 0) > 0:

@@ -118,6 +118,17 @@ int64_t tha4_siren_morpher_param_count(void);
 int tha4_siren_morpher_train_step(tha4_ctx* ctx, const float* image, const float* pose, const float* target_posed,
                                   const float* target_warped, const float* target_grid_change, const float* loss_weights,
                                   const float* params, float* grads, double* host_loss_means, int B, void* stream);
+/* Face student (SirenFaceMorpher00TrainerArgs, src/tha4/nn/siren/face_morpher/siren_face_morpher_00_trainer.py:101-186;
+ * computation protocol siren_face_morpher_protocols_00.py:48-105): number of fp32 parameters in state_dict order (121 476) */
+int64_t tha4_siren_face_morpher_param_count(void);
+/* student forward on pose[:, 0:39] (pose rows pose_ld floats apart) + L1 against `target` [B,4,128,128] (the teacher's
+ * mode-12 output 0 cropped as transform_poser_posed_image_to_groundtruth does, :123-126) + L1 of the difference
+ * multiplied by `mask` [B,4,128,128] (MaskedL1Loss, shion/base/loss/l1_loss.py:40-58; eye_mouth_mask of the batch),
+ * weights loss_weights[2] (1.0 / 20.0 in the reference), mean reduction + full backward.  params / grads as above.
+ * host_loss_means (optional): the two unweighted means (synchronises). */
+int tha4_siren_face_morpher_train_step(tha4_ctx* ctx, const float* pose, int pose_ld, const float* target, const float* mask,
+                                       const float* loss_weights, const float* params, float* grads, double* host_loss_means,
+                                       int B, void* stream);
 /* torch.optim.Adam step on flat buffers (shion/base/optimizer_factories.py:9-17); grads are scaled by grad_scale first
  * (1/world_size after a summing all-reduce = DDP's gradient averaging) */
 int tha4_adam_step(tha4_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

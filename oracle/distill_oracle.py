@@ -21,6 +21,19 @@ def body_losses_and_grads(student_sd: Dict[str, Tensor], image: Tensor, pose: Te
     return [float(t.detach()) for t in terms], flat
 
 
+def face_losses_and_grads(student_sd: Dict[str, Tensor], pose: Tensor, target: Tensor, mask: Tensor,
+                          weights: Sequence[float] = (1.0, 20.0)) -> Tuple[List[float], Tensor]:
+    """Face student (siren_face_morpher_protocols_00.py:72-105; siren_face_morpher_00_trainer.py:112-114,168-186;
+    shion/base/loss/l1_loss.py:9-24,40-58): returns ([mean |t-o|, mean |(t-o) m|], flat gradient in state_dict order)."""
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in student_sd.items()}
+    out = O.siren_face_morpher(sd, pose[:, 0:39])
+    terms = [(target - out).abs().mean(), ((target - out) * mask).abs().mean()]
+    loss = sum(w * t for w, t in zip(weights, terms))
+    loss.backward()
+    flat = torch.cat([sd[k].grad.reshape(-1) for k in student_sd])
+    return [float(t.detach()) for t in terms], flat
+
+
 def adam_reference(params: Tensor, grads: Sequence[Tensor], lr: float, betas=(0.9, 0.999), eps=1e-8) -> Tensor:
     p = params.detach().clone().requires_grad_(True)
     opt = torch.optim.Adam([p], lr=lr, betas=betas, eps=eps)

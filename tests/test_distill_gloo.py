@@ -18,6 +18,11 @@ class _StubCtx:
         grads.copy_(torch.sin(params * 3.0) * (1.0 + dist.get_rank()))       # rank-dependent "gradient"
         return [0.0, 0.0, 0.0, 0.0]
 
+    def siren_face_morpher_train_step(self, pose, target, mask, weights, params, grads, want_losses=True):
+        assert target.shape[1:] == (4, 128, 128) and mask.shape == target.shape
+        grads.copy_(torch.cos(params * 2.0) * (1.0 + dist.get_rank()))
+        return [0.0, 0.0]
+
     def adam_step(self, params, grads, m, v, lr, step, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
         g = grads * grad_scale
         m.mul_(betas[0]).add_(g, alpha=1 - betas[0])
@@ -61,6 +66,20 @@ def _worker(rank, world, port, out):
         out[rank] = float((d.flat - ref).abs().max())
         # parameters stayed views of the flat buffer
         assert torch.equal(torch.cat([p.data.reshape(-1) for p in student.parameters()]), d.flat)
+        # face student: same plumbing (teacher crop -> step -> all-reduce -> Adam)
+        face = mode_14.load_face_morpher(None)
+        for p in face.parameters():
+            p.data.normal_(0, 0.1)
+        f = distill.FaceMorpherDistiller.__new__(distill.FaceMorpherDistiller)
+        f.teacher, f.student, f.ctx = _StubTeacher(), face, _StubCtx()
+        f.flat = distill.flatten_parameters(face)
+        f.grad, f.exp_avg, f.exp_avg_sq = (torch.zeros_like(f.flat) for _ in range(3))
+        f.betas, f.eps, f.step_count, f.group, f.world = (0.9, 0.999), 1e-8, 0, None, world
+        q0 = f.flat.clone()
+        f.train_step(torch.zeros(1, 4, 192, 192), torch.zeros(1, 45), torch.ones(1, 4, 128, 128), lr=1e-3, want_losses=False)
+        mean_grad = torch.cos(q0 * 2.0) * (sum(1.0 + r for r in range(world)) / world)
+        ref = distill_oracle.adam_reference(q0, [mean_grad], 1e-3)
+        out[rank] = max(out[rank], float((f.flat - ref).abs().max()))
     finally:
         dist.destroy_process_group()
 

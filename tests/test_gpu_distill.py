@@ -90,3 +90,67 @@ def test_full_distill_step_with_teacher(teacher_sds, student_sds):
     # the updated student is what the inference path now uses
     outs = student.to(DEV)(t[5].to(DEV), pose.to(DEV))
     assert len(outs) == 5 and torch.isfinite(outs[0]).all()
+
+
+# ------------------------------------------------------------------------------------------ face student (a17)
+def test_face_student_train_step_vs_autograd(student_sds):
+    """SirenFaceMorpher00 step: plain + eye/mouth-masked L1 (weights 1 / 20) and the flat gradient vs CPU autograd."""
+    from tha4_b200.distill import FACE_LOSS_WEIGHTS
+    sd = student_sds['face_morpher']
+    n = 3
+    pose = synth.random_poses(n, seed=9)
+    target = _smooth(31, n, 4)[:, :, 100:228, 190:318].contiguous()
+    g = torch.Generator().manual_seed(5)
+    mask = (torch.rand(n, 1, 128, 128, generator=g) > 0.7).float().repeat(1, 4, 1, 1).contiguous()
+    ref_losses, ref_grad = distill_oracle.face_losses_and_grads(sd, pose, target, mask, FACE_LOSS_WEIGHTS)
+
+    student = mode_14.load_face_morpher(None, sd).to(DEV)
+    flat = flatten_parameters(student)
+    assert flat.numel() == 121476
+    assert torch.equal(flat.cpu(), torch.cat([v.reshape(-1) for v in sd.values()]))
+    grad = torch.zeros_like(flat)
+    losses = G.ctx().siren_face_morpher_train_step(pose.to(DEV), target.to(DEV), mask.to(DEV), FACE_LOSS_WEIGHTS, flat, grad)
+    torch.cuda.synchronize()
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 2e-3 * max(abs(b), 1e-3), (losses, ref_losses)
+    gg = grad.cpu()
+    rel = ((gg - ref_grad).norm() / ref_grad.norm()).item()
+    cos = torch.nn.functional.cosine_similarity(gg, ref_grad, dim=0).item()
+    print('\nface distill grad: rel L2 err %.3e cosine %.6f |g| %.3e' % (rel, cos, ref_grad.norm().item()))
+    off = 0
+    for k, v in sd.items():
+        m = v.numel()
+        a, b = gg[off:off + m], ref_grad[off:off + m]
+        assert ((a - b).norm() / (b.norm() + 1e-20)).item() <= 6e-2, k
+        off += m
+    assert rel <= 3e-2 and cos >= 0.999
+
+
+def test_full_face_distill_step_with_teacher(teacher_sds, student_sds):
+    """mode_12 teacher (strict) -> crop -> face-student step -> Adam; losses against the oracle teacher + oracle student."""
+    from tha4_b200.distill import FaceMorpherDistiller, face_groundtruth_crop
+    from tha4_b200.poser.modes import mode_12
+    teacher = mode_12.create_poser(DEV, state_dicts=teacher_sds)
+    teacher.get_context().set_option('strict', 1)
+    student = mode_14.load_face_morpher(None, student_sds['face_morpher'])
+    d = FaceMorpherDistiller(teacher, student)
+    image = synth.synthetic_image(0, 2)
+    pose = synth.random_poses(2, seed=23)
+    mask = torch.zeros(2, 4, 128, 128)
+    mask[:, :, 40:90, 30:100] = 1.0
+    before = d.flat.clone()
+    out = d.train_step(image.to(DEV), pose.to(DEV), mask.to(DEV), lr=1e-4)
+    with torch.no_grad():
+        t = O.mode_12_outputs(teacher_sds, image, pose)
+    target = face_groundtruth_crop(t[0])
+    assert target.shape == (2, 4, 128, 128)
+    ref_losses, ref_grad = distill_oracle.face_losses_and_grads(student_sds['face_morpher'], pose, target, mask)
+    for name, b in zip(('full', 'eye_mouth'), ref_losses):
+        assert abs(out[name] - b) <= 3e-3 * max(abs(b), 1e-3), (name, out[name], b)
+    assert ((d.grad.cpu() - ref_grad).norm() / ref_grad.norm()).item() <= 4e-2
+    ref_p = distill_oracle.adam_reference(before.cpu(), [ref_grad], 1e-4)
+    upd, ref_upd = (d.flat.cpu() - before.cpu()), (ref_p - before.cpu())
+    big = ref_grad.abs() > 1e-3 * ref_grad.abs().max()
+    assert (torch.sign(upd[big]) == torch.sign(ref_upd[big])).float().mean().item() >= 0.995
+    y = student.to(DEV)(pose[:, 0:39].to(DEV))
+    assert y.shape == (2, 4, 128, 128) and torch.isfinite(y).all()

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     'tha4_eyebrow_decomposer_forward', 'tha4_eyebrow_morphing_combiner_forward', 'tha4_face_morpher_forward',
     'tha4_morpher_forward', 'tha4_upscaler_forward', 'tha4_siren_face_morpher_forward', 'tha4_siren_morpher_forward',
     'tha4_teacher_forward', 'tha4_student_forward', 'tha4_siren_morpher_param_count', 'tha4_siren_morpher_train_step',
+    'tha4_siren_face_morpher_param_count', 'tha4_siren_face_morpher_train_step',
     'tha4_adam_step', 'tha4_images_differ', 'tha4_grid_sample', 'tha4_resize_bilinear',
     'tha4_base_grid', 'tha4_test_conv', 'tha4_test_norm', 'tha4_test_attention', 'tha4_test_linear',
 ]
@@ -51,6 +52,7 @@ def load_library() -> ctypes.CDLL:
     lib.tha4_get_counter.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
     lib.tha4_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]
     lib.tha4_siren_morpher_param_count.restype = ctypes.c_int64
+    lib.tha4_siren_face_morpher_param_count.restype = ctypes.c_int64
     lib.tha4_adam_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                    ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_float,
                                    ctypes.c_void_p]
@@ -261,6 +263,19 @@ class Context:
         losses = (ctypes.c_double * 4)()
         self._call('tha4_siren_morpher_train_step', *[_ptr(t) for t in tensors], w, _ptr(params), _ptr(grads),
                    losses if want_losses else None, B, self._stream())
+        return list(losses) if want_losses else None
+
+    def siren_face_morpher_train_step(self, pose: Tensor, target: Tensor, mask: Tensor, loss_weights: Sequence[float],
+                                      params: Tensor, grads: Tensor, want_losses: bool = True):
+        """pose [B, >= 39] (the first 39 entries are the student's input), target / mask [B,4,128,128]."""
+        pose, target, mask = [_check_input(t, self.device, n) for t, n in ((pose, 'pose'), (target, 'target'), (mask, 'mask'))]
+        B = pose.shape[0]
+        assert target.shape == (B, 4, 128, 128) and mask.shape == (B, 4, 128, 128) and pose.shape[1] >= 39
+        assert params.is_contiguous() and grads.is_contiguous() and params.dtype == torch.float32 and grads.dtype == torch.float32
+        w = (ctypes.c_float * 2)(*[float(x) for x in loss_weights])
+        losses = (ctypes.c_double * 2)()
+        self._call('tha4_siren_face_morpher_train_step', _ptr(pose), int(pose.shape[1]), _ptr(target), _ptr(mask), w, _ptr(params),
+                   _ptr(grads), losses if want_losses else None, B, self._stream())
         return list(losses) if want_losses else None
 
     def adam_step(self, params: Tensor, grads: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, lr: float, step: int,

@@ -385,6 +385,28 @@ int tha4_siren_morpher_train_step(tha4_ctx* ctx, const float* image, const float
     });
 }
 
+int64_t tha4_siren_face_morpher_param_count(void) { return (int64_t)siren_face_param_count(); }
+
+int tha4_siren_face_morpher_train_step(tha4_ctx* ctx, const float* pose, int pose_ld, const float* target, const float* mask,
+                                       const float* loss_weights, const float* params, float* grads, double* host_loss_means,
+                                       int B, void* stream) {
+    return guarded(ctx, [&] {
+        THA4_REQUIRE(B >= 1 && B <= 64, "face distill step: per-GPU batch must be 1..64");
+        THA4_REQUIRE(pose_ld >= 39, "face distill step: pose rows need at least 39 entries");
+        cudaStream_t s = (cudaStream_t)stream;
+        begin_pass(ctx, s);
+        Runtime rt = make_rt(ctx, stream);
+        siren_face_train_step(rt, pose, pose_ld, B, target, mask, loss_weights, params, grads, ctx->loss_acc);
+        if (host_loss_means) {
+            double h[2];
+            THA4_CUDA_CHECK(cudaMemcpyAsync(h, ctx->loss_acc, sizeof(h), cudaMemcpyDeviceToHost, s));
+            THA4_CUDA_CHECK(cudaStreamSynchronize(s));
+            const double nel = (double)B * 4 * 128 * 128;
+            host_loss_means[0] = h[0] / nel; host_loss_means[1] = h[1] / nel;
+        }
+    });
+}
+
 int tha4_adam_step(tha4_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                    float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
     return guarded(ctx, [&] { adam_step(params, grads, exp_avg, exp_avg_sq, (long)n, lr, beta1, beta2, eps, step, grad_scale, (cudaStream_t)stream); });

@@ -22,7 +22,7 @@ constexpr float OMEGA = 30.0f;
 // level input: [up(prev) (Cprev, from `prev` at R/2) | x | y | pose(45) | 0 pad]
 __global__ void __launch_bounds__(256) level_input_kernel(const float* __restrict__ prev, int Cprev, int prev_ld,
                                                           const float* __restrict__ pose, int pose_ld,
-                                                          const float* __restrict__ base, int R, int N, int C, float* __restrict__ out) {
+                                                          const float* __restrict__ base, int R, int N, int C, int npose, float* __restrict__ out) {
     const long total = (long)N * R * R * C;
     const int Rh = R >> 1;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) level_input_kernel(const float* __restric
             v = ty.l0 * (tx.l0 * a + tx.l1 * b) + ty.l1 * (tx.l0 * cc + tx.l1 * d);
         } else if (c == Cprev) v = base[x];
         else if (c == Cprev + 1) v = base[y];
-        else if (c < Cprev + 47) v = pose[(long)n * pose_ld + (c - Cprev - 2)];
+        else if (c < Cprev + 2 + npose) v = pose[(long)n * pose_ld + (c - Cprev - 2)];
         out[i] = v;
     }
 }
@@ -268,6 +268,40 @@ __global__ void __launch_bounds__(256) train_tail_kernel(const float* __restrict
     }
 }
 
+// Face student: out4 [P][4] (NHWC) vs target / mask NCHW [N,4,R,R].  loss_acc[0] = sum |o - t|, loss_acc[1] = sum |(t - o) m|
+// (l1_loss.py:9-24 L1Loss, :40-58 MaskedL1Loss); d_out = wn.x sgn(o - t) + wn.y sgn((o - t) m) m.
+__global__ void __launch_bounds__(256) face_tail_kernel(const float* __restrict__ out4, const float* __restrict__ target,
+                                                        const float* __restrict__ mask, int R, int N, float2 wn,
+                                                        float* __restrict__ d_out, double* __restrict__ loss_acc) {
+    __shared__ float red[8][2];
+    const long hw = (long)R * R, total = (long)N * hw;
+    float l0 = 0.0f, l1 = 0.0f;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long pp = i % hw; const int n = (int)(i / hw);
+        const float4 o = *reinterpret_cast<const float4*>(out4 + i * 4);
+        const float ov[4] = {o.x, o.y, o.z, o.w};
+        float g[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const long ti = ((long)n * 4 + c) * hw + pp;
+            const float d = ov[c] - target[ti], m = mask[ti];
+            l0 += fabsf(d); l1 += fabsf(d * m);
+            g[c] = wn.x * sgn(d) + wn.y * sgn(d * m) * m;
+        }
+        *reinterpret_cast<float4*>(d_out + i * 4) = make_float4(g[0], g[1], g[2], g[3]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { l0 += __shfl_xor_sync(0xffffffffu, l0, off); l1 += __shfl_xor_sync(0xffffffffu, l1, off); }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[warp][0] = l0; red[warp][1] = l1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += (double)red[w][threadIdx.x];
+        atomicAdd(loss_acc + threadIdx.x, s);
+    }
+}
+
 // torch.optim.Adam (no weight decay, no amsgrad): optimizer_factories.py:9-17 (betas 0.9 / 0.999, eps 1e-8)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
                             float lr, float b1, float b2, float eps, float bc1, float bc2, float gscale) {
@@ -356,7 +390,7 @@ void siren_body_train_step(Runtime& rt, const ImgView& image, const float* pose,
         xin[l] = mk(P, N, R, L[3 * l].kpad);
         const View* prev = l > 0 ? &a[l - 1][2] : nullptr;
         level_input_kernel<<<grid_for((long)N * R * R * xin[l].C), 256, 0, s>>>(prev ? prev->p : nullptr, Cprev[l], prev ? prev->ld : 0, pose,
-                                                                              pose_ld, base_grid_table(R), R, N, xin[l].C, xin[l].p);
+                                                                              pose_ld, base_grid_table(R), R, N, xin[l].C, 45, xin[l].p);
         THA4_LAUNCH_CHECK();
         for (int j = 0; j < 3; ++j) {
             const Dense& d = L[3 * l + j];
@@ -414,6 +448,87 @@ void siren_body_train_step(Runtime& rt, const ImgView& image, const float* pose,
             THA4_LAUNCH_CHECK();
             da = dprev;
         }
+    }
+}
+
+// reference layer table of SirenFaceMorpher00 (mode_14.py:93-105; vanilla/siren.py:60-91), in state_dict order
+static void face_layers(Dense (&L)[9]) {
+    long off = 0;
+    for (int i = 0; i < 9; ++i) {
+        L[i].nreal = i == 8 ? 4 : 128; L[i].kreal = i == 0 ? 41 : 128;
+        L[i].npad = L[i].nreal; L[i].kpad = i == 0 ? 44 : 128;
+        L[i].w_off = off; off += (long)L[i].nreal * L[i].kreal;
+        L[i].b_off = off; off += L[i].nreal;
+    }
+}
+
+long siren_face_param_count() { Dense L[9]; face_layers(L); return L[8].b_off + 4; }
+
+// Face-student distillation step: SirenFaceMorpher00 forward with stored activations, L1 +
+// eye/mouth-masked L1 against the teacher crop, full backward into a flat gradient buffer.
+// Reference: siren_face_morpher_protocols_00.py:48-105, siren_face_morpher_00_trainer.py:112-186.
+void siren_face_train_step(Runtime& rt, const float* pose, int pose_ld, int N, const float* target, const float* mask,
+                           const float loss_w[2], const float* params, float* grads, double* loss_acc) {
+    cudaStream_t s = rt.stream;
+    Pool* P = rt.persist;
+    constexpr int R = 128;
+    Dense L[9];
+    face_layers(L);
+    const long nparams = L[8].b_off + 4;
+    THA4_CUDA_CHECK(cudaMemsetAsync(grads, 0, nparams * sizeof(float), s));
+    THA4_CUDA_CHECK(cudaMemsetAsync(loss_acc, 0, 4 * sizeof(double), s));
+    ProfScope prof(PROF_SIREN, s);
+    float* bias_pad[9];
+    for (int i = 0; i < 9; ++i) {
+        bias_pad[i] = P->alloc(L[i].npad);
+        pad_bias_kernel<<<1, 128, 0, s>>>(params + L[i].b_off, L[i].nreal, L[i].npad, bias_pad[i]);
+        THA4_LAUNCH_CHECK();
+    }
+    // ------------------------------------------------------------------ forward, activations stored
+    View xin = mk(P, N, R, L[0].kpad), z[8], a[8];
+    level_input_kernel<<<grid_for((long)N * R * R * xin.C), 256, 0, s>>>(nullptr, 0, 0, pose, pose_ld, base_grid_table(R), R, N, xin.C, 39, xin.p);
+    THA4_LAUNCH_CHECK();
+    const long n4 = (long)N * R * R * 128 / 4;
+    for (int j = 0; j < 8; ++j) {
+        rt.scratch->reset();
+        z[j] = mk(P, N, R, 128);
+        a[j] = mk(P, N, R, 128);
+        dense_gemm(rt, params + L[j].w_off, L[j].nreal, L[j].kreal, false, bias_pad[j], j == 0 ? xin : a[j - 1], z[j]);
+        sine_forward_kernel<<<grid_for(n4), 256, 0, s>>>(z[j].p, a[j].p, n4);
+        THA4_LAUNCH_CHECK();
+    }
+    rt.scratch->reset();
+    View out4 = mk(P, N, R, 4);
+    dense_gemm(rt, params + L[8].w_off, 4, 128, false, bias_pad[8], a[7], out4);
+    // ------------------------------------------------------------------ losses + d(out4)
+    View d_out = mk(P, N, R, 4);
+    const double nel = (double)N * 4 * R * R;
+    face_tail_kernel<<<grid_for((long)N * R * R), 256, 0, s>>>(out4.p, target, mask, R, N,
+                                                              make_float2((float)(loss_w[0] / nel), (float)(loss_w[1] / nel)), d_out.p, loss_acc);
+    THA4_LAUNCH_CHECK();
+    // ------------------------------------------------------------------ backward
+    auto wgrad = [&](const View& dz, const View& x, const Dense& d) {
+        const long Pn = (long)dz.N * dz.H * dz.W;
+        const int psplit = (int)std::max<long>(1, std::min<long>(64, Pn / 4096));
+        dim3 grid(ceil_div(dz.C, 64), ceil_div(x.C, 64), psplit);
+        wgrad_kernel<<<grid, 128, 0, s>>>(dz.p, dz.C, x.p, x.C, Pn, d.nreal, d.kreal, grads + d.w_off);
+        THA4_LAUNCH_CHECK();
+        colsum_kernel<<<std::min<long>(148, std::max<long>(1, Pn / 512)), 256, 0, s>>>(dz.p, Pn, dz.C, d.nreal, grads + d.b_off);
+        THA4_LAUNCH_CHECK();
+    };
+    wgrad(d_out, a[7], L[8]);
+    View da = mk(P, N, R, 128);
+    rt.scratch->reset();
+    dense_gemm(rt, params + L[8].w_off, 4, 128, true, nullptr, d_out, da);       // d a7 = d_out W8
+    for (int j = 7; j >= 0; --j) {
+        sine_backward_kernel<<<grid_for(n4), 256, 0, s>>>(z[j].p, da.p, n4);       // da -> dz (in place)
+        THA4_LAUNCH_CHECK();
+        wgrad(da, j == 0 ? xin : a[j - 1], L[j]);
+        if (j == 0) break;
+        View dx = mk(P, N, R, 128);
+        rt.scratch->reset();
+        dense_gemm(rt, params + L[j].w_off, L[j].nreal, L[j].kreal, true, nullptr, da, dx);   // dx = dz W
+        da = dx;
     }
 }
 

@@ -1,4 +1,4 @@
-"""Distillation inner loop of the body student on the CUDA path -- replaces, as a unit, what the reference does in
+"""Distillation inner loops of the body and face students on the CUDA path -- replaces, as a unit, what the reference does in
 `SirenMorpherTrainingProtocol03.run_training_iteration` (src/tha4/nn/siren/morpher/siren_morpher_protocols_03.py:178-214):
 
     teacher forward under no_grad (mode_07, :102-108)  ->  student forward (:125-135)  ->  SumLoss of four
@@ -68,6 +68,62 @@ class BodyMorpherDistiller:
         if not want_losses:
             return None
         out = dict(zip(LOSS_TERMS, losses))
+        out['loss'] = sum(w * l for w, l in zip(loss_weights, losses))
+        return out
+
+    def state_dict(self) -> Dict[str, Tensor]:
+        return self.student.state_dict()
+
+
+FACE_LOSS_TERMS = ('full', 'eye_mouth')          # siren_face_morpher_00_trainer.py:168-186 (weights 1.0 / 20.0)
+FACE_LOSS_WEIGHTS = (1.0, 20.0)
+
+
+def face_groundtruth_crop(posed_face: Tensor) -> Tensor:
+    """transform_poser_posed_image_to_groundtruth (siren_face_morpher_00_trainer.py:123-126): the 128x128 window centred
+    at (96, 112) of the teacher's 192x192 face image."""
+    return posed_face[:, :, 112 - 64:112 + 64, 96 - 64:96 + 64].contiguous()
+
+
+class FaceMorpherDistiller:
+    """Inner loop of the face student -- replaces SirenFaceMorpherComputationProtocol00 + SirenMorpherTrainingProtocol03
+    for KEY_MODULE = SirenFaceMorpher00 (siren_face_morpher_protocols_00.py:48-105): teacher = the mode_12 poser (face
+    networks only, get_poser at siren_face_morpher_00_trainer.py:23-26), student input pose[:, 0:39], losses L1 + 20 x
+    eye/mouth-masked L1, one flat-gradient all-reduce, Adam."""
+
+    def __init__(self, teacher: GeneralPoser02, student, betas=(0.9, 0.999), eps: float = 1e-8, process_group=None):
+        self.teacher = teacher
+        self.student = student
+        self.ctx: Context = teacher.get_context()
+        teacher.get_modules()
+        student.to(self.ctx.device)
+        self.flat = flatten_parameters(student)
+        assert self.flat.numel() == 121476
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.betas, self.eps = betas, eps
+        self.step_count = 0
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+
+    def train_step(self, image: Tensor, pose: Tensor, eye_mouth_mask: Tensor, lr: float,
+                   loss_weights: Sequence[float] = FACE_LOSS_WEIGHTS, want_losses: bool = True) -> Optional[Dict[str, float]]:
+        """image [b,4,512,512], pose [b,45], eye_mouth_mask [b,4,128,128] (get_face_mask_image, :84-97)."""
+        with torch.no_grad():
+            t = self.teacher.get_posing_outputs(image, pose)            # mode_12: output 0 = posed face [b,4,192,192]
+            target = face_groundtruth_crop(t[0])
+            pose2 = pose if pose.dim() == 2 else pose.unsqueeze(0)
+            losses = self.ctx.siren_face_morpher_train_step(pose2, target, eye_mouth_mask, loss_weights, self.flat, self.grad, want_losses)
+            if self.world > 1:
+                dist.all_reduce(self.grad, group=self.group)
+            self.step_count += 1
+            self.ctx.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, lr, self.step_count, self.betas, self.eps,
+                               grad_scale=1.0 / self.world)
+            self.student._uploaded_key = None
+        if not want_losses:
+            return None
+        out = dict(zip(FACE_LOSS_TERMS, losses))
         out['loss'] = sum(w * l for w, l in zip(loss_weights, losses))
         return out
 
