@@ -104,6 +104,12 @@ CONV_CASES = [
     (0, 1, 528, 16, 512, False, 0, 0, 0),        # pose-concat bottleneck as the f16 path sees it (pose padded to 16)
     (0, 1, 544, 24, 512, False, 0, 0, 3),
     (3, 1, 512, 16, 1536, True, 0, 0, 0),        # attention qkv
+    (0, 1, 32, 512, 32, True, 1, 0, 0),          # > 444 tiles: persistent streaming kernel (ring + TMEM double buffer across tiles)
+    (0, 2, 64, 256, 64, True, 1, 0, 0),
+    (0, 3, 128, 200, 128, True, 0, 0, 0),        # streaming kernel with partial tiles in both directions
+    (4, 1, 64, 128, 64, True, 2, 0, 0),          # 4 phases x 128 tiles
+    (2, 1, 128, 128, 64, False, 0, 0, 0),
+    (0, 1, 96, 384, 32, True, 0, 0, 0),
 ]
 
 

@@ -21,6 +21,7 @@ struct ConvWeights {
     float* bias = nullptr;      // [cout] or nullptr
     int cin = 0, cout = 0, cin_pad = 0, cout_pad = 0;
     int ntaps = 0, nphase = 1;
+    bool dynamic = false;       // weights are rewritten between launches (distillation): never fetch them ahead of the stream order
     bool tf32_rounded = false;  // weights were rounded to TF32 at pack time (non-strict contexts)
     int stride = 1;             // input stride
     int out_mul = 1;            // output coordinate = m * out_mul + phase offset (2 for the transposed conv)
@@ -76,6 +77,7 @@ void conv_tcp_enable(bool on);
 void conv_enable_tc(bool on);
 bool conv_tc_enabled();
 void conv_tc_enable_cluster(bool on);
+void conv_tc_enable_stream(bool on);    // persistent streaming kernel for multi-wave unsplit launches (default on)
 void conv_tc_enable_mt2(bool on);       // two 128-pixel tiles per CTA sharing each weight tile (default on)   // split-K through a thread-block cluster + DSMEM (default) vs workspace + reduce kernel                                                        // default: on
 
 }  // namespace tha4

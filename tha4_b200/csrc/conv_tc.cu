@@ -34,6 +34,7 @@ struct TcParams {
     const float* res; int resH, resW, res_ld, res_mode;
     int N, MH, MW, tiles_x, tiles_y;
     int ntaps, cpt, ksplit, out_mul;
+    int pre_b;                                     // weight tiles may be fetched before the programmatic-dependency wait
     float* ws; long ws_rows; int ws_ld;            // split-K partials: ws[z][tile*128 + row][cout_pad]
     double* stats; int stats_ld; int stats_rep; long stats_rep_stride;   // per-(n,c) sum / sum-of-squares of the output (optional)
     signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
@@ -106,8 +107,21 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // resources are held: let the next kernel of the stream start its prologue, then wait for our own producers
+    // resources are held: let the next kernel of the stream start its prologue, then wait for our own producers.
+    // The WEIGHT tiles of the first ring pass do not depend on the previous kernel: their TMA loads are issued before
+    // the dependency wait, so the DRAM round trip of the weights (they do not fit in L2 at B=1) overlaps the
+    // predecessor's tail instead of following it.
     pdl_trigger();
+    const int npre = p.pre_b ? min(nk, STAGES) : 0;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < npre; ++i) {
+            const uint32_t full = smem_u32(bars + i);
+            mbar_expect_tx(full, A_BYTES + B_BYTES);
+            const int kt = kb + i;
+            const int tap = kt / p.cpt;
+            tma_load_3d(smem_u32(smB + i * B_BYTES), &tmB, (kt - tap * p.cpt) * KCE, n0, phase * p.ntaps + tap, full);
+        }
+    }
     pdl_wait();
 
     if (nk > 0) {
@@ -115,14 +129,16 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             if (lane == 0) {   // ===== TMA producer =====
                 for (int i = 0; i < nk; ++i) {
                     const int s = i % STAGES;
-                    mbar_wait(smem_u32(bars + STAGES + s), ((i / STAGES) & 1) ^ 1);
                     const uint32_t full = smem_u32(bars + s);
-                    mbar_expect_tx(full, A_BYTES + B_BYTES);
                     const int kt = kb + i;
                     const int tap = kt / p.cpt;
                     const int c0 = (kt - tap * p.cpt) * KCE;
+                    if (i >= npre) {
+                        mbar_wait(smem_u32(bars + STAGES + s), ((i / STAGES) & 1) ^ 1);
+                        mbar_expect_tx(full, A_BYTES + B_BYTES);
+                        tma_load_3d(smem_u32(smB + s * B_BYTES), &tmB, c0, n0, phase * p.ntaps + tap, full);
+                    }
                     tma_load_4d(smem_u32(smA + s * A_BYTES), &tmA, c0, x0 + p.dx[phase][tap], y0 + p.dy[phase][tap], n, full);
-                    tma_load_3d(smem_u32(smB + s * B_BYTES), &tmB, c0, n0, phase * p.ntaps + tap, full);
                 }
             }
         } else if (warp == 1) {
@@ -355,6 +371,185 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent ("streaming") variant for the launches that are bound by memory latency rather than by the tensor pipe:
+// many 128-pixel tiles, few k-blocks each (the 32..128-channel layers at 128^2..512^2).  A CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring runs ACROSS tiles (the producer is already fetching tile i+1
+// while tile i is in its epilogue) and the accumulator is double-buffered in TMEM (2 x BN columns), so the three
+// latency chains of a tile -- operand fetch, MMA, residual fetch + store -- overlap between consecutive tiles of one
+// CTA as well as between the ~3 CTAs of an SM.  Unsplit K only (ksplit == 1, no cluster, MT == 1).
+template <int BN, int STAGES_, int OP>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_stream_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                      const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    constexpr int STAGES = op_stages(OP, STAGES_);
+    constexpr int ROWB = op_row_bytes(OP);
+    constexpr int KCE = op_kch(OP);
+    constexpr int A_BYTES = 128 * ROWB;
+    constexpr int B_BYTES = BN * ROWB;
+    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * B_BYTES);   // full[S], empty[S], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* scratch_all = reinterpret_cast<float*>(tmem_slot + 4);           // [4 warps][32][33]
+    float2* part = reinterpret_cast<float2*>(scratch_all + 4 * 32 * 33);    // [4 warps][BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * BN;
+    const int phase = blockIdx.z;
+    const int KT = p.ntaps * p.cpt;
+    const int ntiles = p.tiles_x * p.tiles_y * p.N;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STAGES + s), 1); }
+        mbar_init(smem_u32(bars + 2 * STAGES), 1); mbar_init(smem_u32(bars + 2 * STAGES + 1), 1);          // tmem_full[2]: one commit
+        mbar_init(smem_u32(bars + 2 * STAGES + 2), 128); mbar_init(smem_u32(bars + 2 * STAGES + 3), 128);  // tmem_empty[2]: 128 epilogue threads
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== TMA producer: one continuous ring over all tiles of this CTA =====
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+                for (int kt = 0; kt < KT; ++kt, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(smem_u32(bars + STAGES + s), ((it / STAGES) & 1) ^ 1);
+                    const uint32_t full = smem_u32(bars + s);
+                    mbar_expect_tx(full, A_BYTES + B_BYTES);
+                    const int tap = kt / p.cpt;
+                    const int c0 = (kt - tap * p.cpt) * KCE;
+                    tma_load_4d(smem_u32(smA + s * A_BYTES), &tmA, c0, x0 + p.dx[phase][tap], y0 + p.dy[phase][tap], n, full);
+                    tma_load_3d(smem_u32(smB + s * B_BYTES), &tmB, c0, n0, phase * p.ntaps + tap, full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ===== MMA issuer =====
+            constexpr uint32_t fmt = OP == OP_TF32 ? 2u : 0u;
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+                const uint32_t acc = lt & 1;
+                mbar_wait(smem_u32(bars + 2 * STAGES + 2 + acc), ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                for (int kt = 0; kt < KT; ++kt, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(smem_u32(bars + s), (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint64_t adesc = make_smem_desc_sw<ROWB>(smem_u32(smA + s * A_BYTES));
+                    const uint64_t bdesc = make_smem_desc_sw<ROWB>(smem_u32(smB + s * B_BYTES));
+#pragma unroll
+                    for (int k = 0; k < ROWB / 32; ++k) {
+                        if (OP == OP_TF32) umma_tf32(tmem_base + acc * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kt > 0 || k > 0) ? 1u : 0u);
+                        else umma_f16(tmem_base + acc * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kt > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(bars + STAGES + s));
+                }
+                umma_commit(smem_u32(bars + 2 * STAGES + acc));
+            }
+        }
+    } else {               // ===== epilogue warps =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        float* scratch = scratch_all + q * (32 * 33);
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            const uint32_t acc = lt & 1;
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
+            const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+            const int my = y0 + row / TILE_W, mx = x0 + row % TILE_W;
+            const bool valid = my < p.MH && mx < p.MW;
+            const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
+            float* orow = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld;
+            mbar_wait(smem_u32(bars + 2 * STAGES + acc), (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+                if (c0 + 32 >= BN) {     // last read of this accumulator: hand it back to the MMA thread
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                    mbar_arrive(smem_u32(bars + 2 * STAGES + 2 + acc));
+                }
+                const int cbase = n0 + c0;
+                if (cbase >= p.outC) continue;                         // warp-uniform
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                const int cn = min(32, p.outC - cbase);
+                if (valid) {
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
+                    }
+                    if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
+                        const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
+                        const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + cbase;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += rr[j];
+                    } else if (p.res_mode == RES_DOWN2) {
+                        const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + cbase;
+                        const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < cn) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+                    }
+                    if (cn == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(orow + cbase + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) orow[cbase + j] = v[j];
+                    }
+                }
+                if (p.stats) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = valid ? v[j] : 0.0f;
+                    __syncwarp();
+                    float su = 0.0f, sq = 0.0f;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) { const float t = scratch[rr * 33 + lane]; su += t; sq += t * t; }
+                    __syncwarp();
+                    part[q * BN + c0 + lane] = make_float2(su, sq);
+                }
+            }
+            if (p.stats) {
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                double* base = p.stats + (long)(tile % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + n0) * 2;
+                for (int c = (warp - 2) * 32 + lane; c < BN; c += 128) {
+                    if (n0 + c >= p.outC) break;
+                    const float2 a = part[c], b = part[BN + c], cc = part[2 * BN + c], d = part[3 * BN + c];
+                    atomicAdd(base + 2 * c, (double)a.x + (double)b.x + (double)cc.x + (double)d.x);
+                    atomicAdd(base + 2 * c + 1, (double)a.y + (double)b.y + (double)cc.y + (double)d.y);
+                }
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");       // `part` is rewritten by the next tile
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // out = sum_splits ws + bias + res  (deterministic split-K reduction; replaces fp32 atomics), plus the per-(n,c)
 // statistics of the result.  grid = (pixel slabs, N * nphase); thread (pl, q) walks pixels pl, pl + PL, ... of its slab.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcParams p, int nphase, int ppt) {
@@ -489,6 +684,31 @@ void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
     THA4_LAUNCH_CHECK();
 }
 
+template <int OP, int BN, int STAGES_>
+void launch_tc_stream(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int tiles_m, int tiles_n, int nphase, cudaStream_t s) {
+    constexpr int STAGES = op_stages(OP, STAGES_);
+    constexpr int STAGE_BYTES = (128 + BN) * op_row_bytes(OP);
+    constexpr size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 33 * 4 + 4 * BN * 8;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_stream_kernel<BN, STAGES_, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        THA4_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, conv_tc_stream_kernel<BN, STAGES_, OP>, TC_THREADS, smem));
+        ctas_per_sm = std::max(1, std::min(ctas_per_sm, 512 / (2 * BN)));      // TMEM: 2 x BN columns per CTA
+    }
+    const int slots = 148 * ctas_per_sm;
+    const int gx = std::max(1, std::min(tiles_m, slots / std::max(1, tiles_n * nphase)));
+    launch_pdl(conv_tc_stream_kernel<BN, STAGES_, OP>, dim3(gx, tiles_n, nphase), dim3(TC_THREADS), smem, s, 1, ma, mb, p);
+    THA4_LAUNCH_CHECK();
+}
+
+template <int OP>
+void launch_stream_variants(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int tiles_m, int tiles_n, int nphase, cudaStream_t s) {
+    if (bn == 128) launch_tc_stream<OP, 128, 2>(ma, mb, p, tiles_m, tiles_n, nphase, s);
+    else if (bn == 64) launch_tc_stream<OP, 64, 2>(ma, mb, p, tiles_m, tiles_n, nphase, s);
+    else launch_tc_stream<OP, 32, 2>(ma, mb, p, tiles_m, tiles_n, nphase, s);
+}
+
 template <int OP, int BN, int STAGES>
 void launch_tc_cluster(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
     if (cs == 8) launch_tc<OP, BN, STAGES, 8>(ma, mb, p, grid, s);
@@ -539,6 +759,8 @@ namespace {
 struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW, mt; bool cluster; };
 bool g_use_mt2 = false;    // measured: no gain (the narrow layers are bound by the MMA's own shared-memory operand reads, not by L2)
 bool g_use_cluster = true;
+bool g_use_stream = false; // persistent streaming kernel for multi-wave unsplit launches (option "stream_conv"): validated, measured slower
+                           // (its dedicated epilogue scratch halves the TMA ring; 224 vs 320 frames/s at B=16), kept opt-in
 TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
     TcPlan pl;
     pl.MH = a.out.H / cw.out_mul; pl.MW = a.out.W / cw.out_mul;
@@ -593,6 +815,7 @@ size_t conv_workspace_floats(const ConvWeights& cw, const ConvArgs& a) {
 
 void conv_tc_enable_cluster(bool on) { g_use_cluster = on; }
 void conv_tc_enable_mt2(bool on) { g_use_mt2 = on; }
+void conv_tc_enable_stream(bool on) { g_use_stream = on; }
 
 bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
     const TcPlan pl = tc_plan(cw, a);
@@ -623,6 +846,7 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     THA4_REQUIRE(p.MH == a.in.H && p.MW == a.in.W, "conv_tc: geometry");
     p.tiles_x = pl.tiles_x; p.tiles_y = pl.tiles_y;
     const int op = op_for(cw, a);
+    p.pre_b = cw.dynamic ? 0 : 1;            // static (loaded once) weights only
     p.ntaps = cw.ntaps; p.cpt = cw.cin_pad / op_kch(op);
     if (op != OP_TF32 && !cw.w16) {          // first use with f16 activations: make the f16 copy of the packed weights
         const long nw = (long)conv_packed_floats(cw);
@@ -631,6 +855,7 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
         pack_half_kernel<<<(int)std::min<long>((nw + 255) / 256, 1184), 256, 0, s>>>(cw.w, h, nw);
         THA4_LAUNCH_CHECK();
         cw.w16 = h;
+        p.pre_b = 0;                          // written by the kernel just launched: order through the dependency wait
     }
     for (int ph = 0; ph < CONV_MAX_PHASES; ++ph) {
         p.ph_oy[ph] = cw.ph_oy[ph]; p.ph_ox[ph] = cw.ph_ox[ph];
@@ -666,6 +891,13 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
         else if (bn == 128) launch_tc<OP_TF32, 128, 4, 1, 2>(ma, mb, p, grid, s);
         else if (bn == 64) launch_tc<OP_TF32, 64, 2, 1, 2>(ma, mb, p, grid, s);
         else launch_tc<OP_TF32, 32, 2, 1, 2>(ma, mb, p, grid, s);
+        return;
+    }
+    if (g_use_stream && !pl.cluster && ksplit == 1 && bn <= 128 && total_ctas > 3 * 148) {
+        // many small tiles: persistent CTAs with the TMA ring and a double-buffered accumulator running across tiles
+        if (op == OP_TF32) launch_stream_variants<OP_TF32>(bn, ma, mb, p, tiles_m, tiles_n, cw.nphase, s);
+        else if (op == OP_F16) launch_stream_variants<OP_F16>(bn, ma, mb, p, tiles_m, tiles_n, cw.nphase, s);
+        else launch_stream_variants<OP_F16N>(bn, ma, mb, p, tiles_m, tiles_n, cw.nphase, s);
         return;
     }
     if (op == OP_TF32) launch_variants<OP_TF32>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);

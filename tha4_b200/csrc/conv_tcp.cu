@@ -39,9 +39,6 @@ struct TcpParams {
     signed char ph_oy[CONV_MAX_PHASES], ph_ox[CONV_MAX_PHASES];
 };
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar) : "memory");
-}
 
 struct Work { int n, ty, tx, nt, phase; };
 __device__ __forceinline__ Work decode(long w, const TcpParams& p) {

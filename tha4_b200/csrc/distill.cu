@@ -335,6 +335,7 @@ void dense_gemm(Runtime& rt, const float* W, int nreal, int kreal, bool transpos
     conv_describe(cw, CONV_1x1, x.C, y.C);
     cw.w = rt.scratch->alloc(conv_packed_floats(cw));
     cw.tf32_rounded = true;
+    cw.dynamic = true;
     pack_dense_kernel<<<64, 256, 0, rt.stream>>>(W, nreal, kreal, transpose ? 1 : 0, cw.w, cw.cout_pad, cw.cin_pad);
     THA4_LAUNCH_CHECK();
     cw.bias = const_cast<float*>(bias_padded);
