@@ -235,3 +235,38 @@ def test_student_modules_standalone(student_sds):
         b = body(img.to(DEV), pose.to(DEV))
         br = O.siren_morpher_03(student_sds['body_morpher'], img, pose)
         _check_student('siren body standalone', b + [f], br + [fr])
+
+
+def test_default_mode_error_class_vs_torch_cuda_tf32(teacher_poser, teacher_sds):
+    """Context for the default-mode tolerance: the reference's own CUDA path (cuDNN convolutions with TF32 allowed, PyTorch's
+    default) deviates from the CPU fp32 result by a comparable amount on these random-init (chaotic) networks.  Both
+    deviations are printed; ours must stay within 3x of torch-CUDA's (or under the calibrated 1.2e-2)."""
+    _set_strict(teacher_poser, 0)
+    img = synth.synthetic_image(0, 1)[0]
+    sds_dev = {k: {kk: vv.to(DEV) for kk, vv in v.items()} for k, v in teacher_sds.items()}
+    orig_grid, orig_t0 = O.base_grid, O._timestep_embedding_zero
+    O.base_grid = lambda n, h, w, dtype=torch.float32: orig_grid(n, h, w, dtype).to(DEV)
+    O._timestep_embedding_zero = lambda n, c: orig_t0(n, c).to(DEV)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        worst_ours, worst_torch = 0.0, 0.0
+        for seed in (99, 7):
+            pose = synth.random_poses(1, seed=seed)[0]
+            with torch.no_grad():
+                ours = teacher_poser.get_posing_outputs(img.to(DEV), pose.to(DEV))
+                tcu = O.mode_07_outputs(sds_dev, img.to(DEV).unsqueeze(0), pose.to(DEV).unsqueeze(0))
+            O.base_grid, O._timestep_embedding_zero = orig_grid, orig_t0
+            with torch.no_grad():
+                refs = O.mode_07_outputs(teacher_sds, img, pose)
+            O.base_grid = lambda n, h, w, dtype=torch.float32: orig_grid(n, h, w, dtype).to(DEV)
+            O._timestep_embedding_zero = lambda n, c: orig_t0(n, c).to(DEV)
+            e_ours = max((a.cpu() - b).abs().mean().item() for a, b in zip(ours, refs))
+            e_torch = max((a.cpu() - b).abs().mean().item() for a, b in zip(tcu, refs))
+            print('\nseed %d: worst mean-abs deviation from CPU fp32: tha4_b200 default %.3e | torch CUDA (TF32 convs) %.3e' % (seed, e_ours, e_torch))
+            worst_ours, worst_torch = max(worst_ours, e_ours), max(worst_torch, e_torch)
+        assert worst_ours <= max(3.0 * worst_torch, 1.2e-2), (worst_ours, worst_torch)
+    finally:
+        O.base_grid, O._timestep_embedding_zero = orig_grid, orig_t0
+        torch.backends.cudnn.allow_tf32 = prev
+        _set_strict(teacher_poser, 1)

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const float* __restr
     const int by0 = blockIdx.y * TILE_H, bx0 = blockIdx.x * TILE;
 
     constexpr int WQ = NT * 2;                // float4 chunks of head weights actually used (8 or 16 columns; 12..15 are zero)
+#pragma unroll 4
     for (int i = tid; i < 9 * C * WQ; i += TAIL_THREADS) {
         const int row = i / WQ, part = i - row * WQ;
         if (4 * part >= CO_PAD) { *reinterpret_cast<float4*>(wsm + row * WPITCH + 4 * part) = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
@@ -70,20 +71,38 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const float* __restr
         *reinterpret_cast<float4*>(wsm + row * WPITCH + 4 * part) = wv;
     }
     const int cq = C >> 2;
-    for (int i = tid; i < HALO_H * HALO * cq; i += TAIL_THREADS) {
-        const int q = i % cq, hp = i / cq;
-        const int hy = hp / HALO, hx = hp - hy * HALO;
-        const int gy = by0 + hy - 1, gx = bx0 + hx - 1;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < S && gx >= 0 && gx < S) {
-            v = *reinterpret_cast<const float4*>(feat + (((long)n * S + gy) * S + gx) * ld + 4 * q);
-            const float4 c0 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2);
-            const float4 c1 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q) * 2 + 4);
-            v.x = act_apply(v.x * c0.x + c0.y, act); v.y = act_apply(v.y * c0.z + c0.w, act);
-            v.z = act_apply(v.z * c1.x + c1.y, act); v.w = act_apply(v.w * c1.z + c1.w, act);
+    // halo staging, 4 independent 16-byte loads in flight per thread (a single load per loop trip left the DRAM latency
+    // fully exposed: 23 serial round trips per thread at C = 64)
+    constexpr int SU = 4;
+    const int items = HALO_H * HALO * cq;
+    for (int i0 = tid; i0 < items; i0 += SU * TAIL_THREADS) {
+        float4 v[SU];
+        int hp[SU], q[SU];
+        bool in[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int i = i0 + u * TAIL_THREADS;
+            const int ii = i < items ? i : 0;
+            q[u] = ii % cq; hp[u] = ii / cq;
+            const int hy = hp[u] / HALO, hx = hp[u] - hy * HALO;
+            const int gy = by0 + hy - 1, gx = bx0 + hx - 1;
+            in[u] = i < items && gy >= 0 && gy < S && gx >= 0 && gx < S;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in[u]) v[u] = __ldg(reinterpret_cast<const float4*>(feat + (((long)n * S + gy) * S + gx) * ld + 4 * q[u]));
         }
-        if (!STRICT) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-        *reinterpret_cast<float4*>(fsm + hp * CP + 4 * q) = v;
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            if (i0 + u * TAIL_THREADS >= items) break;
+            float4 w = v[u];
+            if (in[u]) {
+                const float4 c0 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q[u]) * 2);
+                const float4 c1 = *reinterpret_cast<const float4*>(coef + ((long)n * C + 4 * q[u]) * 2 + 4);
+                w.x = act_apply(w.x * c0.x + c0.y, act); w.y = act_apply(w.y * c0.z + c0.w, act);
+                w.z = act_apply(w.z * c1.x + c1.y, act); w.w = act_apply(w.w * c1.z + c1.w, act);
+            }
+            if (!STRICT) { w.x = round_tf32(w.x); w.y = round_tf32(w.y); w.z = round_tf32(w.z); w.w = round_tf32(w.w); }
+            *reinterpret_cast<float4*>(fsm + hp[u] * CP + 4 * q[u]) = w;
+        }
     }
     __syncthreads();
 
