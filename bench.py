@@ -170,7 +170,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': 1.0 / spf, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_torch_cuda(args, rank):
@@ -207,14 +207,36 @@ def run_torch_cuda(args, rank):
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(json.dumps({'impl': 'torch_cuda_eager', 'metric': '512x512 RGBA frames/sec', 'value': args.steps * B / (ms / 1000.0),
+    emit({'impl': 'torch_cuda_eager', 'metric': '512x512 RGBA frames/sec', 'value': args.steps * B / (ms / 1000.0),
                       'unit': 'frames/s', 'ms_per_step': ms / args.steps, 'steps': args.steps, 'warmup': args.warmup,
                       'config': {'workload': wl['desc']},
-                      'note': 'PyTorch eager on the same GPU running the oracle port (the ops the reference dispatches); context only'}),
-          flush=True)
+          'note': 'PyTorch eager on the same GPU running the oracle port (the ops the reference dispatches); context only'})
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner there) share fd 1, so
+    everything else is sent to stderr and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
@@ -330,14 +352,16 @@ def main():
 
         # ---------------- profiled pass for the roofline objects (rank 0) ----------------
         prof = {}
-        if rank == 0:
-            ctx.set_option('profile', 2)
+        if rank == 0 or distiller is not None:    # a distillation step contains the gradient all-reduce: every rank takes part
+            if rank == 0:
+                ctx.set_option('profile', 2)
             for i in range(args.steps):
                 step_resident(args.warmup + i)
             torch.cuda.synchronize()
-            for cat in ('conv', 'norm', 'tail', 'attn', 'siren'):
-                prof[cat] = {w: ctx.counter('prof_%s_%s' % (w, cat)) for w in ('us', 'launches', 'flops', 'bytes')}
-            ctx.set_option('profile', 0)
+            if rank == 0:
+                for cat in ('conv', 'norm', 'tail', 'attn', 'siren'):
+                    prof[cat] = {w: ctx.counter('prof_%s_%s' % (w, cat)) for w in ('us', 'launches', 'flops', 'bytes')}
+                ctx.set_option('profile', 0)
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=device)
@@ -405,7 +429,7 @@ def main():
         line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                                 'sample': '%d frames of the same workload in %.1f s (PyTorch-CPU port of the reference path in oracle/, '
                                           '%d of %d host threads; /root/reference itself is pure Python and does not exist on the GPU box)' % (nfr, dt, threads, os.cpu_count() or 1)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
