@@ -34,6 +34,8 @@ import torch.distributed as dist  # noqa: E402
 
 WORKLOADS = {
     'teacher_b1': dict(mode='mode_07', batch=1, desc='full poser mode_07 forward, batch=1, lambda_00 image, random poses, eyebrow cache hot'),
+    'teacher_b1_nocache': dict(mode='mode_07', batch=1, nocache=True, desc='full poser mode_07 forward, batch=1, the image changes every frame (eyebrow-decomposer cache always misses: 645.9 GFLOP/frame)'),
+    'pose_sweep_512': dict(mode='mode_07', total=512, desc='BASELINE configs[3]: 512-pose sweep of the lambda_00 image, contiguous shards of 512/N frames per GPU (micro-batches of 8), no collective'),
     'teacher_b16': dict(mode='mode_07', batch=16, desc='full poser mode_07 forward, batch=16 pose sweep on the lambda_00 image'),
     'student_b64': dict(mode='mode_14', batch=64, desc='distilled student mode_14 forward, batch=64, lambda_00 weights, fp16 tensor-core products'),
     'distill_b1': dict(mode='distill', batch=1, desc='body-morpher distill step: teacher mode_07 fwd + student fwd/bwd + gradient all-reduce + Adam, per-GPU batch 1 (reference-faithful: total batch <= 8)'),
@@ -161,9 +163,9 @@ def run_reference(args, rank, world):
     spf = sum(times) / len(times)
     line = {
         'impl': 'reference', 'metric': '512x512 RGBA frames/sec', 'value': 1.0 / spf, 'unit': 'frames/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * spf * wl['batch'], 'higher_is_better': True,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * spf * wl.get('batch', wl.get('total', 1)), 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': wl['desc'], 'batch': wl['batch']},
+        'config': {'workload': wl['desc'], 'batch': wl.get('batch', wl.get('total', 1))},
         'cpu_baseline': {'value': 1.0 / spf, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                          'sample': '%d timed steps (of %d requested) of %d frame(s) each of the same workload (PyTorch-CPU port of the reference path, '
                                    '%d of %d host threads)' % (len(times), args.steps, per_step_frames, threads, os.cpu_count() or 1)},
@@ -185,7 +187,7 @@ def run_torch_cuda(args, rank):
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
     sds, _ = load_state_dicts(mode)
     sds = {k: {kk: vv.to(dev) for kk, vv in v.items()} for k, v in sds.items()}
-    B = wl['batch']
+    B = wl.get('batch', 16)
     image = load_inputs(wl).to(dev).unsqueeze(0).expand(B, -1, -1, -1).contiguous()
     poses = synthetic.random_poses((args.warmup + args.steps) * B, seed=1234).to(dev)
     fn = getattr(tha4_oracle, mode + '_outputs')
@@ -260,7 +262,8 @@ def main():
         return
 
     wl = WORKLOADS[args.workload]
-    B = wl['batch']
+    B = wl['batch'] if 'batch' in wl else max(1, wl['total'] // world)     # fixed total: strong scaling
+    strong = 'total' in wl
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
@@ -293,6 +296,10 @@ def main():
 
     img_dev = image.unsqueeze(0).expand(B, -1, -1, -1).contiguous().to(device)
     poses_dev = poses.to(device)
+    img_alt = None
+    if wl.get('nocache'):          # a second image that differs in one pixel value: the cache comparison fails every frame
+        img_alt = img_dev.clone()
+        img_alt[:, 0, 0, 0] += 1.0 / 512.0
 
     def barrier():
         if world > 1:
@@ -302,7 +309,7 @@ def main():
     def step_resident(i):
         if distiller is not None:
             return distiller.train_step(img_dev, poses_dev[i * B:(i + 1) * B], DISTILL_W, DISTILL_LR, want_losses=False)
-        return poser.get_posing_outputs(img_dev, poses_dev[i * B:(i + 1) * B])
+        return poser.get_posing_outputs(img_alt if (img_alt is not None and (i & 1)) else img_dev, poses_dev[i * B:(i + 1) * B])
 
     # ---------------- device-resident timing ----------------
     with torch.no_grad():
@@ -331,6 +338,8 @@ def main():
 
         def step_e2e(i):
             img_in.copy_(img_host, non_blocking=True)
+            if img_alt is not None and (i & 1):
+                img_in[:, 0, 0, 0] += 1.0 / 512.0
             pose_in.copy_(poses_host[i * B:(i + 1) * B], non_blocking=True)
             if distiller is not None:        # result of a training step = its loss terms, read back on the host
                 distiller.train_step(img_in, pose_in, DISTILL_W, DISTILL_LR, want_losses=True)
@@ -383,7 +392,7 @@ def main():
     line = {
         'metric': 'distillation examples/sec' if distill else '512x512 RGBA frames/sec', 'value': value,
         'unit': 'examples/s' if distill else 'frames/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
         'dtype': 'f16/tf32 operands (10-bit mantissa), f32 accumulate, f32 storage outside conv operands' if wl['mode'] in ('mode_07', 'distill') and not args.strict else
                  ('f32 (3xTF32)' if wl['mode'] == 'mode_07' else 'f16 products, f32 accumulate'),
         'data': 'synthetic poses; ' + weights_desc + '; lambda_00.png character image',
@@ -395,7 +404,7 @@ def main():
         'clocks': clocks,
     }
     if wl['mode'] == 'mode_07':
-        line['teacher_tflops_effective'] = TEACHER_GFLOP_PER_FRAME * value / world / 1000.0
+        line['teacher_tflops_effective'] = (645.9 if wl.get('nocache') else TEACHER_GFLOP_PER_FRAME) * value / world / 1000.0
     # roofline objects from the profiled pass
     if prof.get('conv', {}).get('us', 0) > 0:
         c = prof['conv']
