@@ -6,21 +6,23 @@
 namespace tha4 {
 
 // ------------------------------------------------------------------------------------------------ Pool
-Pool::~Pool() { for (auto& b : blocks_) cudaFree(b.p); }
+Pool::~Pool() { for (void* p : all_) cudaFree(p); }
 
 float* Pool::alloc(size_t nfloats) {
     size_t bytes = ((nfloats * sizeof(float) + 255) / 256) * 256;
     if (bytes == 0) bytes = 256;
-    for (auto& b : blocks_)
-        if (!b.used && b.bytes == bytes) { b.used = true; return reinterpret_cast<float*>(b.p); }
+    Bucket& bk = buckets_[bytes];                 // blocks of this exact size, handed out in creation order
+    if (bk.next < bk.blocks.size()) return reinterpret_cast<float*>(bk.blocks[bk.next++]);
     void* p = nullptr;
     THA4_CUDA_CHECK(cudaMalloc(&p, bytes));
-    blocks_.push_back({p, bytes, true});
+    bk.blocks.push_back(p);
+    bk.next = bk.blocks.size();
+    all_.push_back(p);
     total_ += bytes;
     return reinterpret_cast<float*>(p);
 }
 
-void Pool::reset() { for (auto& b : blocks_) b.used = false; }
+void Pool::reset() { for (auto& kv : buckets_) kv.second.next = 0; }
 
 long TensorRef::numel() const { long n = 1; for (long d : shape) n *= d; return n; }
 

@@ -5,6 +5,7 @@
 #include "conv.cuh"
 #include "ops.cuh"
 #include <map>
+#include <unordered_map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -21,8 +22,9 @@ public:
     void reset();          // every block becomes reusable (stream order makes reuse safe: one stream per ctx call)
     size_t bytes() const { return total_; }
 private:
-    struct Block { void* p; size_t bytes; bool used; };
-    std::vector<Block> blocks_;
+    struct Bucket { std::vector<void*> blocks; size_t next = 0; };
+    std::unordered_map<size_t, Bucket> buckets_;   // O(1) per request: a pass makes ~600 of them between kernel launches
+    std::vector<void*> all_;
     size_t total_ = 0;
 };
 
