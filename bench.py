@@ -35,7 +35,7 @@ import torch.distributed as dist  # noqa: E402
 WORKLOADS = {
     'teacher_b1': dict(mode='mode_07', batch=1, desc='full poser mode_07 forward, batch=1, lambda_00 image, random poses, eyebrow cache hot'),
     'teacher_b1_nocache': dict(mode='mode_07', batch=1, nocache=True, desc='full poser mode_07 forward, batch=1, the image changes every frame (eyebrow-decomposer cache always misses: 645.9 GFLOP/frame)'),
-    'pose_sweep_512': dict(mode='mode_07', total=512, desc='BASELINE configs[3]: 512-pose sweep of the lambda_00 image, contiguous shards of 512/N frames per GPU (micro-batches of 8), no collective'),
+    'pose_sweep_512': dict(mode='mode_07', total=512, desc='BASELINE configs[3]: 512-pose sweep of the lambda_00 image, contiguous shards of 512/N frames per GPU (micro-batches of 32), no collective'),
     'teacher_b16': dict(mode='mode_07', batch=16, desc='full poser mode_07 forward, batch=16 pose sweep on the lambda_00 image'),
     'student_b64': dict(mode='mode_14', batch=64, desc='distilled student mode_14 forward, batch=64, lambda_00 weights, fp16 tensor-core products'),
     'distill_b1': dict(mode='distill', batch=1, desc='body-morpher distill step: teacher mode_07 fwd + student fwd/bwd + gradient all-reduce + Adam, per-GPU batch 1 (reference-faithful: total batch <= 8)'),
@@ -282,7 +282,6 @@ def main():
     poser.get_modules()
     ctx = poser.get_context()
     ctx.set_option('strict', args.strict)
-    ctx.set_option('microbatch', 8)
     for kv in args.option:
         k, v = kv.split('=')
         ctx.set_option(k, int(v))
@@ -336,15 +335,21 @@ def main():
         img_in = torch.empty_like(img_dev)
         pose_in = torch.empty((B, 45), device=device)
 
+        img_in2 = torch.empty_like(img_dev) if img_alt is not None else None
+
         def step_e2e(i):
-            img_in.copy_(img_host, non_blocking=True)
-            if img_alt is not None and (i & 1):
-                img_in[:, 0, 0, 0] += 1.0 / 512.0
+            img_cur = img_in
+            if img_alt is not None and (i & 1):      # a different tensor object with different content: the cache must miss
+                img_cur = img_in2
+                img_cur.copy_(img_host, non_blocking=True)
+                img_cur[:, 0, 0, 0] += 1.0 / 512.0
+            else:
+                img_cur.copy_(img_host, non_blocking=True)
             pose_in.copy_(poses_host[i * B:(i + 1) * B], non_blocking=True)
             if distiller is not None:        # result of a training step = its loss terms, read back on the host
-                distiller.train_step(img_in, pose_in, DISTILL_W, DISTILL_LR, want_losses=True)
+                distiller.train_step(img_cur, pose_in, DISTILL_W, DISTILL_LR, want_losses=True)
                 return
-            out = poser.pose(img_in, pose_in)
+            out = poser.pose(img_cur, pose_in)
             out_host.copy_(out, non_blocking=True)
             torch.cuda.current_stream().synchronize()      # the caller consumes the frame on the host
 
