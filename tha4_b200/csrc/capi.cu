@@ -9,7 +9,17 @@
 #include <map>
 #include <tuple>
 
-namespace tha4 { std::atomic<long> g_kernel_launches{0}; bool g_use_pdl = true; }
+namespace tha4 {
+std::atomic<long> g_kernel_launches{0};
+bool g_use_pdl = true;
+thread_local AllocSink* g_alloc_sink = nullptr;
+void* tracked_malloc(size_t bytes) {
+    void* p = nullptr;
+    THA4_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+    if (g_alloc_sink) g_alloc_sink->ptrs.push_back(p);
+    return p;
+}
+}
 
 using namespace tha4;
 
@@ -577,6 +587,7 @@ int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, cons
         if (wsf) { a.ws = ctx->scratch.alloc(wsf); a.ws_floats = wsf; }
         conv_forward(cw, a, s);
         nhwc_to_nchw(yo, y, s);
+        if (cw.w16) { THA4_CUDA_CHECK(cudaStreamSynchronize(s)); cudaFree(cw.w16); cw.w16 = nullptr; }   // made on first use, owned by this call
     });
 }
 

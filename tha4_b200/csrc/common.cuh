@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <atomic>
 #include <algorithm>
+#include <vector>
 
 namespace tha4 {
 
@@ -106,6 +107,23 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
         throw CudaError(std::string("cudaLaunchKernelEx failed: ") + cudaGetErrorString(e));
 }
 #endif
+
+// Device allocations made while a network loads its weights are recorded in the network's AllocSink and released with
+// it (weights are re-uploaded when the precision mode changes and after every distillation step).
+struct AllocSink {
+    std::vector<void*> ptrs;
+    AllocSink() = default;
+    AllocSink(const AllocSink&) = delete;
+    AllocSink& operator=(const AllocSink&) = delete;
+    ~AllocSink() { for (void* p : ptrs) cudaFree(p); }
+};
+extern thread_local AllocSink* g_alloc_sink;
+struct SinkScope {
+    AllocSink* prev;
+    explicit SinkScope(AllocSink* s) : prev(g_alloc_sink) { g_alloc_sink = s; }
+    ~SinkScope() { g_alloc_sink = prev; }
+};
+void* tracked_malloc(size_t bytes);      // cudaMalloc, recorded in the active sink (if any)
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }

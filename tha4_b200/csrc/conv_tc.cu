@@ -813,6 +813,15 @@ size_t conv_workspace_floats(const ConvWeights& cw, const ConvArgs& a) {
     return (size_t)cw.nphase * pl.ksplit * pl.tiles_m * 128 * cw.cout_pad;
 }
 
+void conv_make_half(const ConvWeights& cw, cudaStream_t s) {
+    if (cw.w16 || !cw.w) return;
+    const long nw = (long)conv_packed_floats(cw);
+    __half* h = reinterpret_cast<__half*>(tracked_malloc(nw * sizeof(__half)));
+    pack_half_kernel<<<(int)std::min<long>((nw + 255) / 256, 1184), 256, 0, s>>>(cw.w, h, nw);
+    THA4_LAUNCH_CHECK();
+    cw.w16 = h;
+}
+
 void conv_tc_enable_cluster(bool on) { g_use_cluster = on; }
 void conv_tc_enable_mt2(bool on) { g_use_mt2 = on; }
 void conv_tc_enable_stream(bool on) { g_use_stream = on; }
@@ -848,13 +857,8 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     const int op = op_for(cw, a);
     p.pre_b = cw.dynamic ? 0 : 1;            // static (loaded once) weights only
     p.ntaps = cw.ntaps; p.cpt = cw.cin_pad / op_kch(op);
-    if (op != OP_TF32 && !cw.w16) {          // first use with f16 activations: make the f16 copy of the packed weights
-        const long nw = (long)conv_packed_floats(cw);
-        __half* h = nullptr;
-        THA4_CUDA_CHECK(cudaMalloc(&h, nw * sizeof(__half)));
-        pack_half_kernel<<<(int)std::min<long>((nw + 255) / 256, 1184), 256, 0, s>>>(cw.w, h, nw);
-        THA4_LAUNCH_CHECK();
-        cw.w16 = h;
+    if (op != OP_TF32 && !cw.w16) {          // first use with f16 activations and no copy made at load time
+        conv_make_half(cw, s);
         p.pre_b = 0;                          // written by the kernel just launched: order through the dependency wait
     }
     for (int ph = 0; ph < CONV_MAX_PHASES; ++ph) {

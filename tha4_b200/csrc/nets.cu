@@ -43,7 +43,8 @@ const TensorRef& sd_get(const StateDict& sd, const std::string& key) {
     return it->second;
 }
 
-float* dev_alloc(size_t n) {
+float* dev_alloc(size_t n) { return reinterpret_cast<float*>(tracked_malloc(std::max<size_t>(n, 1) * sizeof(float))); }   // owned by the loading net
+float* dev_alloc_tmp(size_t n) {       // freed by the caller
     float* p = nullptr;
     THA4_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(float)));
     return p;
@@ -80,6 +81,7 @@ ConvWeights load_conv(const StateDict& sd, const std::string& prefix, ConvKind k
     THA4_CUDA_CHECK(cudaMemsetAsync(cw.w, 0, conv_packed_floats(cw) * sizeof(float), s));
     conv_pack(cw, kind, w.p, cin, 0, s);
     cw.tf32_rounded = conv_pack_rounding();
+    if (cw.tf32_rounded) conv_make_half(cw, s);      // default mode: most convs read f16 activations (owned by the loading net)
     if (bias) cw.bias = dev_clone(sd_get(sd, prefix + ".bias"), s);
     return cw;
 }
@@ -177,6 +179,7 @@ EncDecNet::EncDecNet(TailKind kind, int size, int in_ch, int pose_ch)
     : kind_(kind), S_(size), in_ch_(in_ch), pose_ch_(pose_ch), pose_pad_(round_up(pose_ch, 8)) {}
 
 void EncDecNet::load(const StateDict& sd, cudaStream_t s) {
+    SinkScope own(&owned_);
     const std::string p = (kind_ == TAIL_FACE) ? "" : "body.";
     down_[0] = load_conv(sd, p + "downsample_blocks.0.0", CONV_3x3, false, s);
     down_n_[0] = load_norm(sd, p + "downsample_blocks.0.1", s);
@@ -305,6 +308,7 @@ AttnW load_attn(const StateDict& sd, const std::string& p, cudaStream_t s) {
 }  // namespace
 
 void UNetNet::load(const StateDict& sd, cudaStream_t s) {
+    SinkScope own(&owned_);
     const std::string p = "body.";
     std::vector<std::pair<ResBlockW*, std::string>> all_blocks;   // for FiLM batching
     // first conv (Upscaler02: first_conv(rest) + coarse_image_conv(cat(coarse_posed, warped, coarse_grid)) fused
@@ -370,10 +374,10 @@ void UNetNet::load(const StateDict& sd, cudaStream_t s) {
     // time embedding at t = 0 is a constant: cat(cos(0)..., sin(0)...) -> Linear -> SiLU -> Linear  (unet.py:365-376,443-447)
     std::vector<float> t0(mc_, 0.0f);
     for (int i = 0; i < mc_ / 2; ++i) t0[i] = 1.0f;
-    float* d_t0 = dev_alloc(mc_);
+    float* d_t0 = dev_alloc_tmp(mc_);
     THA4_CUDA_CHECK(cudaMemcpyAsync(d_t0, t0.data(), mc_ * sizeof(float), cudaMemcpyHostToDevice, s));
-    float* d_t1 = dev_alloc(256);
-    float* d_t2 = dev_alloc(256);
+    float* d_t1 = dev_alloc_tmp(256);
+    float* d_t2 = dev_alloc_tmp(256);
     linear_forward(d_t0, mc_, 1, mc_, sd_get(sd, p + "time_embed.1.weight").p, sd_get(sd, p + "time_embed.1.bias").p, 256, 0, d_t1, 256, s);
     linear_forward(d_t1, 256, 1, 256, sd_get(sd, p + "time_embed.3.weight").p, sd_get(sd, p + "time_embed.3.bias").p, 256, 1, d_t2, 256, s);
 

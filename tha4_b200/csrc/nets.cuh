@@ -62,6 +62,7 @@ public:
     int num_outputs() const { return kind_ == TAIL_DECOMPOSER ? 6 : 8; }
     bool loaded() const { return loaded_; }
 private:
+    AllocSink owned_;          // every device allocation made by load()
     TailKind kind_;
     int S_, in_ch_, pose_ch_, pose_pad_;
     bool loaded_ = false;
@@ -93,6 +94,7 @@ public:
     int size() const { return S_; }
     bool loaded() const { return loaded_; }
 private:
+    AllocSink owned_;          // every device allocation made by load()
     void res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode, const float* film1, const View& out);
     void attn_block(Runtime& rt, const AttnW& w, const View& x, const View& out);
     bool upscaler_;

@@ -416,10 +416,8 @@ __global__ void pack_vec_kernel(const float* __restrict__ b, int nreal, int NPAD
     if (i < NPAD) dst[i] = (i < nreal) ? scale * b[i] : 0.0f;
 }
 
-template <typename T> T* dmalloc(size_t n) {
-    T* p = nullptr;
-    THA4_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-    return p;
+template <typename T> T* dmalloc(size_t n) {      // owned by the loading net (AllocSink)
+    return reinterpret_cast<T*>(tracked_malloc(std::max<size_t>(n, 1) * sizeof(T)));
 }
 
 const TensorRef& get(const StateDict& sd, const std::string& k) {
@@ -479,6 +477,7 @@ template <typename K> static void set_smem(K kernel, size_t bytes) {
 
 // ------------------------------------------------------------------------------------------------ SirenFaceNet
 void SirenFaceNet::load(const StateDict& sd, cudaStream_t s) {
+    SinkScope own(&owned_);
     for (int i = 0; i < 8; ++i)
         layers_[i].load(sd, "siren.sine_layers." + std::to_string(i) + ".linear", i == 0 ? 0 : 128, i == 0 ? 39 : 0, 128, 128, 30.0f, s);
     head_.load(sd, "siren.last_linear", 128, 0, 128, 8, 1.0f, s);
@@ -504,6 +503,7 @@ void SirenFaceNet::forward(Runtime& rt, const float* pose, int pose_ld, int B, f
 
 // ------------------------------------------------------------------------------------------------ SirenBodyNet
 void SirenBodyNet::load(const StateDict& sd, cudaStream_t s) {
+    SinkScope own(&owned_);
     auto key = [](int i, int j) { return "siren_layers." + std::to_string(i) + "." + std::to_string(j) + ".linear"; };
     l_[0][0].load(sd, key(0, 0), 0, 45, 32, 384, 30.0f, s);
     l_[0][1].load(sd, key(0, 1), 360, 0, 384, 384, 30.0f, s);

@@ -20,6 +20,7 @@ public:
     void forward(Runtime& rt, const float* pose, int pose_ld, int B, float* out);
     bool loaded() const { return loaded_; }
 private:
+    AllocSink owned_;
     SirenLayer layers_[8], head_;
     bool loaded_ = false;
 };
@@ -31,6 +32,7 @@ public:
     void forward(Runtime& rt, const ImgView& image, const float* pose, int pose_ld, float* const* outputs);
     bool loaded() const { return loaded_; }
 private:
+    AllocSink owned_;
     SirenLayer l_[3][3], head_;
     bool loaded_ = false;
 };
