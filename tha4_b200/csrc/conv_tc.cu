@@ -33,7 +33,7 @@ struct TcParams {
     const float* bias;
     const float* res; int resH, resW, res_ld, res_mode;
     int N, MH, MW, tiles_x, tiles_y;
-    int ntaps, cpt, ksplit, out_mul;
+    int ntaps, cpt, ksplit, out_mul, in_mul;       // in_mul: input stride (2 for the 4x4 stride-2 conv: element-strided TMA boxes)
     int pre_b;                                     // weight tiles may be fetched before the programmatic-dependency wait
     float* ws; long ws_rows; int ws_ld;            // split-K partials: ws[z][tile*128 + row][cout_pad]
     double* stats; int stats_ld; int stats_rep; long stats_rep_stride;   // per-(n,c) sum / sum-of-squares of the output (optional)
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                         mbar_expect_tx(full, A_BYTES + B_BYTES);
                         tma_load_3d(smem_u32(smB + s * B_BYTES), &tmB, c0, n0, phase * p.ntaps + tap, full);
                     }
-                    tma_load_4d(smem_u32(smA + s * A_BYTES), &tmA, c0, x0 + p.dx[phase][tap], y0 + p.dy[phase][tap], n, full);
+                    tma_load_4d(smem_u32(smA + s * A_BYTES), &tmA, c0, x0 * p.in_mul + p.dx[phase][tap], y0 * p.in_mul + p.dy[phase][tap], n, full);
                 }
             }
         } else if (warp == 1) {
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_stream_kernel(const __grid
                     mbar_expect_tx(full, A_BYTES + B_BYTES);
                     const int tap = kt / p.cpt;
                     const int c0 = (kt - tap * p.cpt) * KCE;
-                    tma_load_4d(smem_u32(smA + s * A_BYTES), &tmA, c0, x0 + p.dx[phase][tap], y0 + p.dy[phase][tap], n, full);
+                    tma_load_4d(smem_u32(smA + s * A_BYTES), &tmA, c0, x0 * p.in_mul + p.dx[phase][tap], y0 * p.in_mul + p.dy[phase][tap], n, full);
                     tma_load_3d(smem_u32(smB + s * B_BYTES), &tmB, c0, n0, phase * p.ntaps + tap, full);
                 }
             }
@@ -631,8 +631,8 @@ EncodeTiledFn get_encode() {
 using MapKey = std::tuple<const void*, long, long, long, long, long, int>;
 std::map<MapKey, CUtensorMap> g_maps;
 
-const CUtensorMap& activation_map(const View& v, int mt, int op) {
-    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -(mt + 4 * op)};
+const CUtensorMap& activation_map(const View& v, int mt, int op, int stride) {
+    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -(mt + 4 * op + 16 * stride)};
     auto it = g_maps.find(key);
     if (it != g_maps.end()) return it->second;
     CUtensorMap m;
@@ -640,8 +640,9 @@ const CUtensorMap& activation_map(const View& v, int mt, int op) {
     const cuuint64_t eb = op == OP_TF32 ? 4 : 2;
     THA4_REQUIRE((op != OP_TF32) == (v.f16 != 0), "conv_tc: operand format does not match the activation view");
     cuuint64_t strides[3] = {(cuuint64_t)v.ld * eb, (cuuint64_t)v.W * v.ld * eb, (cuuint64_t)v.H * v.W * v.ld * eb};
-    cuuint32_t box[4] = {(cuuint32_t)op_kch(op), TILE_W, (cuuint32_t)(TILE_H * mt), 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // stride 2: the box spans 2x the pixels and is traversed with element stride 2, so it still delivers 16 x 8 pixels
+    cuuint32_t box[4] = {(cuuint32_t)op_kch(op), (cuuint32_t)(TILE_W * stride), (cuuint32_t)(TILE_H * mt * stride), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = get_encode()(&m, op == OP_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, v.p, dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, op == OP_F16N ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -759,6 +760,7 @@ namespace {
 struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW, mt; bool cluster; };
 bool g_use_mt2 = false;    // measured: no gain (the narrow layers are bound by the MMA's own shared-memory operand reads, not by L2)
 bool g_use_cluster = true;
+bool g_use_s2 = true;      // 4x4 stride-2 convs through element-strided TMA boxes (option "tc_stride2")
 bool g_use_stream = false; // persistent streaming kernel for multi-wave unsplit launches (option "stream_conv"): validated, measured slower
                            // (its dedicated epilogue scratch halves the TMA ring; 224 vs 320 frames/s at B=16), kept opt-in
 TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
@@ -825,6 +827,7 @@ void conv_make_half(const ConvWeights& cw, cudaStream_t s) {
 void conv_tc_enable_cluster(bool on) { g_use_cluster = on; }
 void conv_tc_enable_mt2(bool on) { g_use_mt2 = on; }
 void conv_tc_enable_stream(bool on) { g_use_stream = on; }
+void conv_tc_enable_stride2(bool on) { g_use_s2 = on; }
 
 bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
     const TcPlan pl = tc_plan(cw, a);
@@ -833,7 +836,8 @@ bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
 }
 
 bool conv_tc_supported(const ConvWeights& cw, const ConvArgs& a) {
-    if (a.in_up || cw.stride != 1 || a.strict) return false;
+    if (a.in_up || a.strict) return false;
+    if (cw.stride != 1 && !(g_use_s2 && cw.stride == 2 && cw.nphase == 1 && a.in.H % 2 == 0 && a.in.W % 2 == 0)) return false;
     if (a.in.ld % (a.in.f16 ? 8 : 4) != 0 || (((uintptr_t)a.in.p) & 15) != 0) return false;
     if (a.out.ld % 4 != 0 || (((uintptr_t)a.out.p) & 15) != 0) return false;
     if (cw.cout_pad % 32 != 0) return false;
@@ -852,7 +856,8 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     p.out_mul = cw.out_mul;
     const TcPlan pl = tc_plan(cw, a);
     p.MH = pl.MH; p.MW = pl.MW;
-    THA4_REQUIRE(p.MH == a.in.H && p.MW == a.in.W, "conv_tc: geometry");
+    p.in_mul = cw.stride;
+    THA4_REQUIRE(p.MH * cw.stride == a.in.H && p.MW * cw.stride == a.in.W, "conv_tc: geometry");
     p.tiles_x = pl.tiles_x; p.tiles_y = pl.tiles_y;
     const int op = op_for(cw, a);
     p.pre_b = cw.dynamic ? 0 : 1;            // static (loaded once) weights only
@@ -877,7 +882,7 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
     if (ksplit > 1 && !use_ws && !pl.cluster)
         THA4_CUDA_CHECK(cudaMemset2DAsync(a.out.p, (size_t)a.out.ld * sizeof(float), 0, (size_t)a.out.C * sizeof(float), a.out.pixels(), s));
-    const CUtensorMap& ma = activation_map(a.in, pl.mt, op);
+    const CUtensorMap& ma = activation_map(a.in, pl.mt, op, cw.stride);
     const CUtensorMap& mb = weight_map(cw, bn, op);
     dim3 grid(tiles_m, tiles_n, cw.nphase * ksplit);
     // Pipeline depth: grids that cannot even fill the GPU once (the B=1 bottleneck layers, which stream their weights
