@@ -45,13 +45,16 @@ int tha4_ctx_destroy(tha4_ctx* ctx);
 /* message of the last failure on this context (ctx == NULL: last failure of context creation) */
 const char* tha4_last_error(const tha4_ctx* ctx);
 
-/* options: "strict" (0: TF32 tensor-core products, the reference's own default on CUDA
- *                    1: 3xTF32 error-compensated products == fp32 convolution),
- *          "microbatch" (frames processed per pass of the teacher pipeline; bounds the workspace),
- *          "tcgen05" (1, default: stride-1 convs run on the tcgen05/TMA/TMEM kernel; 0: everything on mma.sync),
- *          "cluster_splitk" (1, default: K-split convs reduce through a thread-block cluster / DSMEM; 0: workspace + reduce kernel),
- *          "persistent_conv" (0 default; 1: GPU-filling convs run on the persistent halo-reuse tcgen05 kernel),
- *          "conv_mt2" (0 default; 1: GPU-filling convs use two 128-pixel tiles per CTA sharing each weight tile),
+/* options: "strict" (0: tensor-core products on 10-bit-mantissa operands (f16 / TF32), fp32 accumulate -- the class of the
+ *                       reference's own default on CUDA (cuDNN TF32 convs);
+ *                    1: 3xTF32 error-compensated products == fp32 convolution; weights are re-uploaded on change),
+ *          "microbatch" (frames processed per pass of the teacher pipeline, default 32; bounds the workspace),
+ *          developer switches, default = the measured-best setting:
+ *          "tcgen05" (1: convs on the tcgen05/TMA/TMEM kernel; 0: everything on mma.sync),
+ *          "half_operands" (1: tensors between a normalisation layer and a tcgen05 conv are f16),
+ *          "cluster_splitk" (1: K-split convs reduce through a thread-block cluster / DSMEM; 0: workspace + reduce kernel),
+ *          "pdl" (1: programmatic dependent launch on conv / norm kernels), "tc_stride2" (1: 4x4 stride-2 convs on tcgen05),
+ *          "stream_conv", "persistent_conv", "conv_mt2", "cuda_graphs" (0: validated alternatives that measured slower),
  *          "profile" (1: time every kernel class with CUDA events on the launching stream, 2: same + reset, 0: off) */
 int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value);
 /* counters: "kernel_launches" (kernels this library has launched so far), "workspace_bytes",

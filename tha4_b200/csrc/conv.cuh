@@ -1,4 +1,4 @@
-// Implicit-GEMM convolution on NHWC fp32 activations (declarations).
+// Implicit-GEMM convolution on NHWC activations (fp32, or f16 behind a normalisation layer) -- declarations.
 //
 // One kernel family covers every dense contraction of the teacher networks:
 //   3x3 s1 p1 (nn/conv.py:38-41, unet.py:133,142,454,529), 4x4 s2 p1 downsample (nn/conv.py:141-147),
@@ -14,7 +14,8 @@ constexpr int CONV_MAX_PHASES = 4;
 
 enum ResMode { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2, RES_DOWN2 = 3 };
 
-// Packed weights: [phase][tap][cout_pad][cin_pad] fp32, cin_pad % 32 == 0, cout_pad % 32 == 0, zero padded.
+// Packed weights: [phase][tap][cout_pad][cin_pad] fp32 (+ an f16 copy in the default mode), cin_pad % 32 == 0,
+// cout_pad % 32 == 0, zero padded.
 struct ConvWeights {
     float* w = nullptr;
     mutable __half* w16 = nullptr;   // same layout in f16, made on first use with f16 activations (conv_tc.cu)

@@ -1,16 +1,21 @@
-// Implicit-GEMM convolution on the 5th-generation tensor cores: TMA-staged operands, tcgen05.mma (kind::tf32)
-// with the accumulator in TMEM, warp-specialised producer / MMA-issuer / epilogue roles.
+// Implicit-GEMM convolution on the 5th-generation tensor cores: TMA-staged operands, tcgen05.mma (kind::f16 on f16
+// operands, kind::tf32 on fp32 operands) with the accumulator in TMEM, warp-specialised producer / MMA-issuer /
+// epilogue roles.
 //
-// GEMM view per CTA: D[128 pixels x BN couts] += A[128 x 32] * B[BN x 32]^T per k-block, k-blocks = taps x (Cin/32).
-//  * A (activations, NHWC fp32): one 4-D TMA box {32 ch, 16 w, 8 h, 1 n} per (tap, channel chunk).  The box lands in
-//    shared memory as 128 rows x 128 bytes with the 128-byte swizzle, which is exactly the canonical K-major UMMA
-//    layout; the tap offset (dy,dx) is just a shift of the box origin, and TMA's out-of-bounds zero fill *is* the
-//    convolution's zero padding (and the channel / edge-tile padding).  No im2col buffer, no index arithmetic.
-//  * B (weights, packed [phase*tap][cout_pad][cin_pad]): 3-D TMA box {32 cin, BN cout, 1 tap}, same layout.
+// GEMM view per CTA: D[128 pixels x BN couts] += A[128 x KC] * B[BN x KC]^T per k-block, k-blocks = taps x (Cin/KC),
+// KC = 64 f16 / 32 f16 / 32 fp32 channels (128- or 64-byte rows, see OP_* below).
+//  * A (activations, NHWC): one 4-D TMA box {KC ch, 16 w, 8 h, 1 n} per (tap, channel chunk).  The box lands in shared
+//    memory as 128 rows with the 128-byte (64-byte) swizzle, which is exactly the canonical K-major UMMA layout; the
+//    tap offset (dy,dx) is just a shift of the box origin, and TMA's out-of-bounds zero fill *is* the convolution's
+//    zero padding (and the channel / edge-tile padding).  No im2col buffer, no index arithmetic.  The 4x4 stride-2
+//    conv uses the same box with element strides {1,2,2,1} (a {KC, 32 w, 16 h} window sampled every other pixel).
+//  * B (weights, packed [phase*tap][cout_pad][cin_pad]): 3-D TMA box {KC cin, BN cout, 1 tap}, same layout.
 //  * D: fp32 accumulator in tensor memory (BN columns x 128 lanes), drained by 4 epilogue warps with tcgen05.ld,
-//    bias / residual fused, NHWC stores (atomic accumulation when K is split across CTAs).
-// Handles every stride-1 tap table of conv.cuh (3x3, 1x1, the four phases of the transposed 4x4); the stride-2 conv
-// and the nearest-upsample-fused gather stay on the mma.sync kernel in conv.cu.
+//    bias / residual fused, NHWC stores + per-channel statistics for the normalisation that follows.
+//  * K can be split over a thread-block cluster (partials meet in distributed shared memory), launches use
+//    programmatic dependent launch with the weight tiles fetched ahead of the dependency wait.
+// Handles every tap table of conv.cuh (3x3, 1x1, 4x4 stride 2, the four phases of the transposed 4x4 and of the
+// nearest-x2-upsample + 3x3); strict mode (3xTF32) and non-TMA-able views stay on the mma.sync kernel in conv.cu.
 #include "conv.cuh"
 #include "profiler.cuh"
 #include "tc_common.cuh"
