@@ -1,5 +1,8 @@
 """CPU oracle of the body-distillation step (autograd on the functional restatement)  --  TEST INFRASTRUCTURE.
-Follows siren_morpher_protocols_03.py:102-157,178-214 and siren_morpher_03_trainer.py:32-50 of the reference."""
+Follows siren_morpher_protocols_03.py:102-157,178-214 and siren_morpher_03_trainer.py:32-50 of the reference (body) and
+siren_face_morpher_protocols_00.py:48-105, siren_face_morpher_00_trainer.py:112-186 (face).  Pinned against the reference's
+own run_training_iteration: oracle/make_golden_distill.py -> tests/golden/distill_lambda00.npz, checked by
+tests/test_oracle_pinned.py (fixture everywhere, live reference in the build container)."""
 from typing import Dict, List, Sequence, Tuple
 
 import torch

@@ -137,3 +137,62 @@ def test_oracle_equals_live_reference(teacher_sds, student_sds):
             assert len(ref) == len(mine)
             for a, b in zip(ref, mine):
                 assert a.shape == b.shape and (a - b).abs().max().item() <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------ distillation steps (a16-a18)
+def _distill_oracle_results(lambda00_sds):
+    from oracle import distill_oracle, make_golden_distill as M
+    body_in, face_in = M.distill_inputs()
+    res = {}
+    sd = lambda00_sds['body_morpher']
+    losses, grad = distill_oracle.body_losses_and_grads(sd, body_in['image'], body_in['pose'], body_in['t_posed'], body_in['t_warped'],
+                                                        body_in['t_grid'], M.BODY_WEIGHTS)
+    p0 = torch.cat([v.reshape(-1) for v in sd.values()])
+    res['body'] = dict(weighted=[w * l for w, l in zip(M.BODY_WEIGHTS, losses)], grad=grad,
+                       after=distill_oracle.adam_reference(p0, [grad], M.LR))
+    sd = lambda00_sds['face_morpher']
+    from tha4_b200.distill import face_groundtruth_crop, FACE_LOSS_WEIGHTS
+    losses, grad = distill_oracle.face_losses_and_grads(sd, face_in['pose'], face_groundtruth_crop(face_in['posed_face']), face_in['mask'],
+                                                        FACE_LOSS_WEIGHTS)
+    p0 = torch.cat([v.reshape(-1) for v in sd.values()])
+    res['face'] = dict(weighted=[w * l for w, l in zip(FACE_LOSS_WEIGHTS, losses)], grad=grad,
+                       after=distill_oracle.adam_reference(p0, [grad], M.LR))
+    return res
+
+
+def test_distill_oracle_matches_reference_training_iteration_golden(golden_dir, lambda00_sds):
+    """tests/golden/distill_lambda00.npz was written by oracle/make_golden_distill.py from the reference's OWN
+    run_training_iteration (real protocols, SumLoss, Adam; stub teacher returning fixed tensors).  The restated step must
+    reproduce its weighted loss terms, gradient and post-Adam parameters."""
+    from oracle import make_golden_distill as M
+    npz = numpy.load(os.path.join(golden_dir, 'distill_lambda00.npz'))
+    res = _distill_oracle_results(lambda00_sds)
+    names = {'body': ['full_blended_loss', 'full_warped_loss', 'full_grid_change_loss', 'full_color_change_loss'],
+             'face': ['full_loss', 'eye_mouth_loss']}
+    for net in ('body', 'face'):
+        for name, val in zip(names[net], res[net]['weighted']):
+            ref = float(npz['%s_log_%s' % (net, name)])
+            assert abs(val - ref) <= 2e-6 * max(1.0, abs(ref)), (net, name, val, ref)
+        assert abs(sum(res[net]['weighted']) - float(npz['%s_log_loss' % net])) <= 5e-6
+        g = res[net]['grad']
+        stats = npz['%s_grad_stats' % net]
+        assert g.numel() == int(stats[3])
+        gsub = torch.from_numpy(npz['%s_grad_sub' % net])
+        assert (g[::M.GRAD_STRIDE] - gsub).abs().max().item() <= 1e-5 * max(1.0, float(stats[2])), net
+        assert abs(g.double().norm().item() - stats[0]) <= 1e-4 * stats[0], net
+        after = torch.from_numpy(npz['%s_params_after_sub' % net])
+        assert (res[net]['after'][::M.GRAD_STRIDE] - after).abs().max().item() <= 2e-7, net
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='live reference only exists in the build container')
+def test_distill_oracle_equals_live_reference_iteration(lambda00_sds):
+    from oracle import make_golden_distill as M
+    body_in, face_in = M.distill_inputs()
+    res = _distill_oracle_results(lambda00_sds)
+    live = {'body': M.reference_body_step(lambda00_sds['body_morpher'], body_in),
+            'face': M.reference_face_step(lambda00_sds['face_morpher'], face_in)}
+    for net in ('body', 'face'):
+        g, gl = res[net]['grad'], live[net]['grad']
+        assert (g - gl).abs().max().item() <= 1e-5 * max(1.0, gl.abs().max().item()), net
+        assert (res[net]['after'] - live[net]['params_after']).abs().max().item() <= 2e-7, net
+        assert abs(sum(res[net]['weighted']) - live[net]['logged']['loss']) <= 5e-6, net
