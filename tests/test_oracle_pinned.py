@@ -196,3 +196,33 @@ def test_distill_oracle_equals_live_reference_iteration(lambda00_sds):
         assert (g - gl).abs().max().item() <= 1e-5 * max(1.0, gl.abs().max().item()), net
         assert (res[net]['after'] - live[net]['params_after']).abs().max().item() <= 2e-7, net
         assert abs(sum(res[net]['weighted']) - live[net]['logged']['loss']) <= 5e-6, net
+
+
+# ------------------------------------------------------------------------------------------ image I/O on either side of the path
+@pytest.mark.skipif(not ref_loader.available(), reason='live reference only exists in the build container')
+def test_image_loader_and_output_conversion_equal_reference(golden_dir):
+    """PNG -> poser tensor (full_manual_poser.py:329-339 via extract_pytorch_image_from_filelike) and poser output -> uint8
+    sRGB RGBA (convert_output_image_from_torch_to_numpy, src/tha4/image_util.py:41-58) against the reference's functions."""
+    ref_loader.load()
+    from tha4.shion.base.image_util import extract_pytorch_image_from_filelike
+    from tha4.image_util import convert_output_image_from_torch_to_numpy
+    from tha4_b200 import image_util
+    png = os.path.join(golden_dir, 'data', 'lambda_00.png')
+    ref = extract_pytorch_image_from_filelike(png, scale=2.0, offset=-1.0, premultiply_alpha=True, perform_srgb_to_linear=True)
+    ours, orc = image_util.load_poser_image(png), image_io.load_rgba_png(png)
+    assert ours.shape == ref.shape == (4, 512, 512)
+    assert (ours - ref).abs().max().item() <= 1e-6 and (orc - ref).abs().max().item() <= 1e-6
+    out = synth.synthetic_image(3, 1)[0]
+    a, b = image_util.poser_output_to_rgba_uint8(out), convert_output_image_from_torch_to_numpy(out)
+    assert a.shape == b.shape == (512, 512, 4) and a.dtype == b.dtype == numpy.uint8
+    assert numpy.abs(a.astype(int) - b.astype(int)).max() <= 1        # uint8 rounding of float32 vs float64 pow
+
+
+def test_image_loader_golden_statistics(golden_dir):
+    """Same pin for the GPU box (no reference there): statistics of the loaded lambda_00 image recorded from the reference's
+    loader when the fixture was generated."""
+    from tha4_b200 import image_util
+    img = image_util.load_poser_image(os.path.join(golden_dir, 'data', 'lambda_00.png')).double()
+    stats = numpy.load(os.path.join(golden_dir, 'image_lambda00_stats.npz'))['stats']
+    got = numpy.array([img.mean().item(), img.abs().mean().item(), img[3].mean().item(), img[:3, 200:300, 200:300].mean().item()])
+    assert numpy.abs(got - stats).max() <= 1e-7
