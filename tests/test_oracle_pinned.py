@@ -226,3 +226,32 @@ def test_image_loader_golden_statistics(golden_dir):
     stats = numpy.load(os.path.join(golden_dir, 'image_lambda00_stats.npz'))['stats']
     got = numpy.array([img.mean().item(), img.abs().mean().item(), img[3].mean().item(), img[:3, 200:300, 200:300].mean().item()])
     assert numpy.abs(got - stats).max() <= 1e-7
+
+
+# ------------------------------------------------------------------------------------------ poser API surface (a1, a2)
+@pytest.mark.skipif(not ref_loader.available(), reason='live reference only exists in the build container')
+def test_pose_schema_and_poser_surface_equal_reference():
+    """Every pose parameter group (name, arity, category, default, range, discreteness -- pose_parameters.py:4-35) and the
+    poser getters the GUIs call (poser.py:132-161) match the reference objects field by field."""
+    ref_loader.load()
+    from tha4.poser.modes.pose_parameters import get_pose_parameters as ref_get
+    from tha4_b200.poser.modes.pose_parameters import get_pose_parameters as our_get
+    ref, ours = ref_get(), our_get()
+    assert ours.get_parameter_count() == ref.get_parameter_count() == 45
+    rg, og = ref.get_pose_parameter_groups(), ours.get_pose_parameter_groups()
+    assert len(rg) == len(og)
+    for a, b in zip(og, rg):
+        assert a.get_group_name() == b.get_group_name() and a.get_arity() == b.get_arity()
+        assert a.get_parameter_index() == b.get_parameter_index() and a.get_parameter_names() == b.get_parameter_names()
+        assert a.get_category().name == b.get_category().name and a.get_category().value == b.get_category().value
+        assert a.get_default_value() == b.get_default_value() and tuple(a.get_range()) == tuple(b.get_range())
+        assert a.is_discrete() == b.is_discrete()
+    for i in range(45):
+        assert ours.get_parameter_name(i) == ref.get_parameter_name(i)
+        assert ours.get_parameter_index(ref.get_parameter_name(i)) == i
+    ssd = synth.student_state_dicts(0)
+    rposer = ref_loader.reference_poser('mode_14', ref_loader.build_reference_modules(None, ssd)['student'])
+    from tha4_b200.poser.modes import mode_14
+    oposer = mode_14.create_poser(torch.device('cuda:0'), state_dicts=ssd)          # construction needs no GPU (lazy modules)
+    assert oposer.get_image_size() == rposer.get_image_size() and oposer.get_output_length() == rposer.get_output_length()
+    assert oposer.get_num_parameters() == rposer.get_num_parameters() and oposer.get_dtype() == rposer.get_dtype()
