@@ -54,6 +54,7 @@ const char* tha4_last_error(const tha4_ctx* ctx);
  *          "half_operands" (1: tensors between a normalisation layer and a tcgen05 conv are f16),
  *          "cluster_splitk" (1: K-split convs reduce through a thread-block cluster / DSMEM; 0: workspace + reduce kernel),
  *          "pdl" (1: programmatic dependent launch on conv / norm kernels), "tc_stride2" (1: 4x4 stride-2 convs on tcgen05),
+ *          "small_bn" (1: narrower N tiles for unsplit launches with fewer than 64 CTAs),
  *          "stream_conv", "persistent_conv", "conv_mt2", "cuda_graphs" (0: validated alternatives that measured slower),
  *          "profile" (1: time every kernel class with CUDA events on the launching stream, 2: same + reset, 0: off) */
 int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value);

@@ -80,6 +80,7 @@ bool conv_tc_enabled();
 void conv_make_half(const ConvWeights& cw, cudaStream_t s);   // f16 copy of the packed weights (cw.w16), recorded in the active AllocSink
 void conv_tc_enable_cluster(bool on);
 void conv_tc_enable_stream(bool on);    // persistent streaming kernel for multi-wave unsplit launches (default on)
+void conv_tc_enable_small_bn(bool on);  // narrower N tiles for tiny unsplit GEMMs
 void conv_tc_enable_stride2(bool on);   // stride-2 4x4 convs on the tcgen05 kernel (element-strided TMA) instead of mma.sync
 void conv_tc_enable_mt2(bool on);       // two 128-pixel tiles per CTA sharing each weight tile (default on)   // split-K through a thread-block cluster + DSMEM (default) vs workspace + reduce kernel                                                        // default: on
 

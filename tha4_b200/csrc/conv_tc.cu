@@ -765,6 +765,7 @@ namespace {
 struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW, mt; bool cluster; };
 bool g_use_mt2 = false;    // measured: no gain (the narrow layers are bound by the MMA's own shared-memory operand reads, not by L2)
 bool g_use_cluster = true;
+bool g_small_bn = true;    // narrower N tiles for unsplit launches with < 64 CTAs (option "small_bn"): 161.8 -> 167.5 frames/s at B=1
 bool g_use_s2 = true;      // 4x4 stride-2 convs through element-strided TMA boxes (option "tc_stride2")
 bool g_use_stream = false; // persistent streaming kernel for multi-wave unsplit launches (option "stream_conv"): validated, measured slower
                            // (its dedicated epilogue scratch halves the TMA ring; 224 vs 320 frames/s at B=16), kept opt-in
@@ -796,6 +797,12 @@ TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
     ksplit = std::max(1, std::min(ksplit, KT));
     const int k_per = (KT + ksplit - 1) / ksplit;
     pl.ksplit = (KT + k_per - 1) / k_per;          // every split owns at least one k-block
+    if (g_small_bn && a.ksplit <= 0 && pl.ksplit == 1) {
+        // tiny GEMMs whose K is too short to split (the 1x1 qkv / proj convs at 16^2: 6 CTAs with BN = 256): narrower N
+        // tiles put more SMs to work and shorten each CTA's weight fetch and epilogue
+        while (pl.bn > 32 && (long)pl.tiles_m * (cw.cout_pad / pl.bn) * cw.nphase < 64 && cw.cout_pad % (pl.bn / 2) == 0) pl.bn /= 2;
+        pl.tiles_n = cw.cout_pad / pl.bn;
+    }
     pl.cluster = false;
     if (g_use_cluster && pl.ksplit > 1 && KT >= 2) {
         // Split K over a thread-block cluster instead (partials meet in distributed shared memory, no workspace, no
@@ -833,6 +840,7 @@ void conv_tc_enable_cluster(bool on) { g_use_cluster = on; }
 void conv_tc_enable_mt2(bool on) { g_use_mt2 = on; }
 void conv_tc_enable_stream(bool on) { g_use_stream = on; }
 void conv_tc_enable_stride2(bool on) { g_use_s2 = on; }
+void conv_tc_enable_small_bn(bool on) { g_small_bn = on; }
 
 bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
     const TcPlan pl = tc_plan(cw, a);
