@@ -8,13 +8,16 @@ namespace tha4 {
 namespace {
 
 constexpr int L = 256, D = 32;
-constexpr int DP = D + 4;     // shared-memory row pitch: the 4 key-split lanes of a query hit 4 different banks
 
-// grid = N * heads * 4 (query quarter), block = 256 threads = 64 queries x 4 key splits.  Each thread runs an online
-// softmax over its 64 keys; the 4 partial (max, sum, acc) triples of a query are merged with warp shuffles.
-constexpr int QPB = 64, KSPLIT = 4;
+// grid = N * heads * (L / QPB), block = 256 threads = QPB queries x KSPLIT key splits.  Each thread runs an online softmax
+// over its L / KSPLIT keys; the KSPLIT partial (max, sum, acc) triples of a query are merged with warp shuffles.
+//   <64, 4, 36>: 4 CTAs per (sample, head) -- the measured default;  row pitch 36: the 4 key-split lanes hit 4 banks.
+//   <16, 16, 33>: 16 CTAs per (sample, head) for B=1 latency (128 CTAs instead of 32); row pitch 33: the 16 key-split
+//                 lanes read 16 consecutive rows = 16 different banks.  Opt-in (option "attn_split16"), not yet measured.
+template <int QPB, int KSPLIT, int DP>
 __global__ void __launch_bounds__(QPB * KSPLIT) attention_kernel(const float* __restrict__ qkv, int qkv_ld, int C, int heads,
                                                                  float* __restrict__ out, int out_ld) {
+    static_assert(QPB * KSPLIT == L, "one thread per token while staging K / V");
     extern __shared__ __align__(16) float sm[];
     float* Ks = sm;            // [L][DP]
     float* Vs = sm + L * DP;   // [L][DP]
@@ -28,8 +31,15 @@ __global__ void __launch_bounds__(QPB * KSPLIT) attention_kernel(const float* __
         const float4* vp = reinterpret_cast<const float4*>(base + (long)tid * qkv_ld + 2 * C + h * D);
 #pragma unroll
         for (int j = 0; j < D / 4; ++j) {
-            reinterpret_cast<float4*>(Ks + tid * DP)[j] = kp[j];
-            reinterpret_cast<float4*>(Vs + tid * DP)[j] = vp[j];
+            const float4 kv = kp[j], vv = vp[j];
+            if (DP % 4 == 0) {
+                reinterpret_cast<float4*>(Ks + tid * DP)[j] = kv;
+                reinterpret_cast<float4*>(Vs + tid * DP)[j] = vv;
+            } else {        // odd pitch: rows are not 16-byte aligned
+                float* kd = Ks + tid * DP + 4 * j; float* vd = Vs + tid * DP + 4 * j;
+                kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+                vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+            }
         }
     }
     const int t = qq * QPB + tid / KSPLIT;      // query token
@@ -90,20 +100,30 @@ __global__ void __launch_bounds__(QPB * KSPLIT) attention_kernel(const float* __
     }
 }
 
+bool g_attn_split16 = false;
+
+template <int QPB, int KSPLIT, int DP>
+void launch_attention(const View& qkv, int heads, const View& out, cudaStream_t s) {
+    const size_t smem = 2 * L * DP * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<QPB, KSPLIT, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    attention_kernel<QPB, KSPLIT, DP><<<qkv.N * heads * (L / QPB), QPB * KSPLIT, smem, s>>>(qkv.p, qkv.ld, out.C, heads, out.p, out.ld);
+    THA4_LAUNCH_CHECK();
+}
+
 }  // namespace
+
+void attention_enable_split16(bool on) { g_attn_split16 = on; }
 
 void attention_forward(const View& qkv, int heads, const View& out, cudaStream_t s) {
     THA4_REQUIRE(qkv.H * qkv.W == L && out.C * 3 == qkv.C && out.C / heads == D, "attention: shape (L=256, head dim 32)");
     THA4_REQUIRE(qkv.ld % 4 == 0 && out.ld % 4 == 0, "attention: alignment");
-    const size_t smem = 2 * L * DP * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     ProfScope prof(PROF_ATTN, s);
-    attention_kernel<<<qkv.N * heads * (L / QPB), QPB * KSPLIT, smem, s>>>(qkv.p, qkv.ld, out.C, heads, out.p, out.ld);
-    THA4_LAUNCH_CHECK();
+    if (g_attn_split16) launch_attention<16, 16, 33>(qkv, heads, out, s);
+    else launch_attention<64, 4, 36>(qkv, heads, out, s);
 }
 
 }  // namespace tha4

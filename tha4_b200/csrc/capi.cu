@@ -242,6 +242,7 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         else if (!strcmp(name, "stream_conv")) conv_tc_enable_stream(value != 0);
         else if (!strcmp(name, "tc_stride2")) conv_tc_enable_stride2(value != 0);
         else if (!strcmp(name, "small_bn")) conv_tc_enable_small_bn(value != 0);
+        else if (!strcmp(name, "attn_split16")) attention_enable_split16(value != 0);
         else if (!strcmp(name, "half_operands")) ctx->half_operands = value ? 1 : 0;
         else if (!strcmp(name, "pdl")) g_use_pdl = value != 0;
         else if (!strcmp(name, "profile")) { prof_enable(value != 0); if (value == 2) prof_reset(); }

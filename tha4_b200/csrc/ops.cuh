@@ -37,6 +37,7 @@ void linear_forward(const float* x, int x_ld, int N, int I, const float* W, cons
 // qkv: NHWC [N,L=H*W,3C] with q|k|v channel blocks ("new order", unet.py:192-202), heads of C/heads channels.
 // out: NHWC [N,L,C].  L must be 256, head dim 32.
 void attention_forward(const View& qkv, int heads, const View& out, cudaStream_t s);
+void attention_enable_split16(bool on);   // 16 CTAs per (sample, head) instead of 4 (B=1 latency; opt-in)
 
 // ---------------------------------------------------------------- image glue (image_ops.cu)
 void nchw_to_nhwc(const ImgView& src, const View& dst, cudaStream_t s);                 // dst.C == src.C
