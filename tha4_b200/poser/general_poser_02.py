@@ -1,6 +1,9 @@
-"""`GeneralPoser02` -- mirror of src/tha4/poser/general_poser_02.py:10-98 (constructor arguments, lazy module
-loading, rank-3/rank-1 -> batched promotion, optional subrect, `free()`, `to()`), with one addition: the modules
-of a poser share one library Context so that the poser-level pipelines can run as a single C call."""
+"""`GeneralPoser02`: the poser object every mode's `create_poser` returns.
+
+Interface of src/tha4/poser/general_poser_02.py:10-98 (constructor keywords, lazy module construction, promotion of a
+rank-3 image / rank-1 pose to a batch, optional `subrect` crop, `free()`, `to()`); the implementation differs in that
+all modules of a poser are attached to ONE library `Context` (device workspace + packed weights), which is what lets a
+mode run its whole pipeline as a single C call, and that moving the poser re-creates that context on the new device."""
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -11,6 +14,8 @@ from tha4_b200._lib import Context
 from tha4_b200.poser.poser import PoseParameterGroup, Poser
 from tha4_b200.shion.core.cached_computation import ComputationState
 
+Rect = Tuple[Tuple[int, int], Tuple[int, int]]      # ((row0, row1), (col0, col1))
+
 
 class GeneralPoser02(Poser):
     def __init__(self,
@@ -19,81 +24,79 @@ class GeneralPoser02(Poser):
                  output_length: int,
                  pose_parameters: List[PoseParameterGroup],
                  output_list_func: Callable[[ComputationState], List[Tensor]],
-                 subrect: Optional[Tuple[Tuple[int, int], Tuple[int, int]]] = None,
+                 subrect: Optional[Rect] = None,
                  default_output_index: int = 0,
                  image_size: int = 256,
                  dtype: torch.dtype = torch.float):
-        self.dtype = dtype
-        self.image_size = image_size
-        self.default_output_index = default_output_index
-        self.output_list_func = output_list_func
-        self.subrect = subrect
-        self.pose_parameters = pose_parameters
+        self._loaders = dict(module_loaders)
+        self._pipeline = output_list_func
+        self._groups = list(pose_parameters)
+        self._declared_outputs = output_length
+        self._default_output = default_output_index
+        self._crop = subrect
+        self._size = image_size
+        self._dtype = dtype
         self.device = torch.device(device)
-        self.module_loaders = module_loaders
-        self.modules = None
+        self.modules: Optional[Dict[str, Module]] = None      # built on first use
         self.context: Optional[Context] = None
-        self.num_parameters = sum(p.get_arity() for p in self.pose_parameters)
-        self.output_length = output_length
 
-    def get_image_size(self) -> int:
-        return self.image_size
-
+    # ------------------------------------------------------------------ lazily built state
     def get_context(self) -> Context:
         if self.context is None:
             self.context = Context(self.device)
         return self.context
 
-    def get_modules(self):   # general_poser_02.py:41-49
+    def get_modules(self) -> Dict[str, Module]:
         if self.modules is None:
             ctx = self.get_context()
-            self.modules = {}
-            for key in self.module_loaders:
-                module = self.module_loaders[key]()
-                self.modules[key] = module
+            built = {}
+            for key, make in self._loaders.items():
+                module = make()
                 module.attach_context(ctx)
                 module.to(self.device)
                 module.train(False)
+                built[key] = module
+            self.modules = built
         return self.modules
 
-    def get_pose_parameter_groups(self) -> List[PoseParameterGroup]:
-        return self.pose_parameters
-
-    def get_num_parameters(self) -> int:
-        return self.num_parameters
-
-    def pose(self, image: Tensor, pose: Tensor, output_index: Optional[int] = None) -> Tensor:
-        if output_index is None:
-            output_index = self.default_output_index
-        return self.get_posing_outputs(image, pose)[output_index]
-
-    def get_posing_outputs(self, image: Tensor, pose: Tensor) -> List[Tensor]:   # general_poser_02.py:63-79
-        modules = self.get_modules()
-        if len(image.shape) == 3:
-            image = image.unsqueeze(0)
-        if len(pose.shape) == 1:
-            pose = pose.unsqueeze(0)
-        if self.subrect is not None:
-            image = image[:, :, self.subrect[0][0]:self.subrect[0][1], self.subrect[1][0]:self.subrect[1][1]]
-        state = ComputationState(modules=modules, accumulated_modules={}, batch=[image, pose], outputs={})
-        state.context = self.get_context()
-        return self.output_list_func(state)
-
-    def get_output_length(self) -> int:
-        return self.output_length
-
     def free(self):
-        self.modules = None
-        self.context = None
-
-    def get_dtype(self) -> torch.dtype:
-        return self.dtype
+        """Drops modules and device workspace; they come back on the next call."""
+        self.modules, self.context = None, None
 
     def to(self, device: torch.device) -> 'GeneralPoser02':
-        device = torch.device(device)
-        if device == self.device:
-            return self
-        self.device = device
-        self.modules = None      # rebuilt (and re-uploaded) lazily on the new device
-        self.context = None
+        target = torch.device(device)
+        if target != self.device:
+            self.free()                      # weights are re-uploaded lazily on the new device
+            self.device = target
         return self
+
+    # ------------------------------------------------------------------ schema getters
+    def get_image_size(self) -> int:
+        return self._size
+
+    def get_output_length(self) -> int:
+        return self._declared_outputs
+
+    def get_pose_parameter_groups(self) -> List[PoseParameterGroup]:
+        return self._groups
+
+    def get_num_parameters(self) -> int:
+        return sum(g.get_arity() for g in self._groups)
+
+    def get_dtype(self) -> torch.dtype:
+        return self._dtype
+
+    # ------------------------------------------------------------------ posing
+    def get_posing_outputs(self, image: Tensor, pose: Tensor) -> List[Tensor]:
+        image = image[None] if image.dim() == 3 else image
+        pose = pose[None] if pose.dim() == 1 else pose
+        if self._crop is not None:
+            (r0, r1), (c0, c1) = self._crop
+            image = image[:, :, r0:r1, c0:c1]
+        state = ComputationState(modules=self.get_modules(), accumulated_modules={}, batch=[image, pose], outputs={})
+        state.context = self.get_context()
+        return self._pipeline(state)
+
+    def pose(self, image: Tensor, pose: Tensor, output_index: Optional[int] = None) -> Tensor:
+        outputs = self.get_posing_outputs(image, pose)
+        return outputs[self._default_output if output_index is None else output_index]
