@@ -79,3 +79,40 @@ def test_product_does_not_import_oracle():
             if f.endswith('.py'):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, os.path.join(dirpath, f)
+
+
+def test_general_poser_02_host_logic(monkeypatch):
+    """GeneralPoser02 semantics that need no GPU (general_poser_02.py:41-98): lazy module construction, rank-3 / rank-1
+    promotion, subrect crop, default output index, free(), to().  The library context is replaced by a stub."""
+    from tha4_b200.poser import general_poser_02 as gp
+
+    class FakeCtx:
+        def __init__(self, device): self.device = device
+
+    class FakeModule(torch.nn.Module):
+        built = 0
+        def __init__(self): super().__init__(); FakeModule.built += 1; self.ctx = None
+        def attach_context(self, ctx): self.ctx = ctx
+
+    monkeypatch.setattr(gp, 'Context', FakeCtx)
+    seen = {}
+
+    def pipeline(state):
+        image, pose = state.batch
+        seen.update(image=image, pose=pose, modules=state.modules, ctx=state.context)
+        return [image.mean(dim=(1, 2, 3)), pose.sum(dim=1), image]
+
+    poser = gp.GeneralPoser02(module_loaders={'a': FakeModule, 'b': FakeModule}, device=torch.device('cpu'), output_length=3,
+                              pose_parameters=get_pose_parameters().get_pose_parameter_groups(), output_list_func=pipeline,
+                              subrect=((2, 6), (1, 5)), default_output_index=1, image_size=8)
+    assert FakeModule.built == 0 and poser.get_num_parameters() == 45 and poser.get_image_size() == 8 and poser.get_output_length() == 3
+    out = poser.pose(torch.arange(4 * 8 * 8, dtype=torch.float).view(4, 8, 8), torch.ones(45))
+    assert FakeModule.built == 2 and out.shape == (1,) and out.item() == 45.0              # default_output_index = 1
+    assert seen['image'].shape == (1, 4, 4, 4) and seen['pose'].shape == (1, 45)             # promoted + cropped
+    assert torch.equal(seen['image'][0, 0], torch.arange(64, dtype=torch.float).view(8, 8)[2:6, 1:5])
+    assert all(m.ctx is seen['ctx'] and not m.training for m in seen['modules'].values())
+    assert poser.pose(torch.zeros(2, 4, 8, 8), torch.zeros(2, 45), 2).shape == (2, 4, 4, 4) and FakeModule.built == 2
+    poser.free()
+    poser.get_modules()
+    assert FakeModule.built == 4                                                              # rebuilt after free()
+    assert poser.to(torch.device('cpu')) is poser and FakeModule.built == 4                   # same device: nothing dropped
