@@ -1,6 +1,8 @@
 """Developer script: A/B of one library option inside one process (device-resident B=1 teacher loop)."""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 from tha4_b200 import synthetic
 from tha4_b200.poser.modes import mode_07
 opt = sys.argv[1] if len(sys.argv) > 1 else 'small_bn'

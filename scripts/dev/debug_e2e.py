@@ -1,6 +1,8 @@
 """Developer script: where the host-side time of one e2e frame goes (B=1 teacher)."""
 import os, sys, time, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 from tha4_b200 import synthetic
 from tha4_b200.poser.modes import mode_07
 dev = torch.device('cuda:0')

@@ -1,6 +1,8 @@
 """ncu target: the streaming (HBM / L2 bound) conv layers in isolation (developer script)."""
 import os, sys, math, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import gpu_util as G
 g = torch.Generator().manual_seed(0)

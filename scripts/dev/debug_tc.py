@@ -6,7 +6,9 @@ import os
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import gpu_util as G  # noqa: E402
 
