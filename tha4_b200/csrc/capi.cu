@@ -237,9 +237,6 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         else if (!strcmp(name, "cuda_graphs")) ctx->use_graphs = value ? 1 : 0;
         else if (!strcmp(name, "tcgen05")) conv_enable_tc(value != 0);
         else if (!strcmp(name, "cluster_splitk")) conv_tc_enable_cluster(value != 0);
-        else if (!strcmp(name, "persistent_conv")) conv_tcp_enable(value != 0);
-        else if (!strcmp(name, "conv_mt2")) conv_tc_enable_mt2(value != 0);
-        else if (!strcmp(name, "stream_conv")) conv_tc_enable_stream(value != 0);
         else if (!strcmp(name, "tc_stride2")) conv_tc_enable_stride2(value != 0);
         else if (!strcmp(name, "small_bn")) conv_tc_enable_small_bn(value != 0);
         else if (!strcmp(name, "attn_split16")) attention_enable_split16(value != 0);

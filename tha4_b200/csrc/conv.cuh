@@ -72,16 +72,11 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s); 
 // the caller runs norm_stats on the output.
 bool conv_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
 bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
-bool conv_tcp_supported(const ConvWeights& cw, const ConvArgs& a);                    // conv_tcp.cu (persistent, halo reuse)
-void conv_tcp_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);
-void conv_tcp_enable(bool on);
 void conv_enable_tc(bool on);
 bool conv_tc_enabled();
 void conv_make_half(const ConvWeights& cw, cudaStream_t s);   // f16 copy of the packed weights (cw.w16), recorded in the active AllocSink
 void conv_tc_enable_cluster(bool on);
-void conv_tc_enable_stream(bool on);    // persistent streaming kernel for multi-wave unsplit launches (default on)
 void conv_tc_enable_small_bn(bool on);  // narrower N tiles for tiny unsplit GEMMs
 void conv_tc_enable_stride2(bool on);   // stride-2 4x4 convs on the tcgen05 kernel (element-strided TMA) instead of mma.sync
-void conv_tc_enable_mt2(bool on);       // two 128-pixel tiles per CTA sharing each weight tile (default on)   // split-K through a thread-block cluster + DSMEM (default) vs workspace + reduce kernel                                                        // default: on
 
 }  // namespace tha4

@@ -49,10 +49,6 @@ struct TcParams {
 
 // CS > 1: the K dimension is split over a thread-block cluster of CS CTAs (cluster dims {1,1,CS} along blockIdx.z); the
 // partial accumulators are exchanged through distributed shared memory and every CTA finishes 1/CS of the columns.
-// MT = 2: the CTA owns two vertically adjacent 16x8 pixel tiles (M = 256 as two M = 128 MMAs per k-step into two TMEM
-// accumulators) that SHARE every weight tile -- operand traffic per MAC drops by a third to a half, which is what
-// bounds these kernels (L2 -> shared memory at ~40 B/clk/SM).
-//
 // OP selects the operand format of one k-block (one TMA box row per pixel / per cout):
 //   OP_TF32: 32 fp32 channels  = 128-byte rows, SWIZZLE_128B, kind::tf32 (4 MMAs of K = 8)
 //   OP_F16 : 64 f16 channels   = 128-byte rows, SWIZZLE_128B, kind::f16  (4 MMAs of K = 16)
@@ -65,17 +61,16 @@ __host__ __device__ constexpr int op_row_bytes(int op) { return op == OP_F16N ? 
 __host__ __device__ constexpr int op_kch(int op) { return op == OP_TF32 ? 32 : (op == OP_F16 ? 64 : 32); }   // channels per k-block
 __host__ __device__ constexpr int op_stages(int op, int stages) { return op == OP_F16N ? 2 * stages : stages; }
 
-template <int BN, int STAGES_, int CS, int MT, int OP>
+template <int BN, int STAGES_, int CS, int OP>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    static_assert(MT == 1 || CS == 1, "the two-tile variant is for unsplit launches");
     constexpr int STAGES = op_stages(OP, STAGES_);
     constexpr int ROWB = op_row_bytes(OP);
     constexpr int KCE = op_kch(OP);
     constexpr int A_BYTES1 = 128 * ROWB;
     constexpr int B_BYTES = BN * ROWB;
-    constexpr int A_BYTES = MT * A_BYTES1;
-    constexpr int TMEM_COLS = MT * BN < 32 ? 32 : MT * BN;
+    constexpr int A_BYTES = A_BYTES1;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smA = smem;
@@ -89,7 +84,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     const int tx = tile % p.tiles_x; tile /= p.tiles_x;
     const int ty = tile % p.tiles_y;
     const int n = tile / p.tiles_y;
-    const int x0 = tx * TILE_W, y0 = ty * TILE_H * MT;
+    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
     const int n0 = blockIdx.y * BN;
     const int phase = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
     const int KT = p.ntaps * p.cpt;
@@ -158,14 +153,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     const uint64_t adesc = make_smem_desc_sw<ROWB>(smem_u32(smA + s * A_BYTES));
                     const uint64_t bdesc = make_smem_desc_sw<ROWB>(smem_u32(smB + s * B_BYTES));
 #pragma unroll
-                    for (int h = 0; h < MT; ++h)
-#pragma unroll
                         for (int k = 0; k < ROWB / 32; ++k) {  // one MMA consumes 32 bytes of K per row (8 tf32 / 16 f16): advance the start address by 2 (>>4)
                             if (OP == OP_TF32)
-                                umma_tf32(tmem_base + (uint32_t)(h * BN), adesc + (uint64_t)(h * (A_BYTES1 >> 4)) + 2 * k, bdesc + 2 * k, idesc,
+                                umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc,
                                           (i > 0 || k > 0) ? 1u : 0u);
                             else
-                                umma_f16(tmem_base + (uint32_t)(h * BN), adesc + (uint64_t)(h * (A_BYTES1 >> 4)) + 2 * k, bdesc + 2 * k, idesc,
+                                umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc,
                                          (i > 0 || k > 0) ? 1u : 0u);
                         }
                     umma_commit(smem_u32(bars + STAGES + s));          // frees the smem slot when these MMAs retire
@@ -196,16 +189,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             const int row = q * 32 + lane;
             const bool lead = (split == 0);
             float* scratch = reinterpret_cast<float*>(smA) + q * (32 * 33);   // pipeline smem is idle once tmem_full fired
-#pragma unroll 1
-            for (int h = 0; h < MT; ++h) {
-            const int my = y0 + h * TILE_H + row / TILE_W, mx = x0 + row % TILE_W;
+            const int my = y0 + row / TILE_W, mx = x0 + row % TILE_W;
             const bool valid = my < p.MH && mx < p.MW;
             const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
             float* orow = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + c0), r);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
                 const int cbase = n0 + c0;
                 if (cbase >= p.outC) continue;                         // warp-uniform
                 float v[32];
@@ -274,9 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     atomicAdd(base + 2 * c, (double)a.x + (double)b.x + (double)cc.x + (double)d.x);
                     atomicAdd(base + 2 * c + 1, (double)a.y + (double)b.y + (double)cc.y + (double)d.y);
                 }
-                if (MT > 1) asm volatile("bar.sync 1, 128;\n" ::: "memory");     // `part` is reused by the second tile
             }
-            }   // h
         }
     }
     if (CS > 1) {
@@ -376,185 +365,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Persistent ("streaming") variant for the launches that are bound by memory latency rather than by the tensor pipe:
-// many 128-pixel tiles, few k-blocks each (the 32..128-channel layers at 128^2..512^2).  A CTA walks tiles
-// blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring runs ACROSS tiles (the producer is already fetching tile i+1
-// while tile i is in its epilogue) and the accumulator is double-buffered in TMEM (2 x BN columns), so the three
-// latency chains of a tile -- operand fetch, MMA, residual fetch + store -- overlap between consecutive tiles of one
-// CTA as well as between the ~3 CTAs of an SM.  Unsplit K only (ksplit == 1, no cluster, MT == 1).
-template <int BN, int STAGES_, int OP>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_stream_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                      const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-    constexpr int STAGES = op_stages(OP, STAGES_);
-    constexpr int ROWB = op_row_bytes(OP);
-    constexpr int KCE = op_kch(OP);
-    constexpr int A_BYTES = 128 * ROWB;
-    constexpr int B_BYTES = BN * ROWB;
-    constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smA = smem;
-    uint8_t* smB = smem + STAGES * A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * B_BYTES);   // full[S], empty[S], tmem_full[2], tmem_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* scratch_all = reinterpret_cast<float*>(tmem_slot + 4);           // [4 warps][32][33]
-    float2* part = reinterpret_cast<float2*>(scratch_all + 4 * 32 * 33);    // [4 warps][BN]
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.y * BN;
-    const int phase = blockIdx.z;
-    const int KT = p.ntaps * p.cpt;
-    const int ntiles = p.tiles_x * p.tiles_y * p.N;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STAGES + s), 1); }
-        mbar_init(smem_u32(bars + 2 * STAGES), 1); mbar_init(smem_u32(bars + 2 * STAGES + 1), 1);          // tmem_full[2]: one commit
-        mbar_init(smem_u32(bars + 2 * STAGES + 2), 128); mbar_init(smem_u32(bars + 2 * STAGES + 3), 128);  // tmem_empty[2]: 128 epilogue threads
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmA) : "memory");
-        asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmB) : "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_trigger();
-    pdl_wait();
-
-    if (warp == 0) {
-        if (lane == 0) {   // ===== TMA producer: one continuous ring over all tiles of this CTA =====
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-                for (int kt = 0; kt < KT; ++kt, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(smem_u32(bars + STAGES + s), ((it / STAGES) & 1) ^ 1);
-                    const uint32_t full = smem_u32(bars + s);
-                    mbar_expect_tx(full, A_BYTES + B_BYTES);
-                    const int tap = kt / p.cpt;
-                    const int c0 = (kt - tap * p.cpt) * KCE;
-                    tma_load_4d(smem_u32(smA + s * A_BYTES), &tmA, c0, x0 * p.in_mul + p.dx[phase][tap], y0 * p.in_mul + p.dy[phase][tap], n, full);
-                    tma_load_3d(smem_u32(smB + s * B_BYTES), &tmB, c0, n0, phase * p.ntaps + tap, full);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {   // ===== MMA issuer =====
-            constexpr uint32_t fmt = OP == OP_TF32 ? 2u : 0u;
-            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
-            uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
-                const uint32_t acc = lt & 1;
-                mbar_wait(smem_u32(bars + 2 * STAGES + 2 + acc), ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                for (int kt = 0; kt < KT; ++kt, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(smem_u32(bars + s), (it / STAGES) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const uint64_t adesc = make_smem_desc_sw<ROWB>(smem_u32(smA + s * A_BYTES));
-                    const uint64_t bdesc = make_smem_desc_sw<ROWB>(smem_u32(smB + s * B_BYTES));
-#pragma unroll
-                    for (int k = 0; k < ROWB / 32; ++k) {
-                        if (OP == OP_TF32) umma_tf32(tmem_base + acc * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kt > 0 || k > 0) ? 1u : 0u);
-                        else umma_f16(tmem_base + acc * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kt > 0 || k > 0) ? 1u : 0u);
-                    }
-                    umma_commit(smem_u32(bars + STAGES + s));
-                }
-                umma_commit(smem_u32(bars + 2 * STAGES + acc));
-            }
-        }
-    } else {               // ===== epilogue warps =====
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        float* scratch = scratch_all + q * (32 * 33);
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
-            const uint32_t acc = lt & 1;
-            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, n = tile / (p.tiles_x * p.tiles_y);
-            const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-            const int my = y0 + row / TILE_W, mx = x0 + row % TILE_W;
-            const bool valid = my < p.MH && mx < p.MW;
-            const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
-            float* orow = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld;
-            mbar_wait(smem_u32(bars + 2 * STAGES + acc), (lt >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-                if (c0 + 32 >= BN) {     // last read of this accumulator: hand it back to the MMA thread
-                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                    mbar_arrive(smem_u32(bars + 2 * STAGES + 2 + acc));
-                }
-                const int cbase = n0 + c0;
-                if (cbase >= p.outC) continue;                         // warp-uniform
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                const int cn = min(32, p.outC - cbase);
-                if (valid) {
-                    if (p.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
-                    }
-                    if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
-                        const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
-                        const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + cbase;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += rr[j];
-                    } else if (p.res_mode == RES_DOWN2) {
-                        const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + cbase;
-                        const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < cn) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
-                    }
-                    if (cn == 32) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(orow + cbase + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (j < cn) orow[cbase + j] = v[j];
-                    }
-                }
-                if (p.stats) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = valid ? v[j] : 0.0f;
-                    __syncwarp();
-                    float su = 0.0f, sq = 0.0f;
-#pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr) { const float t = scratch[rr * 33 + lane]; su += t; sq += t * t; }
-                    __syncwarp();
-                    part[q * BN + c0 + lane] = make_float2(su, sq);
-                }
-            }
-            if (p.stats) {
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                double* base = p.stats + (long)(tile % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + n0) * 2;
-                for (int c = (warp - 2) * 32 + lane; c < BN; c += 128) {
-                    if (n0 + c >= p.outC) break;
-                    const float2 a = part[c], b = part[BN + c], cc = part[2 * BN + c], d = part[3 * BN + c];
-                    atomicAdd(base + 2 * c, (double)a.x + (double)b.x + (double)cc.x + (double)d.x);
-                    atomicAdd(base + 2 * c + 1, (double)a.y + (double)b.y + (double)cc.y + (double)d.y);
-                }
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");       // `part` is rewritten by the next tile
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
-}
-
 // out = sum_splits ws + bias + res  (deterministic split-K reduction; replaces fp32 atomics), plus the per-(n,c)
 // statistics of the result.  grid = (pixel slabs, N * nphase); thread (pl, q) walks pixels pl, pl + PL, ... of its slab.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcParams p, int nphase, int ppt) {
@@ -636,8 +446,8 @@ EncodeTiledFn get_encode() {
 using MapKey = std::tuple<const void*, long, long, long, long, long, int>;
 std::map<MapKey, CUtensorMap> g_maps;
 
-const CUtensorMap& activation_map(const View& v, int mt, int op, int stride) {
-    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -(mt + 4 * op + 16 * stride)};
+const CUtensorMap& activation_map(const View& v, int op, int stride) {
+    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -(1 + 4 * op + 16 * stride)};
     auto it = g_maps.find(key);
     if (it != g_maps.end()) return it->second;
     CUtensorMap m;
@@ -646,7 +456,7 @@ const CUtensorMap& activation_map(const View& v, int mt, int op, int stride) {
     THA4_REQUIRE((op != OP_TF32) == (v.f16 != 0), "conv_tc: operand format does not match the activation view");
     cuuint64_t strides[3] = {(cuuint64_t)v.ld * eb, (cuuint64_t)v.W * v.ld * eb, (cuuint64_t)v.H * v.W * v.ld * eb};
     // stride 2: the box spans 2x the pixels and is traversed with element stride 2, so it still delivers 16 x 8 pixels
-    cuuint32_t box[4] = {(cuuint32_t)op_kch(op), (cuuint32_t)(TILE_W * stride), (cuuint32_t)(TILE_H * mt * stride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)op_kch(op), (cuuint32_t)(TILE_W * stride), (cuuint32_t)(TILE_H * stride), 1};
     cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = get_encode()(&m, op == OP_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, v.p, dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, op == OP_F16N ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
@@ -673,46 +483,21 @@ const CUtensorMap& weight_map(const ConvWeights& cw, int bn, int op) {
     return g_maps.emplace(key, m).first->second;
 }
 
-template <int OP, int BN, int STAGES_, int CS = 1, int MT = 1>
+template <int OP, int BN, int STAGES_, int CS = 1>
 void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
     constexpr int STAGES = op_stages(OP, STAGES_);
-    constexpr int STAGE_BYTES = (MT * 128 + BN) * op_row_bytes(OP);
+    constexpr int STAGE_BYTES = (128 + BN) * op_row_bytes(OP);
     constexpr size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static_assert((size_t)STAGES * STAGE_BYTES >= (size_t)4 * 32 * 33 * 4 + 4 * BN * 8, "epilogue scratch must fit in the pipeline buffers");
     static_assert(CS == 1 || (size_t)STAGES * STAGE_BYTES >= (size_t)128 * BN * 4 + 128 * 8 * 4 + 128 * 4, "partial tile + statistics scratch must fit");
     static bool configured = false;
     if (!configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES_, CS, MT, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES_, CS, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    launch_pdl(conv_tc_kernel<BN, STAGES_, CS, MT, OP>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, p);
+    launch_pdl(conv_tc_kernel<BN, STAGES_, CS, OP>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, p);
     THA4_LAUNCH_CHECK();
-}
-
-template <int OP, int BN, int STAGES_>
-void launch_tc_stream(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int tiles_m, int tiles_n, int nphase, cudaStream_t s) {
-    constexpr int STAGES = op_stages(OP, STAGES_);
-    constexpr int STAGE_BYTES = (128 + BN) * op_row_bytes(OP);
-    constexpr size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 4 * 32 * 33 * 4 + 4 * BN * 8;
-    static_assert(smem <= 227 * 1024, "shared memory budget");
-    static int ctas_per_sm = 0;
-    if (!ctas_per_sm) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_stream_kernel<BN, STAGES_, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        THA4_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, conv_tc_stream_kernel<BN, STAGES_, OP>, TC_THREADS, smem));
-        ctas_per_sm = std::max(1, std::min(ctas_per_sm, 512 / (2 * BN)));      // TMEM: 2 x BN columns per CTA
-    }
-    const int slots = 148 * ctas_per_sm;
-    const int gx = std::max(1, std::min(tiles_m, slots / std::max(1, tiles_n * nphase)));
-    launch_pdl(conv_tc_stream_kernel<BN, STAGES_, OP>, dim3(gx, tiles_n, nphase), dim3(TC_THREADS), smem, s, 1, ma, mb, p);
-    THA4_LAUNCH_CHECK();
-}
-
-template <int OP>
-void launch_stream_variants(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int tiles_m, int tiles_n, int nphase, cudaStream_t s) {
-    if (bn == 128) launch_tc_stream<OP, 128, 2>(ma, mb, p, tiles_m, tiles_n, nphase, s);
-    else if (bn == 64) launch_tc_stream<OP, 64, 2>(ma, mb, p, tiles_m, tiles_n, nphase, s);
-    else launch_tc_stream<OP, 32, 2>(ma, mb, p, tiles_m, tiles_n, nphase, s);
 }
 
 template <int OP, int BN, int STAGES>
@@ -762,27 +547,17 @@ int op_for(const ConvWeights& cw, const ConvArgs& a) {
 }  // namespace
 
 namespace {
-struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW, mt; bool cluster; };
-bool g_use_mt2 = false;    // measured: no gain (the narrow layers are bound by the MMA's own shared-memory operand reads, not by L2)
+struct TcPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, ksplit, MH, MW; bool cluster; };
 bool g_use_cluster = true;
 bool g_small_bn = true;    // narrower N tiles for unsplit launches with < 64 CTAs (option "small_bn"): 161.8 -> 167.5 frames/s at B=1
 bool g_use_s2 = true;      // 4x4 stride-2 convs through element-strided TMA boxes (option "tc_stride2")
-bool g_use_stream = false; // persistent streaming kernel for multi-wave unsplit launches (option "stream_conv"): validated, measured slower
-                           // (its dedicated epilogue scratch halves the TMA ring; 224 vs 320 frames/s at B=16), kept opt-in
 TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
     TcPlan pl;
     pl.MH = a.out.H / cw.out_mul; pl.MW = a.out.W / cw.out_mul;
     pl.tiles_x = ceil_div(pl.MW, TILE_W); pl.tiles_y = ceil_div(pl.MH, TILE_H);
-    pl.mt = 1;
     pl.bn = (cw.cout_pad % 256 == 0) ? 256 : (cw.cout_pad % 128 == 0 ? 128 : (cw.cout_pad % 64 == 0 ? 64 : 32));
     pl.tiles_m = pl.tiles_x * pl.tiles_y * a.in.N;
     pl.tiles_n = cw.cout_pad / pl.bn;
-    // two-tile CTAs (M = 256) when that still fills the GPU about twice over
-    if (g_use_mt2 && !a.in.f16 && a.ksplit <= 1 && (long)pl.tiles_x * ceil_div(pl.MH, 2 * TILE_H) * a.in.N * pl.tiles_n * cw.nphase >= 280) {
-        pl.mt = 2;
-        pl.tiles_y = ceil_div(pl.MH, 2 * TILE_H);
-        pl.tiles_m = pl.tiles_x * pl.tiles_y * a.in.N;
-    }
     const int KT = cw.ntaps * (cw.cin_pad / op_kch(op_for(cw, a)));
     int ksplit = a.ksplit;
     if (ksplit <= 0) {
@@ -821,7 +596,7 @@ TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
 }  // namespace
 
 size_t conv_workspace_floats(const ConvWeights& cw, const ConvArgs& a) {
-    if (!conv_tc_supported(cw, a) || conv_tcp_supported(cw, a)) return 0;
+    if (!conv_tc_supported(cw, a)) return 0;
     const TcPlan pl = tc_plan(cw, a);
     if (pl.ksplit <= 1 || pl.cluster) return 0;
     return (size_t)cw.nphase * pl.ksplit * pl.tiles_m * 128 * cw.cout_pad;
@@ -837,8 +612,6 @@ void conv_make_half(const ConvWeights& cw, cudaStream_t s) {
 }
 
 void conv_tc_enable_cluster(bool on) { g_use_cluster = on; }
-void conv_tc_enable_mt2(bool on) { g_use_mt2 = on; }
-void conv_tc_enable_stream(bool on) { g_use_stream = on; }
 void conv_tc_enable_stride2(bool on) { g_use_s2 = on; }
 void conv_tc_enable_small_bn(bool on) { g_small_bn = on; }
 
@@ -895,7 +668,7 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
     if (ksplit > 1 && !use_ws && !pl.cluster)
         THA4_CUDA_CHECK(cudaMemset2DAsync(a.out.p, (size_t)a.out.ld * sizeof(float), 0, (size_t)a.out.C * sizeof(float), a.out.pixels(), s));
-    const CUtensorMap& ma = activation_map(a.in, pl.mt, op, cw.stride);
+    const CUtensorMap& ma = activation_map(a.in, op, cw.stride);
     const CUtensorMap& mb = weight_map(cw, bn, op);
     dim3 grid(tiles_m, tiles_n, cw.nphase * ksplit);
     // Pipeline depth: grids that cannot even fill the GPU once (the B=1 bottleneck layers, which stream their weights
@@ -908,20 +681,6 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     }
     const long total_ctas = (long)grid.x * grid.y * grid.z;
     const int stages_mode = forced >= 0 ? forced : (total_ctas <= 160 ? 0 : 2);
-    if (pl.mt == 2) {          // M = 256 per CTA, accumulators MT x BN columns of TMEM (tf32 operands only)
-        if (bn == 256) launch_tc<OP_TF32, 256, 3, 1, 2>(ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc<OP_TF32, 128, 4, 1, 2>(ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc<OP_TF32, 64, 2, 1, 2>(ma, mb, p, grid, s);
-        else launch_tc<OP_TF32, 32, 2, 1, 2>(ma, mb, p, grid, s);
-        return;
-    }
-    if (g_use_stream && !pl.cluster && ksplit == 1 && bn <= 128 && total_ctas > 3 * 148) {
-        // many small tiles: persistent CTAs with the TMA ring and a double-buffered accumulator running across tiles
-        if (op == OP_TF32) launch_stream_variants<OP_TF32>(bn, ma, mb, p, tiles_m, tiles_n, cw.nphase, s);
-        else if (op == OP_F16) launch_stream_variants<OP_F16>(bn, ma, mb, p, tiles_m, tiles_n, cw.nphase, s);
-        else launch_stream_variants<OP_F16N>(bn, ma, mb, p, tiles_m, tiles_n, cw.nphase, s);
-        return;
-    }
     if (op == OP_TF32) launch_variants<OP_TF32>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
     else if (op == OP_F16) launch_variants<OP_F16>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
     else launch_variants<OP_F16N>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);

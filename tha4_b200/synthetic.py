@@ -5,6 +5,16 @@ The teacher weights are not shipped with the reference (they are a separate down
 (bit-identical across machines running the same torch build).  Tensors that the reference zero-initialises (U-Net
 conv1 / last / attention out-proj, coarse_image_conv, grid_change heads) are drawn from small normals instead,
 otherwise a random-init teacher outputs zero warps and nothing downstream is exercised.
+
+Conditioning (round 2).  A plain He-init teacher is *chaotic* as a function of its conv operands: its heads paint
+full-amplitude white noise, the next network warps that noise, and a 1e-3 change of a warp offset moves the result
+by O(0.1) (profiles/r01_cpu_10bit_sensitivity.txt: rounding the conv operands of the CPU oracle to 10 mantissa bits
+moved the face-morpher outputs by 4.9e-2 mean).  Trained weights do not behave like that: residual branches are
+small corrections, colour changes are small, alphas mostly keep the input image.  `_condition` gives the seeded
+weights that character (key-name based scaling of the head / residual / zero-init tensors), which makes the fp32
+oracle a usable yardstick for the tensor-core precision mode: the same 10-bit-operand emulation now moves every
+mode_07 output by <= 3e-4 mean / 1.4e-2 max (profiles/r02_cpu_10bit_sensitivity.txt), so the default-mode parity
+tests can assert mean <= 2e-3, max <= 5e-2.
 """
 import math
 from typing import Dict
@@ -52,13 +62,41 @@ def _draw(shape, role: str, g: torch.Generator) -> torch.Tensor:
     raise ValueError(role)
 
 
-def make_state_dict(spec: Spec, seed: int) -> Dict[str, torch.Tensor]:
+def _condition(key: str, shape, role: str, t: torch.Tensor) -> torch.Tensor:
+    """Trained-like scaling of one seeded teacher tensor (see the module docstring)."""
+    is_encdec_head = len(shape) == 4 and shape[1] == 64 and shape[2] == 3 and shape[0] <= 4 and not key.startswith('body.')
+    if is_encdec_head and role == 'conv':
+        return t * 0.1                                   # colour changes ~0.1, alpha logits ~ bias
+    if role == 'bias' and 'alpha' in key and not key.startswith('body.'):
+        # alphas keep the input image: eyebrow_layer = image * alpha + colour * (1 - alpha) wants alpha ~ 1,
+        # every other blend is colour * alpha + image * (1 - alpha) and wants alpha ~ 0
+        return t + (2.0 if key.startswith('eyebrow_layer_alpha') else -2.0)
+    if role == 'grid_head':
+        return t * 0.5                                   # warps of ~1-2 pixels
+    if role == 'zconv':
+        return t * 0.3                                   # residual branches are corrections, not replacements
+    if role == 'last':
+        return t * 0.3
+    if key.endswith('resnet_path.4.weight'):             # InstanceNorm gamma that closes a ResnetBlock branch
+        return t * 0.2
+    if key == 'body.last.2.bias':
+        t = t.clone()
+        t[6] -= 2.0                                      # merged = direct * alpha + warped * (1 - alpha): mostly the warp
+        return t
+    return t
+
+
+def make_state_dict(spec: Spec, seed: int, condition: bool = False) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)
-    return {k: _draw(shape, role, g) for k, shape, role in spec}
+    out = {}
+    for k, shape, role in spec:
+        t = _draw(shape, role, g)
+        out[k] = _condition(k, shape, role, t) if condition else t
+    return out
 
 
 def teacher_state_dicts(seed: int = 0) -> Dict[str, Dict[str, torch.Tensor]]:
-    return {name: make_state_dict(fn(), seed * 100 + i) for i, (name, fn) in enumerate(TEACHER_SPECS.items())}
+    return {name: make_state_dict(fn(), seed * 100 + i, condition=True) for i, (name, fn) in enumerate(TEACHER_SPECS.items())}
 
 
 def student_state_dicts(seed: int = 0) -> Dict[str, Dict[str, torch.Tensor]]:
