@@ -103,11 +103,13 @@ int tha4_siren_morpher_forward(tha4_ctx* ctx, const float* image, const float* p
 /* mode 7: FiveStepPoserComputationProtocol (src/tha4/poser/modes/mode_07.py:47-134): 33 outputs in the order
  *   upscaler(5) face_morphed_full(1) body_morpher(5) face_morpher(8) eyebrow_morphing_combiner(8) eyebrow_decomposer(6)
  * mode 12: the face-only teacher (src/tha4/poser/modes/mode_12.py:41-96): 22 outputs, face(8) combiner(8) decomposer(6).
- * image [B,4,512,512], pose [B,45].  cached_decomposer: NULL, or the 6 decomposer outputs of an earlier call with
+ * image [B,4,512,512], pose [B,45].  image_batch_stride: floats between consecutive images -- 4*512*512 for a dense
+ * batch, 0 when ONE image is posed B times (what `image.expand(B, -1, -1, -1)` describes in PyTorch: a pose sweep
+ * never materialises B copies).  cached_decomposer: NULL, or the 6 decomposer outputs of an earlier call with
  * the same image batch (the reference's eyebrow cache, mode_07.py:56-68); then the decomposer is skipped and the
  * last 6 entries of `outputs` are not written. */
-int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, const float* pose, int B, float* const* outputs,
-                         int eyebrow_morphed_image_index, const float* const* cached_decomposer, void* stream);
+int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, int64_t image_batch_stride, const float* pose, int B,
+                         float* const* outputs, int eyebrow_morphed_image_index, const float* const* cached_decomposer, void* stream);
 /* mode 14: TwoStepPoserComputationProtocol (src/tha4/poser/modes/mode_14.py:40-90): body(5) + face(1) */
 int tha4_student_forward(tha4_ctx* ctx, const float* image, const float* pose, int B, float* const* outputs, void* stream);
 /* ---- distillation inner loop of the body student (replaces the autograd part of
@@ -158,9 +160,18 @@ int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, cons
                    int res_mode, int in_up, float* y, int N, int Cin, int H, int W, int Cout, int strict, int ksplit,
                    void* stream);
 /* y = act(norm(x)) with groups == 0: InstanceNorm2d, else GroupNorm(groups); act 0 none / 1 relu / 2 silu; pool 0/1;
- * film0 [2C] / film1 [N,2C] optional FiLM scale-shifts (unet.py:90-97) */
+ * film0 [2C] / film1 [N,2C] optional FiLM scale-shifts (unet.py:90-97); out_f16 = 1 runs the default-mode variant
+ * (f16 output tensor, fast-math SiLU) and returns its values widened to fp32 */
 int tha4_test_norm(tha4_ctx* ctx, const float* x, int N, int C, int H, int W, int groups, const float* gamma,
-                   const float* beta, const float* film0, const float* film1, int act, int pool, float* y, void* stream);
+                   const float* beta, const float* film0, const float* film1, int act, int pool, int out_f16, float* y, void* stream);
+/* One fused decoder tail (SURVEY 8 a-T) in isolation: feature [N,C,S,S] is the raw last feature map; the kernel applies
+ * the pending InstanceNorm (groups 0) / GroupNorm + activation (1 relu / 2 silu), the n_heads 3x3 head convs
+ * (head_w: the reference weights [cout_i, C, 3, 3] concatenated in the order listed in tail.cu for `kind`, head_b:
+ * concatenated biases incl. placeholders for bias-free heads), grid_sample and the blends.  kind 0 U-Net (5 outputs),
+ * 1 decomposer (6), 2 combiner (8), 3 face morpher (8).  image1: combiner background layer, else NULL. */
+int tha4_test_tail(tha4_ctx* ctx, int kind, const float* feature, int N, int C, int S, const float* gamma, const float* beta,
+                   int groups, int act, const float* head_w, const float* head_b, const int* head_cout, int n_heads,
+                   const float* image0, const float* image1, float* const* outputs, int strict, void* stream);
 /* qkv_attention, "new order" (src/tha4/nn/common/unet.py:192-202): qkv [N,3C,16,16] -> out [N,C,16,16] */
 int tha4_test_attention(tha4_ctx* ctx, const float* qkv, int N, int C, int heads, float* out, void* stream);
 /* y[n][o] = b[o] + sum_i f(x[n][i]) W[o][i] */

@@ -35,15 +35,35 @@ def conv(kind, x, w, bias=None, res=None, res_mode=0, in_up=0, strict=1, ksplit=
     return y.cpu()
 
 
-def norm(x, groups, gamma, beta, film0=None, film1=None, act=0, pool=0):
+def norm(x, groups, gamma, beta, film0=None, film1=None, act=0, pool=0, out_f16=0):
     c = ctx()
     N, C, H, W = x.shape
     y = torch.empty(N, C, H // 2 if pool else H, W // 2 if pool else W, device='cuda:0')
     args = [dev(x), dev(gamma), dev(beta), dev(film0) if film0 is not None else None, dev(film1) if film1 is not None else None]
     c._call('tha4_test_norm', _ptr(args[0]), N, C, H, W, groups, _ptr(args[1]), _ptr(args[2]), _ptr(args[3]), _ptr(args[4]),
-            act, pool, _ptr(y), c._stream())
+            act, pool, out_f16, _ptr(y), c._stream())
     torch.cuda.synchronize()
     return y.cpu()
+
+
+TAIL_OUT_SPECS = {0: [4, 1, 4, 2, 4], 1: [4, 1, 4, 4, 1, 4], 2: [4, 1, 4, 4, 1, 4, 4, 2], 3: [4, 1, 4, 4, 1, 4, 4, 2]}
+
+
+def tail(kind, feature, gamma, beta, groups, act, head_ws, head_bs, image0, image1=None, strict=0):
+    """head_ws: list of [cout_i, C, 3, 3]; head_bs: list of [cout_i] or None (bias-free head)."""
+    c = ctx()
+    N, C, S, _ = feature.shape
+    outs = [torch.empty(N, ch, S, S, device='cuda:0') for ch in TAIL_OUT_SPECS[kind]]
+    hw = dev(torch.cat([w.reshape(-1) for w in head_ws]))
+    hb = dev(torch.cat([(b if b is not None else torch.zeros(w.shape[0])) for w, b in zip(head_ws, head_bs)]))
+    couts = (ctypes.c_int * len(head_ws))(*[w.shape[0] for w in head_ws])
+    f, g, b, i0 = dev(feature), dev(gamma), dev(beta), dev(image0)
+    i1 = dev(image1) if image1 is not None else None
+    from tha4_b200._lib import _ptr_array
+    c._call('tha4_test_tail', kind, _ptr(f), N, C, S, _ptr(g), _ptr(b), groups, act, _ptr(hw), _ptr(hb), couts, len(head_ws),
+            _ptr(i0), _ptr(i1), _ptr_array(outs), strict, c._stream())
+    torch.cuda.synchronize()
+    return [o.cpu() for o in outs]
 
 
 def attention(qkv, heads=8):

@@ -64,10 +64,12 @@ def test_student_train_step_vs_autograd(student_sds):
     assert (flat.cpu() - ref_p).abs().max().item() <= 2e-7
 
 
-def test_full_distill_step_with_teacher(teacher_sds, student_sds):
-    """teacher forward (strict) -> student step: losses against the oracle teacher + oracle student."""
+@pytest.mark.parametrize('strict', [1, 0])
+def test_full_distill_step_with_teacher(teacher_sds, student_sds, strict):
+    """teacher forward -> student step: losses against the oracle teacher + oracle student.  strict = 0 is the teacher
+    precision mode bench.py's distill workload runs (default mode: targets within 2e-3 mean of the oracle's)."""
     teacher = mode_07.create_poser(DEV, state_dicts=teacher_sds)
-    teacher.get_context().set_option('strict', 1)
+    teacher.get_context().set_option('strict', strict)
     student = mode_14.load_body_morpher(None, student_sds['body_morpher'])
     d = BodyMorpherDistiller(teacher, student)
     image = synth.synthetic_image(0, 1)
@@ -81,7 +83,7 @@ def test_full_distill_step_with_teacher(teacher_sds, student_sds):
     for name, b in zip(('full_blended', 'full_warped', 'full_grid_change', 'full_color_change'), ref_losses):
         assert abs(out[name] - b) <= 3e-3 * max(abs(b), 1e-3), (name, out[name], b)
     g = d.grad.cpu()
-    assert ((g - ref_grad).norm() / ref_grad.norm()).item() <= 4e-2
+    assert ((g - ref_grad).norm() / ref_grad.norm()).item() <= (4e-2 if strict else 6e-2)
     ref_p = distill_oracle.adam_reference(before.cpu(), [ref_grad], 1e-4)
     # first Adam step moves every weight by ~lr * sign(g): compare the update direction where the gradient is not tiny
     upd, ref_upd = (d.flat.cpu() - before.cpu()), (ref_p - before.cpu())
@@ -126,12 +128,13 @@ def test_face_student_train_step_vs_autograd(student_sds):
     assert rel <= 3e-2 and cos >= 0.999
 
 
-def test_full_face_distill_step_with_teacher(teacher_sds, student_sds):
-    """mode_12 teacher (strict) -> crop -> face-student step -> Adam; losses against the oracle teacher + oracle student."""
+@pytest.mark.parametrize('strict', [1, 0])
+def test_full_face_distill_step_with_teacher(teacher_sds, student_sds, strict):
+    """mode_12 teacher -> crop -> face-student step -> Adam; losses against the oracle teacher + oracle student."""
     from tha4_b200.distill import FaceMorpherDistiller, face_groundtruth_crop
     from tha4_b200.poser.modes import mode_12
     teacher = mode_12.create_poser(DEV, state_dicts=teacher_sds)
-    teacher.get_context().set_option('strict', 1)
+    teacher.get_context().set_option('strict', strict)
     student = mode_14.load_face_morpher(None, student_sds['face_morpher'])
     d = FaceMorpherDistiller(teacher, student)
     image = synth.synthetic_image(0, 2)
@@ -147,10 +150,50 @@ def test_full_face_distill_step_with_teacher(teacher_sds, student_sds):
     ref_losses, ref_grad = distill_oracle.face_losses_and_grads(student_sds['face_morpher'], pose, target, mask)
     for name, b in zip(('full', 'eye_mouth'), ref_losses):
         assert abs(out[name] - b) <= 3e-3 * max(abs(b), 1e-3), (name, out[name], b)
-    assert ((d.grad.cpu() - ref_grad).norm() / ref_grad.norm()).item() <= 4e-2
+    assert ((d.grad.cpu() - ref_grad).norm() / ref_grad.norm()).item() <= (4e-2 if strict else 6e-2)
     ref_p = distill_oracle.adam_reference(before.cpu(), [ref_grad], 1e-4)
     upd, ref_upd = (d.flat.cpu() - before.cpu()), (ref_p - before.cpu())
     big = ref_grad.abs() > 1e-3 * ref_grad.abs().max()
     assert (torch.sign(upd[big]) == torch.sign(ref_upd[big])).float().mean().item() >= 0.995
     y = student.to(DEV)(pose[:, 0:39].to(DEV))
     assert y.shape == (2, 4, 128, 128) and torch.isfinite(y).all()
+
+
+def test_face_student_trajectory_vs_cpu(student_sds):
+    """Five consecutive CUDA steps (forward, backward, Adam on the flat buffers) against five CPU autograd + torch.optim.Adam
+    steps from the same start: the accumulated weight update must point the same way (cosine >= 0.98) and have the same
+    length (within 5 %); a drift between the two optimiser states or a stale weight upload would show here."""
+    from tha4_b200.distill import FACE_LOSS_WEIGHTS
+    sd = {k: v.clone() for k, v in student_sds['face_morpher'].items()}
+    keys = list(sd.keys())
+    n, steps, lr = 2, 5, 1e-4
+    poses = [synth.random_poses(n, seed=40 + i) for i in range(steps)]
+    targets = [_smooth(50 + i, n, 4)[:, :, 100:228, 190:318].contiguous() for i in range(steps)]
+    mask = torch.zeros(n, 4, 128, 128)
+    mask[:, :, 40:90, 30:100] = 1.0
+
+    student = mode_14.load_face_morpher(None, sd).to(DEV)
+    flat = flatten_parameters(student)
+    p0 = flat.clone().cpu()
+    grad, m, v = torch.zeros_like(flat), torch.zeros_like(flat), torch.zeros_like(flat)
+    ctx = G.ctx()
+    for i in range(steps):
+        ctx.siren_face_morpher_train_step(poses[i].to(DEV), targets[i].to(DEV), mask.to(DEV), FACE_LOSS_WEIGHTS, flat, grad, False)
+        ctx.adam_step(flat, grad, m, v, lr, i + 1)
+    torch.cuda.synchronize()
+
+    grads, cur = [], p0.clone()
+    for i in range(steps):
+        off, cur_sd = 0, {}
+        for k in keys:
+            cnt = sd[k].numel()
+            cur_sd[k] = cur[off:off + cnt].view_as(sd[k])
+            off += cnt
+        _, g = distill_oracle.face_losses_and_grads(cur_sd, poses[i], targets[i], mask, FACE_LOSS_WEIGHTS)
+        grads.append(g)
+        cur = distill_oracle.adam_reference(p0, grads, lr)
+    upd, ref_upd = flat.cpu() - p0, cur - p0
+    cos = torch.nn.functional.cosine_similarity(upd, ref_upd, dim=0).item()
+    ratio = (upd.norm() / ref_upd.norm()).item()
+    print('\nface trajectory, %d steps: cosine %.5f, |update| ratio %.4f' % (steps, cos, ratio))
+    assert cos >= 0.98 and abs(ratio - 1.0) <= 0.05

@@ -145,7 +145,114 @@ def test_conv_vs_torch(case, path):
     assert mx < tol * max(1.0, ref.abs().max().item()), (case, path, mx, mean)
 
 
+@pytest.mark.parametrize('wscale', [1e-6, 1e-4, 1.0, 300.0])
+def test_conv_f16_weight_range(wscale):
+    """The f16 operand copy of a layer's weights is normalised by a power of two (conv_tc.cu, conv_make_half): a layer whose
+    weights all sit in f16's subnormal range (|w| < 6.1e-5), or beyond f16's maximum, must still convolve to TF32-class
+    accuracy.  Weights span five orders of magnitude below the layer maximum."""
+    G.ctx().set_option('tcgen05', 1)
+    G.ctx().set_option('half_operands', 1)
+    g = _gen(77)
+    x = torch.randn(1, 64, 32, 32, generator=g)
+    mag = 10.0 ** (-5.0 * torch.rand(64, 64, 3, 3, generator=g))                 # 1e-5 .. 1 of the maximum
+    w = torch.randn(64, 64, 3, 3, generator=g).sign() * mag * wscale / math.sqrt(64 * 9)
+    ref = F.conv2d(x, w, None, 1, 1)
+    out = G.conv(0, x, w, None, None, 0, 0, 0, 0)
+    mx, mean = G.err(out, ref)
+    assert mx < 6e-3 * ref.abs().max().item(), (wscale, mx, ref.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------ normalisation
+@pytest.mark.parametrize('C,H,groups,act,pool', [(64, 48, 0, 1, 0), (512, 16, 0, 0, 0), (32, 64, 32, 2, 0), (192, 16, 32, 2, 1), (384, 16, 32, 2, 0)])
+def test_norm_default_mode_f16_output(C, H, groups, act, pool):
+    """The normalisation variant the default (benchmarked) mode runs: f16 output tensor, fast-math SiLU (ex2.approx /
+    rcp.approx).  Tolerance: f16 rounding of an O(1) value (2^-11 relative) + 2 ulp of fast math."""
+    g = _gen(C * 3 + H)
+    x = torch.randn(2, C, H, H, generator=g) * 2 - 0.5
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    f0 = f1 = None
+    if groups:
+        f0, f1 = torch.randn(2 * C, generator=g) * 0.3, torch.randn(2, 2 * C, generator=g) * 0.3
+        h = F.group_norm(x, groups, gamma, beta, eps=1e-5)
+        h = O._scaleshift(O._scaleshift(h, f0.unsqueeze(0).expand(2, -1)), f1)
+    else:
+        h = F.instance_norm(x, weight=gamma, bias=beta, eps=1e-5)
+    ref = {0: h, 1: F.relu(h), 2: F.silu(h)}[act]
+    if pool:
+        ref = F.avg_pool2d(ref, 2, 2)
+    out = G.norm(x, groups, gamma, beta, f0, f1, act=act, pool=pool, out_f16=1)
+    d = (out - ref).abs()
+    assert (d <= 6e-4 * ref.abs() + 2e-5).all(), (d.max().item(), (d / (ref.abs() + 1e-3)).max().item())
+
+
+# ------------------------------------------------------------------------------------------ fused decoder tails
+def _tail_reference(kind, feature, gamma, beta, groups, act, ws, bs, image0, image1):
+    """The reference's own ops for one tail site (eyebrow_decomposer_00.py:49-64, eyebrow_morphing_combiner_00.py:51-72,
+    face_morpher_08.py:170-193, morpher_00.py:53-66), restated on the raw last feature map."""
+    h = F.group_norm(feature, groups, gamma, beta, eps=1e-5) if groups else F.instance_norm(feature, weight=gamma, bias=beta, eps=1e-5)
+    h = F.relu(h) if act == 1 else F.silu(h)
+    heads = [F.conv2d(h, w, b, 1, 1) for w, b in zip(ws, bs)]
+    if kind == 0:
+        return O._unet_tail(heads[0], image0)
+    if kind == 1:
+        bga, bgc, eba, ebc = torch.sigmoid(heads[0]), torch.tanh(heads[1]), torch.sigmoid(heads[2]), torch.tanh(heads[3])
+        return [O.apply_color_change(eba, image0, ebc), eba, ebc, O.apply_color_change(bga, bgc, image0), bga, bgc]
+    if kind == 2:
+        gc, alpha, color, ca = heads[0], torch.sigmoid(heads[1]), torch.tanh(heads[2]), torch.sigmoid(heads[3])
+        warped = O.apply_grid_change(gc, image0)
+        morphed = O.apply_color_change(alpha, color, warped)
+        return [O.apply_rgb_change(ca, morphed, image1), ca, O.apply_rgb_change((morphed[:, 3:4] + 1.0) / 2.0, morphed, image1),
+                morphed, alpha, color, warped, gc]
+    gc, imc, ima, eyc, eya = heads[0], torch.tanh(heads[1]), torch.sigmoid(heads[2]), torch.tanh(heads[3]), torch.sigmoid(heads[4])
+    im0 = O.apply_grid_change(gc, image0)
+    im1 = O.apply_color_change(ima, imc, im0)
+    return [O.apply_color_change(eya, eyc, im1), eya, eyc, im1, ima, imc, im0, gc]
+
+
+TAIL_SITES = [
+    # kind, C, S, groups, act, head couts (tail.cu order), which heads have a bias
+    (0, 32, 512, 32, 2, [7], [True]),                              # Upscaler02 (upscaler_02.py:84-96)
+    (0, 64, 256, 32, 2, [7], [True]),                              # Morpher00 (morpher_00.py:53-66)
+    (1, 64, 128, 0, 1, [1, 4, 1, 4], [True] * 4),                  # EyebrowDecomposer00
+    (2, 64, 128, 0, 1, [2, 1, 4, 1], [False, True, True, True]),   # EyebrowMorphingCombiner00
+    (3, 64, 192, 0, 1, [2, 4, 1, 4, 1], [False, True, True, True, True]),   # FaceMorpher08
+]
+
+
+@pytest.mark.parametrize('site', TAIL_SITES)
+@pytest.mark.parametrize('strict', [0, 1])
+def test_tail_site_vs_reference_ops(site, strict):
+    """Every fused 'grid_sample + decoder' site in isolation, in the default (benchmarked) mode and in strict mode.
+    Head weights have trained-like scales (colour ~0.2, warps of a few pixels) so that the warp of a smooth image is a
+    well-conditioned function of the head outputs.  Default-mode tolerance: 10-bit operands of a 9*C-term dot product
+    (~2e-4 of the head output scale) seen through sigmoid / tanh / a bilinear warp of a smooth image."""
+    kind, C, S, groups, act, couts, has_b = site
+    g = _gen(kind * 1000 + C + S)
+    N = 2 if S <= 256 else 1
+    feature = torch.randn(N, C, S, S, generator=g) * 1.5 + 0.3
+    gamma, beta = 1.0 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    ws, bs = [], []
+    for co, hb in zip(couts, has_b):
+        w = torch.randn(co, C, 3, 3, generator=g) / math.sqrt(9 * C)
+        if not hb or (kind == 0):
+            w = w * 0.3
+        if not hb:
+            w = w * 0.1                                               # grid_change heads: offsets of ~0.02 (a few pixels)
+        ws.append(w)
+        bs.append(0.1 * torch.randn(co, generator=g) if hb else None)
+    if kind == 0:
+        ws[0][4:6] *= 0.1
+    image0 = synth.synthetic_image(kind + 3, N)[:, :, :S, :S].contiguous()
+    image1 = synth.synthetic_image(kind + 9, N)[:, :, :S, :S].contiguous() if kind == 2 else None
+    with torch.no_grad():
+        refs = _tail_reference(kind, feature, gamma, beta, groups, act, ws, bs, image0, image1)
+    outs = G.tail(kind, feature, gamma, beta, groups, act, ws, bs, image0, image1, strict=strict)
+    max_tol, mean_tol = (2e-4, 1e-5) if strict else (6e-3, 3e-4)
+    for i, (a, b) in enumerate(zip(outs, refs)):
+        mx, mean = G.err(a, b)
+        assert mx <= max_tol and mean <= mean_tol, (site, strict, i, mx, mean)
+
+
 @pytest.mark.parametrize('C,H', [(64, 48), (512, 16), (128, 24)])
 def test_instance_norm_relu(C, H):
     g = _gen(C + H)

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     'tha4_teacher_forward', 'tha4_student_forward', 'tha4_siren_morpher_param_count', 'tha4_siren_morpher_train_step',
     'tha4_siren_face_morpher_param_count', 'tha4_siren_face_morpher_train_step',
     'tha4_adam_step', 'tha4_images_differ', 'tha4_grid_sample', 'tha4_resize_bilinear',
-    'tha4_base_grid', 'tha4_test_conv', 'tha4_test_norm', 'tha4_test_attention', 'tha4_test_linear',
+    'tha4_base_grid', 'tha4_test_conv', 'tha4_test_norm', 'tha4_test_tail', 'tha4_test_attention', 'tha4_test_linear',
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ class Context:
             raise Tha4Error('tha4_ctx_create failed: %s' % self.lib.tha4_last_error(None).decode())
         self.handle = handle
         self.loaded: Dict[str, object] = {}
+        self.epoch = 0                       # bumped whenever options or weights change: results cached by callers are stale
         self.modules = weakref.WeakSet()     # NativeModules whose weights live in this context
 
     def __del__(self):
@@ -116,6 +117,7 @@ class Context:
 
     def set_option(self, name: str, value: int):
         self._call('tha4_set_option', name.encode(), int(value))
+        self.epoch += 1
         if name == 'strict':      # weight packing depends on it (TF32-rounded vs exact fp32): re-upload lazily
             for m in list(self.modules):
                 m._uploaded_key = None
@@ -141,6 +143,7 @@ class Context:
                        self._stream())
             torch.cuda.current_stream(self.device).synchronize()
         self.loaded[net] = True
+        self.epoch += 1
 
     def _empty(self, specs, B: int) -> List[Tensor]:
         return [torch.empty((B, c, s, s), dtype=torch.float32, device=self.device) for c, s in specs]
@@ -226,9 +229,15 @@ class Context:
 
     def teacher_forward(self, mode: int, image: Tensor, pose: Tensor, eyebrow_morphed_image_index: int = 2,
                         cached_decomposer: Optional[List[Tensor]] = None) -> List[Tensor]:
-        image = _check_input(image, self.device, 'image')
-        pose = _check_input(pose, self.device, 'pose')
         B = image.shape[0]
+        if B > 1 and image.stride(0) == 0 and image[0].is_contiguous():
+            # ONE image posed B times (image.expand(B, ...)): the library reads it with batch stride 0, no B-fold copy
+            image0 = _check_input(image[0], self.device, 'image')
+            img_ptr, img_stride, keep = _ptr(image0), 0, image0
+        else:
+            image = _check_input(image, self.device, 'image')
+            img_ptr, img_stride, keep = _ptr(image), 4 * 512 * 512, image
+        pose = _check_input(pose, self.device, 'pose')
         assert image.shape[1:] == (4, 512, 512) and pose.shape == (B, 45)
         specs = self.TEACHER_SPECS[mode] + self.FACE_COMB_DEC
         n = len(specs)
@@ -238,8 +247,9 @@ class Context:
         else:
             outs = self._empty(specs[:n - 6], B) + list(cached_decomposer)
             cached = _ptr_array(cached_decomposer)
-        self._call('tha4_teacher_forward', mode, _ptr(image), _ptr(pose), B, _ptr_array(outs), eyebrow_morphed_image_index,
-                   cached, self._stream())
+        self._call('tha4_teacher_forward', mode, img_ptr, ctypes.c_int64(img_stride), _ptr(pose), B, _ptr_array(outs),
+                   eyebrow_morphed_image_index, cached, self._stream())
+        del keep
         return outs
 
     def student_forward(self, image: Tensor, pose: Tensor) -> List[Tensor]:

@@ -105,11 +105,7 @@ bool g_attn_split16 = false;
 template <int QPB, int KSPLIT, int DP>
 void launch_attention(const View& qkv, int heads, const View& out, cudaStream_t s) {
     const size_t smem = 2 * L * DP * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<QPB, KSPLIT, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    THA4_ENSURE_SMEM((attention_kernel<QPB, KSPLIT, DP>), smem);
     attention_kernel<QPB, KSPLIT, DP><<<qkv.N * heads * (L / QPB), QPB * KSPLIT, smem, s>>>(qkv.p, qkv.ld, out.C, heads, out.p, out.ld);
     THA4_LAUNCH_CHECK();
 }

@@ -96,14 +96,15 @@ Runtime make_rt(tha4_ctx* ctx, void* stream) {
 }
 
 // one micro-batch of the teacher pipeline (mode_07.py:72-132 / mode_12.py:66-94)
-void teacher_chunk(tha4_ctx* ctx, Runtime& rt, int mode, const float* image, const float* pose, int b, float* const* out,
+void teacher_chunk(tha4_ctx* ctx, Runtime& rt, int mode, const float* image, long image_sn, const float* pose, int b, float* const* out,
                    int eyebrow_index, const float* const* cached) {
     cudaStream_t s = rt.stream;
     const int base = (mode == 7) ? 11 : 0;          // index of face_morpher outputs
     float* const* o_face = out + base;
     float* const* o_comb = out + base + 8;
     float* const* o_dec = out + base + 16;
-    const ImgView img = make_img(image, b, 4, 512, 512);
+    ImgView img = make_img(image, b, 4, 512, 512);
+    img.sn = image_sn;                               // 0: one image posed b times (pose sweep), no replicated copies
     THA4_REQUIRE(eyebrow_index >= 0 && eyebrow_index < 8 && eyebrow_index != 1 && eyebrow_index != 4 && eyebrow_index != 7,
                  "eyebrow_morphed_image_index must select a 4-channel combiner output");
     const float* dec[6];
@@ -367,10 +368,12 @@ int tha4_siren_morpher_forward(tha4_ctx* ctx, const float* image, const float* p
 }
 
 // ------------------------------------------------------------------------------------------------ poser level
-int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, const float* pose, int B, float* const* outputs,
-                         int eyebrow_morphed_image_index, const float* const* cached_decomposer, void* stream) {
+int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, int64_t image_batch_stride, const float* pose, int B,
+                         float* const* outputs, int eyebrow_morphed_image_index, const float* const* cached_decomposer, void* stream) {
     return guarded(ctx, [&] {
         THA4_REQUIRE(mode == 7 || mode == 12, "teacher mode must be 7 or 12");
+        THA4_REQUIRE(image_batch_stride == 0 || image_batch_stride == 4L * 512 * 512, "image batch stride must be 0 (one image, B poses) or 4*512*512");
+        const long img_sn = (long)image_batch_stride;
         Runtime rt = make_rt(ctx, stream);
         OutSpec spec[33];
         int n = 0;
@@ -390,13 +393,13 @@ int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, const floa
                 const float* cd[6];
                 if (cached_p)
                     for (int i = 0; i < 6; ++i) cd[i] = cached_p[i] + (size_t)n0 * kEncDecDecomposer[i].c * 128 * 128;
-                teacher_chunk(ctx, rt, mode, img_p + (size_t)n0 * 4 * 512 * 512, pose_p + (size_t)n0 * 45, b, o,
+                teacher_chunk(ctx, rt, mode, img_p + (size_t)n0 * img_sn, img_sn, pose_p + (size_t)n0 * 45, b, o,
                               eyebrow_morphed_image_index, cached_p ? cd : nullptr);
             });
         };
         // ---- CUDA-graph path: single-chunk calls, from the second identical call on ----
         cudaStream_t s = rt.stream;
-        if (ctx->use_graphs && B <= ctx->microbatch && !prof_enabled()) {
+        if (ctx->use_graphs && B <= ctx->microbatch && !prof_enabled() && img_sn != 0) {
             TeacherGraph& g = ctx->graphs[std::make_tuple(mode, B, eyebrow_morphed_image_index, cached_decomposer ? 1 : 0)];
             if (!g.failed && ++g.calls >= 2) {
                 if (!g.image) {
@@ -592,7 +595,7 @@ int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, cons
 }
 
 int tha4_test_norm(tha4_ctx* ctx, const float* x, int N, int C, int H, int W, int groups, const float* gamma,
-                   const float* beta, const float* film0, const float* film1, int act, int pool, float* y, void* stream) {
+                   const float* beta, const float* film0, const float* film1, int act, int pool, int out_f16, float* y, void* stream) {
     return guarded(ctx, [&] {
         cudaStream_t s = (cudaStream_t)stream;
         begin_pass(ctx, s);
@@ -606,8 +609,50 @@ int tha4_test_norm(tha4_ctx* ctx, const float* x, int N, int C, int H, int W, in
         View yo = xin; yo.stats = nullptr;
         if (pool) { yo.H = H / 2; yo.W = W / 2; }
         yo.p = P->alloc((size_t)N * yo.H * yo.W * C);
-        norm_apply_fused(xin, groups, gamma, beta, film0, film1, 2 * C, act, pool, nullptr, yo, s, 0);
+        if (out_f16) {     // the variant the default mode runs: f16 output (operand of a tcgen05 conv), fast-math SiLU
+            View y16 = yo; y16.f16 = 1; y16.p = P->alloc(((size_t)N * yo.H * yo.W * C + 1) / 2);
+            norm_apply_fused(xin, groups, gamma, beta, film0, film1, 2 * C, act == ACT_SILU ? ACT_SILU_FAST : act, pool, nullptr, y16, s, 1);
+            convert_f32(y16, yo, s);
+        } else {
+            norm_apply_fused(xin, groups, gamma, beta, film0, film1, 2 * C, act, pool, nullptr, yo, s, 0);
+        }
         nhwc_to_nchw(yo, y, s);
+    });
+}
+
+int tha4_test_tail(tha4_ctx* ctx, int kind, const float* feature, int N, int C, int S, const float* gamma, const float* beta,
+                   int groups, int act, const float* head_w, const float* head_b, const int* head_cout, int n_heads,
+                   const float* image0, const float* image1, float* const* outputs, int strict, void* stream) {
+    return guarded(ctx, [&] {
+        cudaStream_t s = (cudaStream_t)stream;
+        begin_pass(ctx, s);
+        Runtime rt = make_rt(ctx, stream);
+        rt.strict = strict;
+        Pool* P = &ctx->persist;
+        View f; f.N = N; f.H = S; f.W = S; f.C = C; f.ld = C; f.p = P->alloc((size_t)N * S * S * C);
+        f.stats_rep = 2; f.stats_rep_stride = (long)N * C * 2;
+        f.stats = rt.alloc_stats((size_t)2 * N * C * 2); f.stats_ld = C;
+        nchw_to_nhwc(make_img(feature, N, C, S, S), f, s);
+        norm_stats(f, s);
+        float* coef = P->alloc((size_t)N * C * 2);
+        norm_finalize(f, groups, gamma, beta, nullptr, nullptr, 0, coef, s);
+        AllocSink sink;
+        TailWeights tw;
+        {
+            SinkScope own(&sink);
+            tail_init(tw, C, s);
+            size_t woff = 0, boff = 0;
+            for (int i = 0; i < n_heads; ++i) {
+                const bool has_b = head_b != nullptr && !((kind == TAIL_COMBINER || kind == TAIL_FACE) && i == 0);   // grid_change heads have no bias
+                tail_add(tw, head_w + woff, has_b ? head_b + boff : nullptr, head_cout[i], s);
+                woff += (size_t)head_cout[i] * C * 9; boff += head_cout[i];
+            }
+        }
+        const int a = (act == ACT_SILU && !strict) ? ACT_SILU_FAST : act;
+        const ImgView i0 = make_img(image0, N, 4, S, S);
+        const ImgView i1 = image1 ? make_img(image1, N, 4, S, S) : ImgView{};
+        tail_forward((TailKind)kind, tw, f, coef, a, i0, i1, outputs, s, strict);
+        THA4_CUDA_CHECK(cudaStreamSynchronize(s));       // `sink` frees the head weights on return
     });
 }
 

@@ -71,6 +71,20 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
         THA4_CUDA_CHECK(cudaGetLastError());                                                      \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device property: every call site keeps what it has already
+// configured per device (a process may hold contexts on several GPUs), not per process.
+constexpr int THA4_MAX_DEVICES = 64;
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= THA4_MAX_DEVICES ? 0 : d; }
+#define THA4_ENSURE_SMEM(kernel, bytes)                                                           \
+    do {                                                                                          \
+        static size_t _cfg[tha4::THA4_MAX_DEVICES] = {};                                          \
+        const int _d = tha4::current_device();                                                    \
+        if (_cfg[_d] < (size_t)(bytes)) {                                                         \
+            THA4_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _cfg[_d] = (size_t)(bytes);                                                           \
+        }                                                                                         \
+    } while (0)
+
 #define THA4_REQUIRE(cond, msg)                                                                   \
     do {                                                                                          \
         if (!(cond)) throw std::runtime_error(std::string("tha4: ") + (msg) + " [" #cond "] at " + \

@@ -262,12 +262,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_igemm_kernel(const ConvKernelPa
 template <int BN, int WM, int WN, int STAGES>
 void launch_conv(const ConvKernelParams& p, dim3 grid, cudaStream_t s) {
     constexpr size_t smem = (size_t)STAGES * (BM + BN) * PITCH * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, WM, WN, STAGES>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    THA4_ENSURE_SMEM((conv_igemm_kernel<BN, WM, WN, STAGES>), smem);
     conv_igemm_kernel<BN, WM, WN, STAGES><<<grid, NTHREADS, smem, s>>>(p);
     THA4_LAUNCH_CHECK();
 }
@@ -354,7 +349,7 @@ void conv_describe(ConvWeights& cw, ConvKind kind, int cin, int cout) {
     }
 }
 
-static bool g_pack_round = true;
+static thread_local bool g_pack_round = true;   // set by the caller right before it packs (tha4_load_net): per thread, not per process
 void conv_set_pack_rounding(bool r) { g_pack_round = r; }
 bool conv_pack_rounding() { return g_pack_round; }
 

@@ -19,6 +19,8 @@ enum ResMode { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2, RES_DOWN2 = 3 };
 struct ConvWeights {
     float* w = nullptr;
     mutable __half* w16 = nullptr;   // same layout in f16, made on first use with f16 activations (conv_tc.cu)
+    mutable float w16_scale = 1.0f;  // power of two the f16 copy was multiplied by (max |w| normalised into [0.5, 1): a layer of
+                                     // tiny weights would otherwise land in f16's subnormal range); undone on the accumulator
     float* bias = nullptr;      // [cout] or nullptr
     int cin = 0, cout = 0, cin_pad = 0, cout_pad = 0;
     int ntaps = 0, nphase = 1;

@@ -22,7 +22,9 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <map>
+#include <mutex>
 #include <tuple>
 
 namespace tha4 {
@@ -40,6 +42,7 @@ struct TcParams {
     int N, MH, MW, tiles_x, tiles_y;
     int ntaps, cpt, ksplit, out_mul, in_mul;       // in_mul: input stride (2 for the 4x4 stride-2 conv: element-strided TMA boxes)
     int pre_b;                                     // weight tiles may be fetched before the programmatic-dependency wait
+    float acc_scale;                               // accumulator scale (undoes the power-of-two normalisation of the f16 weights)
     float* ws; long ws_rows; int ws_ld;            // split-K partials: ws[z][tile*128 + row][cout_pad]
     double* stats; int stats_ld; int stats_rep; long stats_rep_stride;   // per-(n,c) sum / sum-of-squares of the output (optional)
     signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 if (cbase >= p.outC) continue;                         // warp-uniform
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.acc_scale;
                 const int cn = min(32, p.outC - cbase);
                 const bool to_ws = p.ksplit > 1 && p.ws;
                 if (valid) {
@@ -293,6 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                     asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                 }
+                acc.x *= p.acc_scale; acc.y *= p.acc_scale; acc.z *= p.acc_scale; acc.w *= p.acc_scale;
                 const int my = y0 + row / TILE_W, mx = x0 + row % TILE_W;
                 if (my >= p.MH || mx >= p.MW || col >= p.outC) continue;
                 const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcParams p, in
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
             const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
-            float v[4] = {acc.x, acc.y, acc.z, acc.w};
+            float v[4] = {acc.x, acc.y, acc.z, acc.w};      // partials were scaled (acc_scale) by the producing CTAs
             if (p.bias) for (int j = 0; j < cn; ++j) v[j] += __ldg(p.bias + c + j);
             if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
                 const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
@@ -443,11 +447,16 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-using MapKey = std::tuple<const void*, long, long, long, long, long, int>;
+// Encoded tensor maps are cached process-wide, keyed by (device, base pointer, geometry); the cache is shared by every
+// context of the process (contexts may be driven from different host threads: ctypes releases the GIL), hence the lock.
+// std::map nodes are stable, so the returned references stay valid after the lock is dropped.
+using MapKey = std::tuple<int, const void*, long, long, long, long, long, int>;
 std::map<MapKey, CUtensorMap> g_maps;
+std::mutex g_maps_mu;
 
 const CUtensorMap& activation_map(const View& v, int op, int stride) {
-    MapKey key{v.p, v.N, v.H, v.W, v.C, v.ld, -(1 + 4 * op + 16 * stride)};
+    MapKey key{current_device(), v.p, v.N, v.H, v.W, v.C, v.ld, -(1 + 4 * op + 16 * stride)};
+    std::lock_guard<std::mutex> lock(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) return it->second;
     CUtensorMap m;
@@ -467,7 +476,8 @@ const CUtensorMap& activation_map(const View& v, int op, int stride) {
 
 const CUtensorMap& weight_map(const ConvWeights& cw, int bn, int op) {
     const void* wp = op == OP_TF32 ? (const void*)cw.w : (const void*)cw.w16;
-    MapKey key{wp, cw.cin_pad, cw.cout_pad, cw.ntaps, cw.nphase, op, bn};
+    MapKey key{current_device(), wp, cw.cin_pad, cw.cout_pad, cw.ntaps, cw.nphase, op, bn};
+    std::lock_guard<std::mutex> lock(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) return it->second;
     CUtensorMap m;
@@ -491,11 +501,7 @@ void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static_assert((size_t)STAGES * STAGE_BYTES >= (size_t)4 * 32 * 33 * 4 + 4 * BN * 8, "epilogue scratch must fit in the pipeline buffers");
     static_assert(CS == 1 || (size_t)STAGES * STAGE_BYTES >= (size_t)128 * BN * 4 + 128 * 8 * 4 + 128 * 4, "partial tile + statistics scratch must fit");
-    static bool configured = false;
-    if (!configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES_, CS, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    THA4_ENSURE_SMEM((conv_tc_kernel<BN, STAGES_, CS, OP>), smem);
     launch_pdl(conv_tc_kernel<BN, STAGES_, CS, OP>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, p);
     THA4_LAUNCH_CHECK();
 }
@@ -534,9 +540,17 @@ void launch_variants(bool cluster, int stages_mode, int bn, int ksplit, const CU
     }
 }
 
-// fp32 packed weights -> f16 (the packed values were already rounded to 10 mantissa bits, so this is exact in range)
-__global__ void pack_half_kernel(const float* __restrict__ w, __half* __restrict__ h, long n) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) h[i] = __float2half_rn(w[i]);
+// fp32 packed weights -> f16, scaled by a power of two chosen so that max |w| lands in [0.5, 1): the scaling is exact,
+// keeps a layer of small weights out of f16's subnormal range (|w| < 6.1e-5 would lose mantissa bits) and is undone
+// on the fp32 accumulator (TcParams::acc_scale).  The packed values were already rounded to 10 mantissa bits.
+__global__ void pack_half_kernel(const float* __restrict__ w, __half* __restrict__ h, long n, float scale) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) h[i] = __float2half_rn(w[i] * scale);
+}
+__global__ void absmax_kernel(const float* __restrict__ w, long n, unsigned* __restrict__ out) {
+    float m = 0.0f;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));          // non-negative floats order like their bit patterns
 }
 
 int op_for(const ConvWeights& cw, const ConvArgs& a) {
@@ -606,9 +620,24 @@ void conv_make_half(const ConvWeights& cw, cudaStream_t s) {
     if (cw.w16 || !cw.w) return;
     const long nw = (long)conv_packed_floats(cw);
     __half* h = reinterpret_cast<__half*>(tracked_malloc(nw * sizeof(__half)));
-    pack_half_kernel<<<(int)std::min<long>((nw + 255) / 256, 1184), 256, 0, s>>>(cw.w, h, nw);
+    const int blocks = (int)std::min<long>((nw + 255) / 256, 1184);
+    unsigned* dmax = reinterpret_cast<unsigned*>(h);                          // scratch: the first word of the (not yet written) copy
+    THA4_CUDA_CHECK(cudaMemsetAsync(dmax, 0, sizeof(unsigned), s));
+    absmax_kernel<<<blocks, 256, 0, s>>>(cw.w, nw, dmax);
     THA4_LAUNCH_CHECK();
-    cw.w16 = h;
+    unsigned hmax = 0;
+    THA4_CUDA_CHECK(cudaMemcpyAsync(&hmax, dmax, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    THA4_CUDA_CHECK(cudaStreamSynchronize(s));                                // load time (or the first call of a test conv)
+    float mx; memcpy(&mx, &hmax, sizeof(float));
+    float scale = 1.0f;
+    if (mx > 0.0f && std::isfinite(mx)) {
+        int e = 0; frexpf(mx, &e);                                             // mx = f * 2^e, f in [0.5, 1)
+        e = std::max(-24, std::min(8, e));
+        scale = ldexpf(1.0f, -e);
+    }
+    pack_half_kernel<<<blocks, 256, 0, s>>>(cw.w, h, nw, scale);
+    THA4_LAUNCH_CHECK();
+    cw.w16 = h; cw.w16_scale = scale;
 }
 
 void conv_tc_enable_cluster(bool on) { g_use_cluster = on; }
@@ -648,10 +677,12 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     const int op = op_for(cw, a);
     p.pre_b = cw.dynamic ? 0 : 1;            // static (loaded once) weights only
     p.ntaps = cw.ntaps; p.cpt = cw.cin_pad / op_kch(op);
+    p.acc_scale = 1.0f;
     if (op != OP_TF32 && !cw.w16) {          // first use with f16 activations and no copy made at load time
         conv_make_half(cw, s);
         p.pre_b = 0;                          // written by the kernel just launched: order through the dependency wait
     }
+    if (op != OP_TF32) p.acc_scale = 1.0f / cw.w16_scale;
     for (int ph = 0; ph < CONV_MAX_PHASES; ++ph) {
         p.ph_oy[ph] = cw.ph_oy[ph]; p.ph_ox[ph] = cw.ph_ox[ph];
         for (int t = 0; t < CONV_MAX_TAPS; ++t) { p.dy[ph][t] = cw.dy[ph][t]; p.dx[ph][t] = cw.dx[ph][t]; }

@@ -4,6 +4,7 @@
 #include "ops.cuh"
 #include "gridsample.cuh"
 #include <map>
+#include <mutex>
 #include <vector>
 
 namespace tha4 {
@@ -62,6 +63,14 @@ __global__ void convert_f16_kernel(const float* __restrict__ src, int src_ld, __
         const int c = (int)(i % C);
         const long pix = i / C;
         dst[pix * dst_ld + c] = __float2half_rn(src[pix * src_ld + c]);
+    }
+}
+
+__global__ void convert_f32_kernel(const __half* __restrict__ src, int src_ld, float* __restrict__ dst, int dst_ld, int C, long total) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const long pix = i / C;
+        dst[pix * dst_ld + c] = __half2float(src[pix * src_ld + c]);
     }
 }
 
@@ -159,15 +168,19 @@ void base_grid_host(int W, float* out) {
 }
 
 const float* base_grid_table(int size) {
-    static std::map<int, float*> tables;
-    auto it = tables.find(size);
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, float*> all_tables;      // (device, size): device pointers are per device
+    std::lock_guard<std::mutex> lock(mu);
+    const std::pair<int, int> key(current_device(), size);
+    auto& tables = all_tables;
+    auto it = tables.find(key);
     if (it != tables.end()) return it->second;
     std::vector<float> h(size);
     base_grid_host(size, h.data());
     float* d = nullptr;
     THA4_CUDA_CHECK(cudaMalloc(&d, size * sizeof(float)));
     THA4_CUDA_CHECK(cudaMemcpy(d, h.data(), size * sizeof(float), cudaMemcpyHostToDevice));
-    tables[size] = d;
+    tables[key] = d;
     return d;
 }
 
@@ -198,6 +211,13 @@ void convert_f16(const View& src, const View& dst, cudaStream_t s) {
     THA4_REQUIRE(!src.f16 && dst.f16 && src.C == dst.C && src.pixels() == dst.pixels(), "convert_f16: views");
     const long total = (long)src.pixels() * src.C;
     convert_f16_kernel<<<grid_for(total), 256, 0, s>>>(src.p, src.ld, dst.hp(), dst.ld, src.C, total);
+    THA4_LAUNCH_CHECK();
+}
+
+void convert_f32(const View& src, const View& dst, cudaStream_t s) {
+    THA4_REQUIRE(src.f16 && !dst.f16 && src.C == dst.C && src.pixels() == dst.pixels(), "convert_f32: views");
+    const long total = (long)src.pixels() * src.C;
+    convert_f32_kernel<<<grid_for(total), 256, 0, s>>>(src.hp(), src.ld, dst.p, dst.ld, src.C, total);
     THA4_LAUNCH_CHECK();
 }
 

@@ -86,34 +86,12 @@ ConvWeights load_conv(const StateDict& sd, const std::string& prefix, ConvKind k
     return cw;
 }
 
-__global__ void tail_pack_kernel(float* w, float* b, const float* src_w, const float* src_b, int C, int cout, int co_off) {
-    const int total = cout * C * 9;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int tap = i % 9;
-        const int c = (i / 9) % C;
-        const int co = i / (9 * C);
-        w[(tap * C + c) * TAIL_CO_PAD + co_off + co] = src_w[i];
-    }
-    if (src_b && blockIdx.x == 0 && threadIdx.x < cout) b[co_off + threadIdx.x] = src_b[threadIdx.x];
-}
-
-void tail_init(TailWeights& tw, int C, cudaStream_t s) {
-    tw.C = C; tw.CO = 0;
-    tw.w = dev_alloc((size_t)9 * C * TAIL_CO_PAD);
-    tw.bias = dev_alloc(TAIL_CO_PAD);
-    THA4_CUDA_CHECK(cudaMemsetAsync(tw.w, 0, (size_t)9 * C * TAIL_CO_PAD * sizeof(float), s));
-    THA4_CUDA_CHECK(cudaMemsetAsync(tw.bias, 0, TAIL_CO_PAD * sizeof(float), s));
-}
-
 void tail_add_head(TailWeights& tw, const StateDict& sd, const std::string& prefix, bool bias, cudaStream_t s) {
     const TensorRef& w = sd_get(sd, prefix + ".weight");
     THA4_REQUIRE(w.shape.size() == 4 && w.shape[1] == tw.C && w.shape[2] == 3 && w.shape[3] == 3, "head shape: " + prefix);
     const int cout = (int)w.shape[0];
-    THA4_REQUIRE(tw.CO + cout <= TAIL_CO_PAD, "too many head channels");
     const float* b = bias ? sd_get(sd, prefix + ".bias").p : nullptr;
-    tail_pack_kernel<<<32, 256, 0, s>>>(tw.w, tw.bias, w.p, b, tw.C, cout, tw.CO);
-    THA4_LAUNCH_CHECK();
-    tw.CO += cout;
+    tail_add(tw, w.p, b, cout, s);
 }
 
 __global__ void vec_add_kernel(float* dst, const float* a, const float* b, int n) {

@@ -45,6 +45,7 @@ void nhwc_to_nchw(const View& src, float* dst, cudaStream_t s);                 
 void copy_window(const ImgView& src, float* dst, long dn, long dc, long dh, cudaStream_t s);  // strided NCHW copy
 void tile_vector(const float* vec, int vec_ld, int P, const View& dst, cudaStream_t s); // dst[n,y,x,c] = c<P ? vec[n][c] : 0  (dst fp32 or f16)
 void convert_f16(const View& src, const View& dst, cudaStream_t s);                      // fp32 view -> f16 view (tests)
+void convert_f32(const View& src, const View& dst, cudaStream_t s);                      // f16 view -> fp32 view (tests)
 void resize_bilinear(const ImgView& src, float* dst, int Ho, int Wo, cudaStream_t s);   // align_corners=False
 void grid_sample(const ImgView& image, const float* grid_change, float* out, int* x0, int* y0, float* tx, float* ty,
                  cudaStream_t s);                                                        // any output may be null
@@ -68,6 +69,10 @@ struct TailWeights {
     int C = 0, CO = 0;
 };
 constexpr int TAIL_CO_PAD = 12;
+// Head weights: tail_init allocates zeroed storage (recorded in the active AllocSink), tail_add appends one reference
+// head conv (weight [cout, C, 3, 3], bias [cout] or nullptr) in the channel order the kernel expects for its kind.
+void tail_init(TailWeights& tw, int C, cudaStream_t s);
+void tail_add(TailWeights& tw, const float* w_ref, const float* b_ref, int cout, cudaStream_t s);
 // feature: raw conv output NHWC; coef: per-(n,c) affine from norm_finalize; act: ReLU (enc-dec) or SiLU (U-Net).
 // image0: the image that is warped / blended (NCHW view); image1: second image (combiner: background layer).
 // outputs: NCHW contiguous, order/meaning per kind (see tail.cu).

@@ -494,8 +494,7 @@ void SirenFaceNet::forward(Runtime& rt, const float* pose, int pose_ld, int B, f
     for (int i = 1; i < 8; ++i) L.l[i] = lw(layers_[i]);
     L.head = lw(head_);
     using SM = Smem<128, 128, 3>;
-    static bool cfg = false;
-    if (!cfg) { set_smem(siren_face_kernel, SM::bytes); cfg = true; }
+    THA4_ENSURE_SMEM(siren_face_kernel, SM::bytes);
     ProfScope prof(PROF_SIREN, rt.stream);
     siren_face_kernel<<<B * R * (R / TP), NTHREADS, SM::bytes, rt.stream>>>(L, layers_[0].NPAD, base_grid_table(R), R, out);
     THA4_LAUNCH_CHECK();
@@ -532,13 +531,9 @@ void SirenBodyNet::forward(Runtime& rt, const ImgView& image, const float* pose,
     using SM0 = Smem<384, 384, 2>;
     using SM1 = Smem<192, 192, 3>;
     using SM2 = Smem<96, 96, 3>;
-    static bool cfg = false;
-    if (!cfg) {
-        set_smem(siren_body_l0_kernel, SM0::bytes);
-        set_smem(siren_body_l1_kernel, SM1::bytes);
-        set_smem(siren_body_l2_kernel, SM2::bytes);
-        cfg = true;
-    }
+    THA4_ENSURE_SMEM(siren_body_l0_kernel, SM0::bytes);
+    THA4_ENSURE_SMEM(siren_body_l1_kernel, SM1::bytes);
+    THA4_ENSURE_SMEM(siren_body_l2_kernel, SM2::bytes);
     ProfScope prof(PROF_SIREN, s);
     siren_body_l0_kernel<<<B * 128 * (128 / TP), NTHREADS, SM0::bytes, s>>>(lw(l_[0][0], pb0), lw(l_[0][1]), lw(l_[0][2]), 384,
                                                                           base_grid_table(128), 128, f0);

@@ -271,11 +271,7 @@ void launch_tail(const TailWeights& tw, const View& f, const float* coef, int ac
     THA4_REQUIRE(tw.C % 8 == 0 && tw.CO <= NT * 8, "tail: head channel layout");
     const size_t halo = (size_t)HALO_H * HALO * (tw.C + 4), outs = (size_t)TILE * TILE_H * OPITCH;
     const size_t smem = ((size_t)9 * tw.C * wpitch(NT) + std::max(halo, outs)) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        THA4_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel<KIND, NT, STRICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    THA4_ENSURE_SMEM((tail_kernel<KIND, NT, STRICT>), smem);
     float* op[8];
     for (int i = 0; i < 8; ++i) op[i] = i < nout ? o[i] : nullptr;
     dim3 grid(f.W / TILE, f.H / TILE_H, f.N);
@@ -290,7 +286,33 @@ void launch_tail(const TailWeights& tw, const View& f, const float* coef, int ac
     THA4_LAUNCH_CHECK();
 }
 
+__global__ void tail_pack_kernel(float* w, float* b, const float* src_w, const float* src_b, int C, int cout, int co_off) {
+    const int total = cout * C * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9;
+        const int c = (i / 9) % C;
+        const int co = i / (9 * C);
+        w[(tap * C + c) * TAIL_CO_PAD + co_off + co] = src_w[i];
+    }
+    if (src_b && blockIdx.x == 0 && threadIdx.x < cout) b[co_off + threadIdx.x] = src_b[threadIdx.x];
+}
+
 }  // namespace
+
+void tail_init(TailWeights& tw, int C, cudaStream_t s) {
+    tw.C = C; tw.CO = 0;
+    tw.w = reinterpret_cast<float*>(tracked_malloc((size_t)9 * C * TAIL_CO_PAD * sizeof(float)));
+    tw.bias = reinterpret_cast<float*>(tracked_malloc(TAIL_CO_PAD * sizeof(float)));
+    THA4_CUDA_CHECK(cudaMemsetAsync(tw.w, 0, (size_t)9 * C * TAIL_CO_PAD * sizeof(float), s));
+    THA4_CUDA_CHECK(cudaMemsetAsync(tw.bias, 0, TAIL_CO_PAD * sizeof(float), s));
+}
+
+void tail_add(TailWeights& tw, const float* w_ref, const float* b_ref, int cout, cudaStream_t s) {
+    THA4_REQUIRE(tw.w != nullptr && tw.CO + cout <= TAIL_CO_PAD, "too many head channels");
+    tail_pack_kernel<<<32, 256, 0, s>>>(tw.w, tw.bias, w_ref, b_ref, tw.C, cout, tw.CO);
+    THA4_LAUNCH_CHECK();
+    tw.CO += cout;
+}
 
 void tail_forward(TailKind kind, const TailWeights& tw, const View& feature, const float* coef, int act,
                   const ImgView& image0, const ImgView& image1, float* const* outputs, cudaStream_t s, int strict) {

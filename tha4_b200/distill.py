@@ -35,7 +35,7 @@ def flatten_parameters(module: torch.nn.Module) -> Tensor:
 
 class BodyMorpherDistiller:
     def __init__(self, teacher: GeneralPoser02, student: SirenMorpher03, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None):
+                 process_group=None, distributed: bool = True):
         self.teacher = teacher
         self.student = student
         self.ctx: Context = teacher.get_context()
@@ -49,7 +49,7 @@ class BodyMorpherDistiller:
         self.betas, self.eps = betas, eps
         self.step_count = 0
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size(process_group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
 
     def train_step(self, image: Tensor, pose: Tensor, loss_weights: Sequence[float], lr: float,
                    want_losses: bool = True) -> Optional[Dict[str, float]]:
@@ -71,6 +71,16 @@ class BodyMorpherDistiller:
         out['loss'] = sum(w * l for w, l in zip(loss_weights, losses))
         return out
 
+    def reset(self, state_dict: Optional[Dict[str, Tensor]] = None):
+        """Zeroes the optimiser state (and optionally reloads the student's weights) -- a fresh run on the same buffers."""
+        if state_dict is not None:
+            self.flat.copy_(torch.cat([state_dict[k].reshape(-1).float() for k in self.student.state_dict().keys()]).to(self.flat.device))
+            self.student._uploaded_key = None
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.grad.zero_()
+        self.step_count = 0
+
     def state_dict(self) -> Dict[str, Tensor]:
         return self.student.state_dict()
 
@@ -91,7 +101,8 @@ class FaceMorpherDistiller:
     networks only, get_poser at siren_face_morpher_00_trainer.py:23-26), student input pose[:, 0:39], losses L1 + 20 x
     eye/mouth-masked L1, one flat-gradient all-reduce, Adam."""
 
-    def __init__(self, teacher: GeneralPoser02, student, betas=(0.9, 0.999), eps: float = 1e-8, process_group=None):
+    def __init__(self, teacher: GeneralPoser02, student, betas=(0.9, 0.999), eps: float = 1e-8, process_group=None,
+                 distributed: bool = True):
         self.teacher = teacher
         self.student = student
         self.ctx: Context = teacher.get_context()
@@ -105,7 +116,7 @@ class FaceMorpherDistiller:
         self.betas, self.eps = betas, eps
         self.step_count = 0
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size(process_group) if (distributed and dist.is_available() and dist.is_initialized()) else 1
 
     def train_step(self, image: Tensor, pose: Tensor, eye_mouth_mask: Tensor, lr: float,
                    loss_weights: Sequence[float] = FACE_LOSS_WEIGHTS, want_losses: bool = True) -> Optional[Dict[str, float]]:
@@ -126,6 +137,16 @@ class FaceMorpherDistiller:
         out = dict(zip(FACE_LOSS_TERMS, losses))
         out['loss'] = sum(w * l for w, l in zip(loss_weights, losses))
         return out
+
+    def reset(self, state_dict: Optional[Dict[str, Tensor]] = None):
+        """Zeroes the optimiser state (and optionally reloads the student's weights) -- a fresh run on the same buffers."""
+        if state_dict is not None:
+            self.flat.copy_(torch.cat([state_dict[k].reshape(-1).float() for k in self.student.state_dict().keys()]).to(self.flat.device))
+            self.student._uploaded_key = None
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.grad.zero_()
+        self.step_count = 0
 
     def state_dict(self) -> Dict[str, Tensor]:
         return self.student.state_dict()

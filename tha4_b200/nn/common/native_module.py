@@ -17,8 +17,8 @@ class _Node(Module):
         raise Tha4Error('container node: call the owning network module instead')
 
 
-def _init_tensor(shape, role: str) -> Tensor:
-    """Reference initialisers by role (see state_dict_spec.py)."""
+def _init_tensor(shape, role: str, fan_in: int = 0, key: str = '') -> Tensor:
+    """Reference initialisers by role (see state_dict_spec.py).  `fan_in`: fan-in of the weight this bias belongs to."""
     t = torch.empty(shape, dtype=torch.float32)
     if role in ('conv', 'conv1', 'convT', 'student_last'):
         fan_in = shape[1] * (shape[2] * shape[3] if len(shape) == 4 else 1)
@@ -33,6 +33,11 @@ def _init_tensor(shape, role: str) -> Tensor:
     if role in ('norm_b',):
         return t.zero_()
     if role == 'bias':
+        if key.endswith('last_linear.bias') and fan_in > 0:
+            # the students' last_linear is a plain Conv2d whose WEIGHT is re-initialised (siren.py:76-79, HeInitialization);
+            # its bias keeps Conv2d's default uniform(+-1/sqrt(fan_in))
+            b = 1.0 / math.sqrt(fan_in)
+            return t.uniform_(-b, b)
         return t.zero_()
     if role == 'siren_first':
         return t.uniform_(-1.0 / shape[1], 1.0 / shape[1])                  # siren.py:32
@@ -40,7 +45,9 @@ def _init_tensor(shape, role: str) -> Tensor:
         b = math.sqrt(6.0 / shape[1]) / 30.0
         return t.uniform_(-b, b)                                            # siren.py:34-36
     if role == 'siren_bias':
-        b = 1.0 / math.sqrt(shape[0]) if len(shape) == 1 else 0.0
+        # SineLinearLayer only re-initialises the weight (siren.py:31-36): the bias keeps Conv2d's default
+        # uniform(+-1/sqrt(fan_in)), fan_in = in_channels of the 1x1 conv
+        b = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
         return t.uniform_(-b, b)
     raise ValueError(role)
 
@@ -51,14 +58,17 @@ class NativeModule(Module):
     def __init__(self, spec):
         super().__init__()
         self._spec = spec
+        fan_in = 0
         for key, shape, role in spec:
+            if len(shape) >= 2:      # a weight: remember its fan-in for the bias that follows it in registration order
+                fan_in = shape[1] * (shape[2] * shape[3] if len(shape) == 4 else 1)
             parts = key.split('.')
             node = self
             for p in parts[:-1]:
                 if p not in node._modules:
                     node.add_module(p, _Node())
                 node = node._modules[p]
-            node.register_parameter(parts[-1], Parameter(_init_tensor(shape, role)))
+            node.register_parameter(parts[-1], Parameter(_init_tensor(shape, role, fan_in, key)))
         self._ctx: Optional[Context] = None
         self._uploaded_key = None
 

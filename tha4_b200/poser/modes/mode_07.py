@@ -64,6 +64,13 @@ class FiveStepPoserComputationProtocol(CachedComputationProtocol):
         self.eyebrow_morphed_image_index = eyebrow_morphed_image_index
         self.cached_batch_0 = None
         self.cached_eyebrow_decomposer_output = None
+        self.cached_epoch = None
+        self.cached_batch_size = None
+        # The reference compares the image with the cached one on every call (mode_07.py:56-61, a reduction + host sync).
+        # trust_image_identity = True skips that comparison when the caller passes the very same tensor object with an
+        # unchanged version counter; writes that bypass the counter (`.data`, raw CUDA writes) are then NOT seen, so it is
+        # opt-in for callers that own the image tensor (the puppeteer apps and bench.py's device-resident loop do).
+        self.trust_image_identity = False
 
     def compute_func(self):
         def func(state: ComputationState) -> List[Tensor]:
@@ -72,23 +79,29 @@ class FiveStepPoserComputationProtocol(CachedComputationProtocol):
             # eyebrow cache (mode_07.py:56-68): recompute the decomposer iff there is no cache, the batch size changed
             # or the image differs anywhere.  The comparison is skipped when the caller passes the very same, unmodified
             # tensor object; otherwise it is one reduction kernel + the same host sync the reference pays for .item().
-            if self.cached_batch_0 is None or image.shape[0] != self.cached_batch_0.shape[0]:
-                new_batch_0 = True
-            elif image is self.cached_batch_0 and image._version == self.cached_version:
-                new_batch_0 = False
-            else:
-                new_batch_0 = ctx.images_differ(image, self.cached_batch_0)
-            cached = None if new_batch_0 else self.cached_eyebrow_decomposer_output
             for net in Network:
                 if net.name in state.modules:
                     state.modules[net.name].sync_weights()
+            # one image posed B times (image.expand(B, ...)) is compared through its single stored frame
+            key_image = image[:1] if (image.shape[0] > 1 and image.stride(0) == 0) else image
+            if (self.cached_batch_0 is None or image.shape[0] != self.cached_batch_size
+                    or key_image.shape != self.cached_batch_0.shape
+                    or self.cached_epoch != ctx.epoch):          # options / weights changed: cached outputs are stale
+                new_batch_0 = True
+            elif self.trust_image_identity and key_image is self.cached_batch_0 and key_image._version == self.cached_version:
+                new_batch_0 = False
+            else:
+                new_batch_0 = ctx.images_differ(key_image, self.cached_batch_0)
+            cached = None if new_batch_0 else self.cached_eyebrow_decomposer_output
             output = ctx.teacher_forward(self.TEACHER_MODE, image, state.batch[1], self.eyebrow_morphed_image_index, cached)
             for key, sl in self.SLICES.items():
                 state.outputs[key] = output[sl]
             state.outputs[Branch.all_outputs.name] = output
             if new_batch_0:
-                self.cached_batch_0 = image
-                self.cached_version = image._version
+                self.cached_batch_0 = key_image
+                self.cached_batch_size = image.shape[0]
+                self.cached_version = key_image._version
+                self.cached_epoch = ctx.epoch
                 self.cached_eyebrow_decomposer_output = output[self.SLICES[Network.eyebrow_decomposer.outputs_key]]
             return output
 
@@ -156,12 +169,15 @@ def create_poser(
         name: _loader(cls, module_file_names[name], None if state_dicts is None else state_dicts[name])
         for name, cls in _CLASSES.items()
     }
-    return GeneralPoser02(
+    protocol = FiveStepPoserComputationProtocol(eyebrow_morphed_image_index)
+    poser = GeneralPoser02(
         image_size=512,
         module_loaders=loaders,
         pose_parameters=get_pose_parameters().get_pose_parameter_groups(),
-        output_list_func=FiveStepPoserComputationProtocol(eyebrow_morphed_image_index).compute_func(),
+        output_list_func=protocol.compute_func(),
         subrect=None,
         device=device,
         output_length=5 + 1 + 5 + 8 + 8 + 6,
         default_output_index=default_output_index)
+    poser.protocol = protocol          # not in the reference: gives callers access to `trust_image_identity`
+    return poser

@@ -63,12 +63,15 @@ def create_poser(
         name: mode_07._loader(cls, module_file_names[name], None if state_dicts is None else state_dicts[name])
         for name, cls in _CLASSES.items()
     }
-    return GeneralPoser02(
+    protocol = FiveStepPoserComputationProtocol(eyebrow_morphed_image_index)
+    poser = GeneralPoser02(
         image_size=512,
         module_loaders=loaders,
         pose_parameters=get_pose_parameters().get_pose_parameter_groups(),
-        output_list_func=FiveStepPoserComputationProtocol(eyebrow_morphed_image_index).compute_func(),
+        output_list_func=protocol.compute_func(),
         subrect=None,
         device=device,
         output_length=5 + 5 + 8,
         default_output_index=default_output_index)
+    poser.protocol = protocol          # not in the reference: gives callers access to `trust_image_identity`
+    return poser
