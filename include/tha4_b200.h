@@ -143,6 +143,16 @@ int tha4_adam_step(tha4_ctx* ctx, float* params, const float* grads, float* exp_
 /* max|a-b| > 0 ?  -- the cache-validity test of mode_07.py:61 (synchronises the stream); result written to *differ */
 int tha4_images_differ(tha4_ctx* ctx, const float* a, const float* b, int64_t n, int* differ, void* stream);
 
+/* ---- image I/O on either side of the path ---- */
+/* Poser output frame [B,4,H,W] fp32 in [-1,1] -> displayable [B,H,W,4] uint8 sRGB, the post-processing of the puppeteer
+ * apps (src/tha4/app/character_model_ifacialmocap_puppeteer.py:325-349): clip((x+1)/2) -> linear->sRGB (RGB only) ->
+ * background (0 none, 1 green, 2 blue, 3 black, 4 white: blend over it, alpha = 1) -> *255 -> uint8 (round_mode 0:
+ * truncation as torch's .byte() there; 1: rint as tha4/image_util.py:56).  A 512x512 frame leaves the GPU as 1 MB. */
+int tha4_frame_to_srgb8(tha4_ctx* ctx, const float* frame, int B, int H, int W, int background, int round_mode, uint8_t* out, void* stream);
+/* PNG pixels [H,W,4] uint8 (sRGB, straight alpha) -> poser input [4,H,W] fp32 in [-1,1], linear RGB premultiplied by
+ * alpha (src/tha4/shion/base/image_util.py:127-162) */
+int tha4_rgba8_to_poser_image(tha4_ctx* ctx, const uint8_t* rgba, int H, int W, float* out, void* stream);
+
 /* ---- kernel-level entry points (unit tests, ncu) ---- */
 /* apply_grid_change (src/tha4/nn/image_processing_util.py:13-24): image [N,C,H,W], grid_change [N,2,H,W] ->
  * out [N,C,H,W]; optional corner indices x0,y0 [N,H,W] int32 and lerp weights tx,ty [N,H,W] (NULL to skip) */

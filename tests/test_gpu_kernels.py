@@ -294,3 +294,36 @@ def test_linear_silu():
     x, W, b = torch.randn(3, 256, generator=g), torch.randn(640, 256, generator=g) / 16, torch.randn(640, generator=g)
     assert G.err(G.linear(x, W, b, 1), F.linear(F.silu(x), W, b))[0] < 2e-5
     assert G.err(G.linear(x[:, :6].contiguous(), W[:, :6].contiguous(), b, 0), F.linear(x[:, :6], W[:, :6], b))[0] < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ image I/O
+@pytest.mark.parametrize('background', [0, 1, 2, 3, 4])
+@pytest.mark.parametrize('rint', [False, True])
+def test_frame_to_srgb8_vs_oracle(background, rint):
+    """The puppeteers' display conversion on the GPU: within 1 LSB of the op-by-op restatement everywhere (powf differs
+    from torch's pow in the last ulp, which can move a value across an integer), exact on >= 99.5 % of the bytes."""
+    from oracle import image_io
+    frames = synth.synthetic_image(21, 2) * 1.1                    # a little outside [-1, 1]: exercises the clip
+    out = G.ctx().frame_to_srgb8(frames.to('cuda:0'), background={0: None, 1: 'green', 2: 'blue', 3: 'black', 4: 'white'}[background], rint=rint)
+    torch.cuda.synchronize()
+    assert out.shape == (2, 512, 512, 4) and out.dtype == torch.uint8
+    for n in range(2):
+        ref = image_io.frame_to_srgb8(frames[n], background, rint)
+        d = (out[n].cpu().int() - ref.int()).abs()
+        assert d.max().item() <= 1, (background, rint, d.max().item())
+        assert (d == 0).float().mean().item() >= 0.995
+
+
+def test_rgba8_to_poser_image_vs_loader(golden_dir):
+    """PNG pixels -> poser input tensor on the GPU against the host loader (which is pinned to the reference's
+    extract_pytorch_image_from_filelike in tests/test_oracle_pinned.py)."""
+    import os
+    import numpy
+    import PIL.Image
+    from oracle import image_io
+    path = os.path.join(golden_dir, 'data', 'lambda_00.png')
+    rgba = torch.from_numpy(numpy.asarray(PIL.Image.open(path).convert('RGBA')).copy())
+    out = G.ctx().rgba8_to_poser_image(rgba.to('cuda:0')).cpu()
+    ref = image_io.load_rgba_png(path)
+    assert out.shape == ref.shape == (4, 512, 512)
+    assert G.err(out, ref)[0] <= 2e-6

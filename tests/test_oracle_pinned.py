@@ -255,3 +255,20 @@ def test_pose_schema_and_poser_surface_equal_reference():
     oposer = mode_14.create_poser(torch.device('cuda:0'), state_dicts=ssd)          # construction needs no GPU (lazy modules)
     assert oposer.get_image_size() == rposer.get_image_size() and oposer.get_output_length() == rposer.get_output_length()
     assert oposer.get_num_parameters() == rposer.get_num_parameters() and oposer.get_dtype() == rposer.get_dtype()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason='reference checkout not present')
+def test_display_conversion_pinned_to_reference_functions():
+    """oracle/image_io.frame_to_srgb8 restates the puppeteers' post-processing (a wx app that cannot be imported here);
+    its building blocks are the reference's own convert_linear_to_srgb / torch_linear_to_srgb."""
+    ref_loader.load()
+    from tha4.image_util import convert_linear_to_srgb
+    from oracle import image_io
+    x = synth.synthetic_image(3, 1)[0] * 1.05
+    o = torch.clip((x + 1.0) / 2.0, 0.0, 1.0)
+    assert torch.equal(convert_linear_to_srgb(o), torch.cat([image_io.linear_to_srgb_torch(o[0:3]), o[3:4]], dim=0))
+    plain = image_io.frame_to_srgb8(x, 0)
+    want = (255.0 * convert_linear_to_srgb(o)).permute(1, 2, 0).byte()
+    assert torch.equal(plain, want)
+    white = image_io.frame_to_srgb8(x, 4)
+    assert (white[:, :, 3] == 255).all()

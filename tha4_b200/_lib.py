@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     'tha4_morpher_forward', 'tha4_upscaler_forward', 'tha4_siren_face_morpher_forward', 'tha4_siren_morpher_forward',
     'tha4_teacher_forward', 'tha4_student_forward', 'tha4_siren_morpher_param_count', 'tha4_siren_morpher_train_step',
     'tha4_siren_face_morpher_param_count', 'tha4_siren_face_morpher_train_step',
-    'tha4_adam_step', 'tha4_images_differ', 'tha4_grid_sample', 'tha4_resize_bilinear',
+    'tha4_adam_step', 'tha4_images_differ', 'tha4_frame_to_srgb8', 'tha4_rgba8_to_poser_image', 'tha4_grid_sample', 'tha4_resize_bilinear',
     'tha4_base_grid', 'tha4_test_conv', 'tha4_test_norm', 'tha4_test_tail', 'tha4_test_attention', 'tha4_test_linear',
 ]
 
@@ -294,6 +294,25 @@ class Context:
                                      betas[0], betas[1], eps, step, grad_scale, self._stream())
         if rc != 0:
             raise Tha4Error('tha4_adam_step failed: %s' % self.lib.tha4_last_error(self.handle).decode())
+
+    BACKGROUNDS = {None: 0, 'none': 0, 'green': 1, 'blue': 2, 'black': 3, 'white': 4}
+
+    def frame_to_srgb8(self, frame: Tensor, background=None, rint: bool = False) -> Tensor:
+        """[B,4,H,W] (or [4,H,W]) poser output -> [B,H,W,4] uint8 sRGB on the device (the puppeteers' display conversion)."""
+        frame = _check_input(frame[None] if frame.dim() == 3 else frame, self.device, 'frame')
+        B, C, H, W = frame.shape
+        assert C == 4
+        out = torch.empty((B, H, W, 4), dtype=torch.uint8, device=self.device)
+        self._call('tha4_frame_to_srgb8', _ptr(frame), B, H, W, self.BACKGROUNDS[background], 1 if rint else 0, _ptr(out), self._stream())
+        return out
+
+    def rgba8_to_poser_image(self, rgba: Tensor) -> Tensor:
+        """[H,W,4] uint8 PNG pixels on the device -> [4,H,W] fp32 poser input."""
+        assert rgba.dtype == torch.uint8 and rgba.dim() == 3 and rgba.shape[2] == 4 and rgba.device == self.device
+        rgba = rgba.contiguous()
+        out = torch.empty((4, rgba.shape[0], rgba.shape[1]), dtype=torch.float32, device=self.device)
+        self._call('tha4_rgba8_to_poser_image', _ptr(rgba), rgba.shape[0], rgba.shape[1], _ptr(out), self._stream())
+        return out
 
     def images_differ(self, a: Tensor, b: Tensor) -> bool:
         a = _check_input(a, self.device, 'a')

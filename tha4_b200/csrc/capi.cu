@@ -530,6 +530,14 @@ int tha4_images_differ(tha4_ctx* ctx, const float* a, const float* b, int64_t n,
     return guarded(ctx, [&] { *differ = images_differ(a, b, (size_t)n, ctx->flag, (cudaStream_t)stream) ? 1 : 0; });
 }
 
+int tha4_frame_to_srgb8(tha4_ctx* ctx, const float* frame, int B, int H, int W, int background, int round_mode, uint8_t* out, void* stream) {
+    return guarded(ctx, [&] { frame_to_srgb8(frame, B, H, W, background, round_mode, out, (cudaStream_t)stream); });
+}
+
+int tha4_rgba8_to_poser_image(tha4_ctx* ctx, const uint8_t* rgba, int H, int W, float* out, void* stream) {
+    return guarded(ctx, [&] { rgba8_to_poser_image(rgba, H, W, out, (cudaStream_t)stream); });
+}
+
 // ------------------------------------------------------------------------------------------------ kernel level
 int tha4_grid_sample(tha4_ctx* ctx, const float* image, const float* grid_change, int N, int C, int H, int W,
                      float* out, int32_t* x0, int32_t* y0, float* tx, float* ty, void* stream) {

@@ -74,6 +74,49 @@ __global__ void convert_f32_kernel(const __half* __restrict__ src, int src_ld, f
     }
 }
 
+// ---- image I/O on either side of the poser ----
+// Poser output [B,4,H,W] fp32 in [-1,1] (linear RGB, alpha) -> HWC uint8 sRGB, what the puppeteer apps display
+// (character_model_ifacialmocap_puppeteer.py:325-349): clip((x+1)/2, 0, 1) -> linear->sRGB on RGB
+// (shion/base/image_util.py:30-32) -> optional blend over an opaque background colour (:377-381) -> * 255 -> uint8
+// (`.byte()` truncates; round_mode 1 = rint as convert_output_image_from_torch_to_numpy does, tha4/image_util.py:56).
+// One thread per pixel: four coalesced planar loads, one 4-byte store.
+__device__ __forceinline__ float linear_to_srgb_f(float x) {
+    x = fminf(fmaxf(x, 0.0f), 1.0f);
+    return x <= 0.003130804953560372f ? x * 12.92f : 1.055f * powf(x, 1.0f / 2.4f) - 0.055f;
+}
+__device__ __forceinline__ float srgb_to_linear_f(float x) {
+    x = fminf(fmaxf(x, 0.0f), 1.0f);
+    return x <= 0.04045f ? x / 12.92f : powf((x + 0.055f) / 1.055f, 2.4f);
+}
+__global__ void frame_to_srgb8_kernel(const float* __restrict__ frame, long plane, long total, int has_bg, float bg_r, float bg_g, float bg_b,
+                                      int round_mode, uchar4* __restrict__ out) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long n = i / plane, pix = i - n * plane;
+        const float* f = frame + n * 4 * plane + pix;
+        float c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = fminf(fmaxf((f[k * plane] + 1.0f) / 2.0f, 0.0f), 1.0f);
+        float r = linear_to_srgb_f(c[0]), g = linear_to_srgb_f(c[1]), b = linear_to_srgb_f(c[2]), a = c[3];
+        if (has_bg) {
+            r = r * a + (1.0f - a) * bg_r; g = g * a + (1.0f - a) * bg_g; b = b * a + (1.0f - a) * bg_b; a = 1.0f;
+        }
+        uchar4 o;
+        if (round_mode) { o.x = (unsigned char)rintf(r * 255.0f); o.y = (unsigned char)rintf(g * 255.0f); o.z = (unsigned char)rintf(b * 255.0f); o.w = (unsigned char)rintf(a * 255.0f); }
+        else { o.x = (unsigned char)(255.0f * r); o.y = (unsigned char)(255.0f * g); o.z = (unsigned char)(255.0f * b); o.w = (unsigned char)(255.0f * a); }
+        out[i] = o;
+    }
+}
+// PNG pixels (HWC uint8 RGBA, sRGB) -> poser input [4,H,W] fp32: / 255, sRGB -> linear, premultiply by alpha, * 2 - 1
+// (shion/base/image_util.py:127-162 with scale 2, offset -1).
+__global__ void rgba8_to_poser_image_kernel(const uchar4* __restrict__ rgba, long plane, float* __restrict__ out) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < plane; i += (long)gridDim.x * blockDim.x) {
+        const uchar4 p = rgba[i];
+        const float a = (float)p.w / 255.0f;
+        const float r = srgb_to_linear_f((float)p.x / 255.0f) * a, g = srgb_to_linear_f((float)p.y / 255.0f) * a, b = srgb_to_linear_f((float)p.z / 255.0f) * a;
+        out[i] = r * 2.0f - 1.0f; out[plane + i] = g * 2.0f - 1.0f; out[2 * plane + i] = b * 2.0f - 1.0f; out[3 * plane + i] = a * 2.0f - 1.0f;
+    }
+}
+
 __global__ void resize_bilinear_kernel(ImgView src, float* __restrict__ dst, int Ho, int Wo) {
     const float sy = (float)src.H / (float)Ho, sx = (float)src.W / (float)Wo;
     const long total = (long)src.N * src.C * Ho * Wo;
@@ -218,6 +261,21 @@ void convert_f32(const View& src, const View& dst, cudaStream_t s) {
     THA4_REQUIRE(src.f16 && !dst.f16 && src.C == dst.C && src.pixels() == dst.pixels(), "convert_f32: views");
     const long total = (long)src.pixels() * src.C;
     convert_f32_kernel<<<grid_for(total), 256, 0, s>>>(src.hp(), src.ld, dst.p, dst.ld, src.C, total);
+    THA4_LAUNCH_CHECK();
+}
+
+void frame_to_srgb8(const float* frame, int B, int H, int W, int background, int round_mode, unsigned char* out, cudaStream_t s) {
+    THA4_REQUIRE(background >= 0 && background <= 4, "background: 0 none, 1 green, 2 blue, 3 black, 4 white");
+    const float bg[5][3] = {{0, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}, {1, 1, 1}};
+    const long plane = (long)H * W, total = plane * B;
+    frame_to_srgb8_kernel<<<grid_for(total), 256, 0, s>>>(frame, plane, total, background != 0, bg[background][0], bg[background][1], bg[background][2],
+                                                        round_mode, reinterpret_cast<uchar4*>(out));
+    THA4_LAUNCH_CHECK();
+}
+
+void rgba8_to_poser_image(const unsigned char* rgba, int H, int W, float* out, cudaStream_t s) {
+    const long plane = (long)H * W;
+    rgba8_to_poser_image_kernel<<<grid_for(plane), 256, 0, s>>>(reinterpret_cast<const uchar4*>(rgba), plane, out);
     THA4_LAUNCH_CHECK();
 }
 

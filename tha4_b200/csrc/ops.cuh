@@ -55,6 +55,10 @@ void grid_sample(const ImgView& image, const float* grid_change, float* out, int
 // coarse_size: resolution of `posed` / `grid` (S/2 in the fused pipeline; S when the caller already upsampled).
 void upscaler_prologue(const ImgView& rest, const float* posed, const float* grid, int coarse_size, const View& dst,
                        cudaStream_t s);
+// Poser output [B,4,H,W] in [-1,1] -> [B,H,W,4] uint8 sRGB (+ optional opaque background), and PNG pixels [H,W,4] uint8 ->
+// poser input [4,H,W]; see image_ops.cu.
+void frame_to_srgb8(const float* frame, int B, int H, int W, int background, int round_mode, unsigned char* out, cudaStream_t s);
+void rgba8_to_poser_image(const unsigned char* rgba, int H, int W, float* out, cudaStream_t s);
 // max |a - b| > 0 ?  (eyebrow-decomposer cache check, mode_07.py:56-61).  Synchronises the stream.
 bool images_differ(const float* a, const float* b, size_t n, int* dev_flag, cudaStream_t s);
 // Base-grid table (affine_grid identity, align_corners=False) for a given size; device pointer, cached.

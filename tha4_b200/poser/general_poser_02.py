@@ -97,6 +97,12 @@ class GeneralPoser02(Poser):
         state.context = self.get_context()
         return self._pipeline(state)
 
+    def pose_to_srgb8(self, image: Tensor, pose: Tensor, background=None, rint: bool = False,
+                      output_index: Optional[int] = None) -> Tensor:
+        """Not in the reference: `pose()` followed, on the GPU, by the display conversion every app applies to the frame
+        (character_model_ifacialmocap_puppeteer.py:325-349) -> [B,H,W,4] uint8 sRGB on the device."""
+        return self.get_context().frame_to_srgb8(self.pose(image, pose, output_index), background, rint)
+
     def pose(self, image: Tensor, pose: Tensor, output_index: Optional[int] = None) -> Tensor:
         outputs = self.get_posing_outputs(image, pose)
         return outputs[self._default_output if output_index is None else output_index]
