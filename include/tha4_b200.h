@@ -169,6 +169,14 @@ int tha4_base_grid(int size, float* host_out);
 int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, const float* bias, const float* res,
                    int res_mode, int in_up, float* y, int N, int Cin, int H, int W, int Cout, int strict, int ksplit,
                    void* stream);
+/* conv(act(norm(x))) with the normalisation FUSED into the tcgen05 conv's operand path (default mode of the networks):
+ * x [N,Cin,H,W] is the raw tensor; its first norm_C channels are normalised (groups 0: InstanceNorm2d, else GroupNorm;
+ * FiLM vectors film0 [2*norm_C] / film1 [N,2*norm_C] optional; act 0 none / 1 relu / 2 silu), the remaining channels
+ * pass through.  y: fp32 output [N,Cout,Ho,Wo]; y_from_f16 (optional): the f16 copy the kernel writes, widened. */
+int tha4_test_conv_norm(tha4_ctx* ctx, int kind, const float* x, int N, int Cin, int H, int W, int norm_C, int groups,
+                        const float* gamma, const float* beta, const float* film0, const float* film1, int act,
+                        const float* w, const float* bias, const float* res, int res_mode, int Cout, int ksplit,
+                        float* y, float* y_from_f16, void* stream);
 /* y = act(norm(x)) with groups == 0: InstanceNorm2d, else GroupNorm(groups); act 0 none / 1 relu / 2 silu; pool 0/1;
  * film0 [2C] / film1 [N,2C] optional FiLM scale-shifts (unet.py:90-97); out_f16 = 1 runs the default-mode variant
  * (f16 output tensor, fast-math SiLU) and returns its values widened to fp32 */

@@ -19,7 +19,9 @@ using namespace tha4::tc;
 
 constexpr int R = 200;
 
+template <int ROWB>
 __global__ void __launch_bounds__(128) probe(int shift_rows, int sbo_bytes, int use_base_offset, int kstep, float* out) {
+    constexpr int NCH = ROWB / 16, CH = ROWB / 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smA = smem;                         // R rows x 128 B
@@ -28,20 +30,21 @@ __global__ void __launch_bounds__(128) probe(int shift_rows, int sbo_bytes, int 
     uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     // fill A with the absolute-address swizzle
-    for (int i = tid; i < R * 8; i += 128) {
-        const int row = i >> 3, chunk = i & 7;
+    for (int i = tid; i < R * NCH; i += 128) {
+        const int row = i / NCH, chunk = i % NCH;
         __half v[8];
         for (int e = 0; e < 8; ++e) { const int ch = chunk * 8 + e; v[e] = __float2half((ch & 1) ? (float)ch : (float)(row % 251)); }
-        const uint32_t row_addr = smem_u32(smA) + row * 128;
-        const uint32_t phys = (uint32_t)chunk ^ ((row_addr >> 7) & 7);
-        *reinterpret_cast<uint4*>(smA + row * 128 + phys * 16) = *reinterpret_cast<uint4*>(v);
+        const uint32_t row_addr = smem_u32(smA) + row * ROWB;
+        const uint32_t phys = (uint32_t)chunk ^ (ROWB == 128 ? ((row_addr >> 7) & 7) : ((row_addr >> 7) & 3));
+        *reinterpret_cast<uint4*>(smA + row * ROWB + phys * 16) = *reinterpret_cast<uint4*>(v);
     }
-    for (int i = tid; i < 16 * 8; i += 128) {
-        const int row = i >> 3, chunk = i & 7;
+    for (int i = tid; i < 16 * NCH; i += 128) {
+        const int row = i / NCH, chunk = i % NCH;
         __half v[8];
         for (int e = 0; e < 8; ++e) { const int k = chunk * 8 + e; v[e] = __float2half(k == row + 16 * kstep ? 1.0f : 0.0f); }
-        const uint32_t phys = (uint32_t)chunk ^ (row & 7);
-        *reinterpret_cast<uint4*>(smB + row * 128 + phys * 16) = *reinterpret_cast<uint4*>(v);
+        const uint32_t row_addr = smem_u32(smB) + row * ROWB;
+        const uint32_t phys = (uint32_t)chunk ^ (ROWB == 128 ? ((row_addr >> 7) & 7) : ((row_addr >> 7) & 3));
+        *reinterpret_cast<uint4*>(smB + row * ROWB + phys * 16) = *reinterpret_cast<uint4*>(v);
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic-proxy writes -> async proxy (UMMA) reads
     if (tid == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
@@ -54,13 +57,13 @@ __global__ void __launch_bounds__(128) probe(int shift_rows, int sbo_bytes, int 
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = *slot;
     if (tid == 0) {
-        const uint32_t a_addr = smem_u32(smA) + shift_rows * 128 + kstep * 32;
+        const uint32_t a_addr = smem_u32(smA) + shift_rows * ROWB + kstep * 32;
         const uint32_t b_addr = smem_u32(smB) + kstep * 32;
         uint32_t lo = ((a_addr & 0x3FFFF) >> 4) | (1u << 16);
-        uint32_t hi = ((uint32_t)sbo_bytes >> 4) | (1u << 14) | (2u << 29);
+        uint32_t hi = ((uint32_t)sbo_bytes >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
         if (use_base_offset) hi |= (((a_addr >> 7) & 7u) << 17);          // descriptor bits 49..51
         const uint64_t adesc = ((uint64_t)hi << 32) | lo;
-        const uint64_t bdesc = make_smem_desc(b_addr);
+        const uint64_t bdesc = make_smem_desc_sw<ROWB>(b_addr);
         constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(16 >> 3) << 17) | ((128u >> 4) << 24);
         umma_f16(tmem, adesc, bdesc, idesc, 0u);
         umma_commit(smem_u32(bar));
@@ -75,20 +78,20 @@ __global__ void __launch_bounds__(128) probe(int shift_rows, int sbo_bytes, int 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(32) : "memory");
 }
 
-int main() {
-    float* d = nullptr;
-    cudaMalloc(&d, 128 * 16 * sizeof(float));
+template <int ROWB>
+int run_all(float* d) {
     const size_t smem = 1024 + 26 * 1024 + 2048 + 64;
-    cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int shifts[] = {0, 1, 3, 8, 10, 19, 37};
-    const int sbos[] = {1024, 1280};
+    cudaFuncSetAttribute(probe<ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int shifts[] = {0, 1, 2, 3, 8, 10, 19, 37};
+    const int sbos[] = {8 * ROWB, 10 * ROWB};
     int all_ok_abs_nobo = 1, all_ok_abs_bo = 1;
-    for (int kstep = 0; kstep < 4; kstep += 3)
+    printf("==== %d-byte operand rows (%s) ====\n", ROWB, ROWB == 128 ? "SWIZZLE_128B" : "SWIZZLE_64B");
+    for (int kstep = 0; kstep < ROWB / 32; kstep += ROWB / 32 - 1)
     for (int sbo : sbos)
         for (int shift : shifts)
             for (int bo = 0; bo < 2; ++bo) {
                 cudaMemset(d, 0xff, 128 * 16 * sizeof(float));
-                probe<<<1, 128, smem>>>(shift, sbo, bo, kstep, d);
+                probe<ROWB><<<1, 128, smem>>>(shift, sbo, bo, kstep, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("kstep %d sbo %d shift %d bo %d: CUDA error %s\n", kstep, sbo, shift, bo, cudaGetErrorString(e)); return 1; }
                 std::vector<float> h(128 * 16);
@@ -96,7 +99,7 @@ int main() {
                 // hypothesis: row(m) = shift + (m / 8) * (sbo / 128) + m % 8, chunk un-swizzled by absolute address
                 int bad = 0, first_m = -1; float got_row = 0, got_ch = 0;
                 for (int m = 0; m < 128; ++m) {
-                    const int row = shift + (m / 8) * (sbo / 128) + m % 8;
+                    const int row = shift + (m / 8) * (sbo / ROWB) + m % 8;
                     for (int n = 0; n < 16; ++n) {
                         const int ch = n + 16 * kstep;
                         const float want = (ch & 1) ? (float)ch : (float)(row % 251);
@@ -105,10 +108,18 @@ int main() {
                 }
                 printf("kstep %d sbo %4d shift %2d base_offset %d : %s (%d mismatches", kstep, sbo, shift, bo, bad ? "MISMATCH" : "ok", bad);
                 if (bad) printf("; first at m=%d: fetched row-code %.0f chunk-code %.0f, wanted row %d ch %d", first_m, got_row, got_ch,
-                                (shift + (first_m / 8) * (sbo / 128) + first_m % 8) % 251, 1 + 16 * kstep);
+                                (shift + (first_m / 8) * (sbo / ROWB) + first_m % 8) % 251, 1 + 16 * kstep);
                 printf(")\n");
                 if (bad) { if (bo) all_ok_abs_bo = 0; else all_ok_abs_nobo = 0; }
             }
-    printf("SUMMARY absolute-address swizzle holds for every shift: without base_offset %d, with base_offset %d\n", all_ok_abs_nobo, all_ok_abs_bo);
+    printf("SUMMARY (%d-byte rows) absolute-address swizzle holds for every shift: without base_offset %d, with base_offset %d\n", ROWB, all_ok_abs_nobo, all_ok_abs_bo);
+    return 0;
+}
+
+int main() {
+    float* d = nullptr;
+    cudaMalloc(&d, 128 * 16 * sizeof(float));
+    if (run_all<128>(d)) return 1;
+    if (run_all<64>(d)) return 1;
     return 0;
 }

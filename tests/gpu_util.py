@@ -35,6 +35,21 @@ def conv(kind, x, w, bias=None, res=None, res_mode=0, in_up=0, strict=1, ksplit=
     return y.cpu()
 
 
+def conv_norm(kind, x, norm_C, groups, gamma, beta, film0, film1, act, w, bias=None, res=None, res_mode=0, ksplit=0):
+    """conv(act(norm(x))) through the fused-input-normalisation tcgen05 kernel; returns (fp32 output, f16 copy widened)."""
+    c = ctx()
+    N, Cin, H, W = x.shape
+    Cout = w.shape[1] if kind == 2 else w.shape[0]
+    Ho, Wo = {0: (H, W), 1: (H // 2, W // 2), 2: (H * 2, W * 2), 3: (H, W), 4: (H * 2, W * 2)}[kind]
+    y = torch.empty(N, Cout, Ho, Wo, device='cuda:0')
+    y16 = torch.empty_like(y)
+    t = [dev(v) if v is not None else None for v in (x, gamma, beta, film0, film1, w, bias, res)]
+    c._call('tha4_test_conv_norm', kind, _ptr(t[0]), N, Cin, H, W, norm_C, groups, _ptr(t[1]), _ptr(t[2]), _ptr(t[3]), _ptr(t[4]), act,
+            _ptr(t[5]), _ptr(t[6]), _ptr(t[7]), res_mode, Cout, ksplit, _ptr(y), _ptr(y16), c._stream())
+    torch.cuda.synchronize()
+    return y.cpu(), y16.cpu()
+
+
 def norm(x, groups, gamma, beta, film0=None, film1=None, act=0, pool=0, out_f16=0):
     c = ctx()
     N, C, H, W = x.shape

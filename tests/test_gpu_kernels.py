@@ -162,6 +162,67 @@ def test_conv_f16_weight_range(wscale):
     assert mx < 6e-3 * ref.abs().max().item(), (wscale, mx, ref.abs().max().item())
 
 
+CONV_NORM_CASES = [
+    # kind, N, Cin, norm_C, H, Cout, groups, act, film, bias, res_mode, ksplit
+    (0, 2, 64, 64, 32, 64, 32, 2, True, True, 1, 0),          # U-Net ResBlock conv1: GroupNorm + FiLM + SiLU, residual
+    (0, 1, 128, 128, 64, 128, 32, 2, False, True, 0, 0),      # conv0 of a same-resolution ResBlock
+    (0, 1, 32, 32, 128, 32, 32, 2, True, True, 1, 0),         # 64-byte operand rows (Cin % 64 == 32), many tiles
+    (0, 1, 96, 96, 48, 32, 32, 2, False, True, 0, 0),         # concat-sized input, partial tiles in both directions
+    (0, 1, 512, 512, 16, 512, 0, 1, False, False, 0, 0),      # enc-dec bottleneck: InstanceNorm + ReLU, cluster split-K
+    (0, 1, 528, 512, 16, 512, 0, 1, False, False, 0, 0),      # pose-concat bottleneck conv: 512 normalised + 16 pass-through channels
+    (0, 2, 512, 512, 24, 512, 0, 1, False, False, 0, 3),      # workspace split-K
+    (1, 1, 64, 64, 64, 128, 0, 1, False, False, 0, 0),        # 4x4 stride-2 (element-strided TMA boxes)
+    (2, 1, 256, 256, 32, 128, 0, 1, False, False, 0, 0),      # transposed 4x4 stride-2 (4 phases)
+    (4, 1, 128, 128, 32, 128, 32, 2, True, True, 2, 0),       # up-sampling ResBlock conv0 (phase-decomposed), upsampled residual
+    (3, 2, 256, 256, 16, 768, 32, 0, False, True, 0, 0),      # attention: GroupNorm (no activation) -> 1x1 qkv
+    (0, 1, 64, 64, 256, 64, 32, 2, True, True, 1, 0),
+]
+
+
+@pytest.mark.parametrize('case', CONV_NORM_CASES)
+@pytest.mark.parametrize('halo', [1, 0])
+def test_conv_with_fused_input_norm(case, halo):
+    """The default mode's conv: the pending normalisation (+FiLM, +activation) of the RAW f16 input is applied to the
+    operand tiles in shared memory between TMA and tcgen05.mma.  Reference: conv(act(norm(x))) in fp32.  Tolerance:
+    two f16 roundings of O(1) operands (raw value, normalised value) + tanh.approx SiLU, over a K-term dot product:
+    6e-3 of the output's scale (same class as the separate-pass f16 path)."""
+    kind, N, Cin, nC, H, Cout, groups, act, film, has_bias, res_mode, ksplit = case
+    if kind != 0 and not halo:
+        pytest.skip('only 3x3 stride-1 convs have two kernels')
+    G.ctx().set_option('tcgen05', 1)
+    G.ctx().set_option('halo_conv', halo)      # 1: conv_halo.cu (one halo box per chunk, transformed once); 0: conv_tc.cu (one box per tap)
+    g = _gen(hash(case) % 10007)
+    k = {0: 3, 1: 4, 2: 4, 3: 1, 4: 3}[kind]
+    x = torch.randn(N, Cin, H, H, generator=g) * 1.7 + 0.4
+    if nC < Cin:
+        x[:, nC:] = torch.rand(N, Cin - nC, 1, 1, generator=g).expand(-1, -1, H, H)      # tiled pose planes: constant per channel
+    gamma, beta = 1.0 + 0.3 * torch.randn(nC, generator=g), 0.3 * torch.randn(nC, generator=g)
+    f0 = torch.randn(2 * nC, generator=g) * 0.3 if film else None
+    f1 = torch.randn(N, 2 * nC, generator=g) * 0.3 if film else None
+    wshape = (Cin, Cout, k, k) if kind == 2 else (Cout, Cin, k, k)
+    w = torch.randn(wshape, generator=g) / math.sqrt(Cin * k * k)
+    bias = torch.randn(Cout, generator=g) if has_bias else None
+    xn = x[:, :nC]
+    h = F.group_norm(xn, groups, gamma, beta, eps=1e-5) if groups else F.instance_norm(xn, weight=gamma, bias=beta, eps=1e-5)
+    if film:
+        h = O._scaleshift(O._scaleshift(h, f0.unsqueeze(0).expand(N, -1)), f1)
+    h = {0: h, 1: F.relu(h), 2: F.silu(h)}[act]
+    h = torch.cat([h, x[:, nC:]], dim=1)
+    ref = _conv_ref(kind, h, w, bias, 0)
+    res = None
+    if res_mode:
+        Ho = ref.shape[2]
+        rh = {1: Ho, 2: Ho // 2, 3: Ho * 2}[res_mode]
+        res = torch.randn(N, Cout, rh, rh, generator=g)
+        ref = ref + {1: res, 2: F.interpolate(res, scale_factor=2, mode='nearest'), 3: F.avg_pool2d(res, 2, 2)}[res_mode]
+    out, out16 = G.conv_norm(kind, x, nC, groups, gamma, beta, f0, f1, act, w, bias, res, res_mode, ksplit)
+    G.ctx().set_option('halo_conv', 1)
+    scale = max(1.0, ref.abs().max().item())
+    mx, mean = G.err(out, ref)
+    assert mx < 6e-3 * scale, (case, mx, mean)
+    assert G.err(out16, out)[0] <= 1e-3 * scale, 'the f16 copy is the fp32 output rounded once'
+
+
 # ------------------------------------------------------------------------------------------ normalisation
 @pytest.mark.parametrize('C,H,groups,act,pool', [(64, 48, 0, 1, 0), (512, 16, 0, 0, 0), (32, 64, 32, 2, 0), (192, 16, 32, 2, 1), (384, 16, 32, 2, 0)])
 def test_norm_default_mode_f16_output(C, H, groups, act, pool):

@@ -238,6 +238,7 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         else if (!strcmp(name, "cuda_graphs")) ctx->use_graphs = value ? 1 : 0;
         else if (!strcmp(name, "tcgen05")) conv_enable_tc(value != 0);
         else if (!strcmp(name, "cluster_splitk")) conv_tc_enable_cluster(value != 0);
+        else if (!strcmp(name, "halo_conv")) conv_halo_enable(value != 0);
         else if (!strcmp(name, "tc_stride2")) conv_tc_enable_stride2(value != 0);
         else if (!strcmp(name, "small_bn")) conv_tc_enable_small_bn(value != 0);
         else if (!strcmp(name, "attn_split16")) attention_enable_split16(value != 0);
@@ -602,6 +603,67 @@ int tha4_test_conv(tha4_ctx* ctx, int kind, const float* x, const float* w, cons
     });
 }
 
+int tha4_test_conv_norm(tha4_ctx* ctx, int kind, const float* x, int N, int Cin, int H, int W, int norm_C, int groups,
+                        const float* gamma, const float* beta, const float* film0, const float* film1, int act,
+                        const float* w, const float* bias, const float* res, int res_mode, int Cout, int ksplit,
+                        float* y, float* y_from_f16, void* stream) {
+    return guarded(ctx, [&] {
+        cudaStream_t s = (cudaStream_t)stream;
+        begin_pass(ctx, s);
+        Runtime rt = make_rt(ctx, stream);
+        Pool* P = &ctx->persist;
+        THA4_REQUIRE(Cin % 8 == 0 && norm_C % 8 == 0 && norm_C <= Cin, "test_conv_norm: channel counts must be multiples of 8");
+        AllocSink sink;
+        ConvWeights cw;
+        {
+            SinkScope own(&sink);
+            conv_describe(cw, (ConvKind)kind, Cin, Cout);
+            conv_set_pack_rounding(true);
+            cw.tf32_rounded = true;
+            cw.w = reinterpret_cast<float*>(tracked_malloc(conv_packed_floats(cw) * sizeof(float)));
+            THA4_CUDA_CHECK(cudaMemsetAsync(cw.w, 0, conv_packed_floats(cw) * sizeof(float), s));
+            conv_pack(cw, (ConvKind)kind, w, Cin, 0, s);
+            conv_make_half(cw, s);
+        }
+        cw.bias = const_cast<float*>(bias);
+        auto mk = [&](int n, int h, int ww, int c) { View v; v.N = n; v.H = h; v.W = ww; v.C = c; v.ld = c; v.p = P->alloc((size_t)n * h * ww * c); return v; };
+        // raw input: fp32 (for the statistics, as a producing conv's fp32 accumulators would give them) + its f16 copy
+        View xin = mk(N, H, W, Cin);
+        xin.stats_rep = 2; xin.stats_rep_stride = (long)N * Cin * 2;
+        xin.stats = rt.alloc_stats((size_t)2 * N * Cin * 2); xin.stats_ld = Cin;
+        nchw_to_nhwc(make_img(x, N, Cin, H, W), xin, s);
+        norm_stats(xin, s);
+        View x16 = xin; x16.f16 = 1; x16.stats = nullptr; x16.p = P->alloc(((size_t)N * H * W * Cin + 1) / 2);
+        convert_f16(xin, x16, s);
+        const bool x2 = (kind == CONVT_4x4_S2 || kind == CONV_UP2_3x3);
+        const int Ho = (kind == CONV_4x4_S2) ? H / 2 : (x2 ? H * 2 : H), Wo = (kind == CONV_4x4_S2) ? W / 2 : (x2 ? W * 2 : W);
+        View yo = mk(N, Ho, Wo, Cout);
+        View y16 = yo; y16.f16 = 1; y16.p = P->alloc(((size_t)N * Ho * Wo * Cout + 1) / 2);
+        ConvArgs a;
+        a.in = x16; a.out = yo; a.out16 = y16; a.ksplit = ksplit;
+        a.nin.on = true; a.nin.C = norm_C; a.nin.groups = groups; a.nin.act = act == ACT_SILU ? ACT_SILU_FAST : act;
+        a.nin.gamma = gamma; a.nin.beta = beta; a.nin.film0 = film0; a.nin.film1 = film1; a.nin.film1_ld = 2 * norm_C;
+        a.nin.stats = xin.stats; a.nin.stats_ld = xin.stats_ld; a.nin.stats_rep = xin.stats_rep; a.nin.stats_rep_stride = xin.stats_rep_stride;
+        if (res) {
+            const int rh = res_mode == RES_UP2 ? Ho / 2 : (res_mode == RES_DOWN2 ? Ho * 2 : Ho);
+            const int rw = res_mode == RES_UP2 ? Wo / 2 : (res_mode == RES_DOWN2 ? Wo * 2 : Wo);
+            View r = mk(N, rh, rw, Cout);
+            nchw_to_nhwc(make_img(res, N, Cout, rh, rw), r, s);
+            a.res = r; a.res_mode = res_mode;
+        }
+        const size_t wsf = conv_workspace_floats(cw, a);
+        if (wsf) { a.ws = ctx->scratch.alloc(wsf); a.ws_floats = wsf; }
+        conv_forward(cw, a, s);
+        nhwc_to_nchw(yo, y, s);
+        if (y_from_f16) {
+            View back = mk(N, Ho, Wo, Cout);
+            convert_f32(y16, back, s);
+            nhwc_to_nchw(back, y_from_f16, s);
+        }
+        THA4_CUDA_CHECK(cudaStreamSynchronize(s));
+    });
+}
+
 int tha4_test_norm(tha4_ctx* ctx, const float* x, int N, int C, int H, int W, int groups, const float* gamma,
                    const float* beta, const float* film0, const float* film1, int act, int pool, int out_f16, float* y, void* stream) {
     return guarded(ctx, [&] {
@@ -659,7 +721,15 @@ int tha4_test_tail(tha4_ctx* ctx, int kind, const float* feature, int N, int C, 
         const int a = (act == ACT_SILU && !strict) ? ACT_SILU_FAST : act;
         const ImgView i0 = make_img(image0, N, 4, S, S);
         const ImgView i1 = image1 ? make_img(image1, N, 4, S, S) : ImgView{};
-        tail_forward((TailKind)kind, tw, f, coef, a, i0, i1, outputs, s, strict);
+        if (!strict && rt.f16) {      // the default mode's kernel: raw f16 feature map + statistics -> tcgen05 tail
+            { SinkScope own(&sink); tail_make_half(tw, s); }
+            View f16v = f; f16v.f16 = 1; f16v.p = P->alloc(((size_t)N * S * S * C + 1) / 2);
+            convert_f16(f, f16v, s);
+            NormSpecTail ns; ns.groups = groups; ns.act = a; ns.gamma = gamma; ns.beta = beta;
+            tail_tc_forward((TailKind)kind, tw, f16v, ns, i0, i1, outputs, s);
+        } else {
+            tail_forward((TailKind)kind, tw, f, coef, a, i0, i1, outputs, s, strict);
+        }
         THA4_CUDA_CHECK(cudaStreamSynchronize(s));       // `sink` frees the head weights on return
     });
 }

@@ -372,11 +372,15 @@ bool conv_tc_enabled() { return g_use_tc; }
 
 bool conv_fuses_stats(const ConvWeights& cw, const ConvArgs& a) {
     if (a.out.stats == nullptr || !g_use_tc) return false;
+    if (conv_halo_supported(cw, a)) return true;
     return conv_tc_supported(cw, a) && conv_tc_fuses_stats(cw, a);
 }
 
 void conv_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
-    if (g_use_tc && conv_tc_supported(cw, a)) conv_tc_forward(cw, a, s);
+    if (a.nin.on || a.out16.p || !a.out.p)
+        THA4_REQUIRE(g_use_tc && conv_tc_supported(cw, a), "conv: fused input normalisation / f16 outputs exist on the tcgen05 kernel only");
+    if (g_use_tc && conv_halo_supported(cw, a)) conv_halo_forward(cw, a, s);
+    else if (g_use_tc && conv_tc_supported(cw, a)) conv_tc_forward(cw, a, s);
     else conv_mma_forward(cw, a, s);
 }
 

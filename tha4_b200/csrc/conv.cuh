@@ -49,10 +49,25 @@ void conv_pack(const ConvWeights& cw, ConvKind kind, const float* w_ref, int w_c
 void conv_set_pack_rounding(bool round_tf32);   // applies to subsequent conv_pack calls (set from the context's strict option)
 bool conv_pack_rounding();
 
+// Pending normalisation of the conv's INPUT, applied by the tcgen05 kernel to its f16 operand tiles in shared memory
+// (conv_tc.cu, XF kernels): y = act(A_c x + B_c) with (A, B) built per CTA from the statistics the producing conv
+// accumulated -- InstanceNorm2d (groups == 0) / GroupNorm(groups), eps 1e-5, affine, up to two FiLM scale-shifts.
+// Replaces a separate normalisation pass (one launch + one read and one write of the tensor) per conv.
+struct ConvNormIn {
+    bool on = false;
+    int C = 0;                  // leading channels of `in` that are normalised (the rest -- tiled pose planes -- pass through)
+    int groups = 0, act = ACT_NONE;
+    const float* gamma = nullptr; const float* beta = nullptr;
+    const float* film0 = nullptr; const float* film1 = nullptr; int film1_ld = 0;
+    const double* stats = nullptr; int stats_ld = 0, stats_rep = 1; long stats_rep_stride = 0;   // statistics of the raw input tensor
+};
+
 struct ConvArgs {
     View in;                    // stored input (if in_up: stored at half the logical resolution)
     int in_up = 0;              // nearest-neighbour x2 upsample fused into the gather (unet.py:46)
-    View out;
+    View out;                   // geometry + statistics slot of the output; out.p may be null when only the f16 copy is wanted
+    View out16;                 // optional f16 copy of the output (out16.p == nullptr: none)
+    ConvNormIn nin;             // fused normalisation of the input (tcgen05 kernel, f16 input only)
     View res;                   // residual added in the epilogue (res.p == nullptr: none)
     int res_mode = RES_NONE;    // RES_UP2: res stored at half resolution; RES_DOWN2: res at double resolution (2x2 mean)
     int strict = 0;             // 1: 3xTF32 error-compensated products (fp32-equivalent); 0: single TF32
@@ -74,6 +89,11 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s); 
 // the caller runs norm_stats on the output.
 bool conv_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
 bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
+// conv_halo.cu: 3x3 stride-1 convs on f16 operands with halo reuse (one activation box per channel chunk, taps as
+// row-shifted UMMA descriptors); preferred over conv_tc_forward when it supports the configuration
+bool conv_halo_supported(const ConvWeights& cw, const ConvArgs& a);
+void conv_halo_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);
+void conv_halo_enable(bool on);
 void conv_enable_tc(bool on);
 bool conv_tc_enabled();
 void conv_make_half(const ConvWeights& cw, cudaStream_t s);   // f16 copy of the packed weights (cw.w16), recorded in the active AllocSink

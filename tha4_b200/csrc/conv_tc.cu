@@ -18,7 +18,7 @@
 // nearest-x2-upsample + 3x3); strict mode (3xTF32) and non-TMA-able views stay on the mma.sync kernel in conv.cu.
 #include "conv.cuh"
 #include "profiler.cuh"
-#include "tc_common.cuh"
+#include "conv_tc_device.cuh"
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
@@ -31,40 +31,9 @@ namespace tha4 {
 namespace {
 
 using namespace tc;
+using namespace tcdev;
 
-constexpr int TILE_W = 16, TILE_H = 8;          // 128 output pixels per CTA
-constexpr int TC_THREADS = 192;                  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-
-struct TcParams {
-    float* out; int outH, outW, outC, out_ld;
-    const float* bias;
-    const float* res; int resH, resW, res_ld, res_mode;
-    int N, MH, MW, tiles_x, tiles_y;
-    int ntaps, cpt, ksplit, out_mul, in_mul;       // in_mul: input stride (2 for the 4x4 stride-2 conv: element-strided TMA boxes)
-    int pre_b;                                     // weight tiles may be fetched before the programmatic-dependency wait
-    float acc_scale;                               // accumulator scale (undoes the power-of-two normalisation of the f16 weights)
-    float* ws; long ws_rows; int ws_ld;            // split-K partials: ws[z][tile*128 + row][cout_pad]
-    double* stats; int stats_ld; int stats_rep; long stats_rep_stride;   // per-(n,c) sum / sum-of-squares of the output (optional)
-    signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
-    signed char dx[CONV_MAX_PHASES][CONV_MAX_TAPS];
-    signed char ph_oy[CONV_MAX_PHASES], ph_ox[CONV_MAX_PHASES];
-};
-
-// CS > 1: the K dimension is split over a thread-block cluster of CS CTAs (cluster dims {1,1,CS} along blockIdx.z); the
-// partial accumulators are exchanged through distributed shared memory and every CTA finishes 1/CS of the columns.
-// OP selects the operand format of one k-block (one TMA box row per pixel / per cout):
-//   OP_TF32: 32 fp32 channels  = 128-byte rows, SWIZZLE_128B, kind::tf32 (4 MMAs of K = 8)
-//   OP_F16 : 64 f16 channels   = 128-byte rows, SWIZZLE_128B, kind::f16  (4 MMAs of K = 16)
-//   OP_F16N: 32 f16 channels   =  64-byte rows, SWIZZLE_64B,  kind::f16  (2 MMAs of K = 16)  -- Cin % 64 == 32 layers
-// f16 operands carry the same 10-bit mantissa as TF32 (the normalisation kernels that produce conv inputs write them),
-// so the products are as exact as the TF32 path's while every operand byte count -- HBM, L2 -> smem, smem -> tensor
-// core -- is halved, and the tensor pipe runs at twice the TF32 rate.
-enum { OP_TF32 = 0, OP_F16 = 1, OP_F16N = 2 };
-__host__ __device__ constexpr int op_row_bytes(int op) { return op == OP_F16N ? 64 : 128; }
-__host__ __device__ constexpr int op_kch(int op) { return op == OP_TF32 ? 32 : (op == OP_F16 ? 64 : 32); }   // channels per k-block
-__host__ __device__ constexpr int op_stages(int op, int stages) { return op == OP_F16N ? 2 * stages : stages; }
-
-template <int BN, int STAGES_, int CS, int OP>
+template <int BN, int STAGES_, int CS, int OP, int XF>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     constexpr int STAGES = op_stages(OP, STAGES_);
@@ -78,8 +47,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smA = smem;
     uint8_t* smB = smem + STAGES * A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * B_BYTES);   // full[STAGES], empty[STAGES], tmem_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * B_BYTES);   // full[STAGES], empty[STAGES], tmem_full, xf[STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    float* xf_A = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // XF: per-channel affine y = act(A * x + B), [xf_C] each
+    static_assert(XF == 0 || OP != OP_TF32, "the fused input normalisation works on f16 operands");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile coordinates
@@ -98,6 +69,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + STAGES + s), 1); }
         mbar_init(smem_u32(bars + 2 * STAGES), 1);
+        if (XF) for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(bars + 2 * STAGES + 1 + s), 128);   // all transform threads arrive
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmB) : "memory");
@@ -151,7 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
                 for (int i = 0; i < nk; ++i) {
                     const int s = i % STAGES;
-                    mbar_wait(smem_u32(bars + s), (i / STAGES) & 1);
+                    mbar_wait(smem_u32(bars + (XF ? 2 * STAGES + 1 + s : s)), (i / STAGES) & 1);     // XF: operands are ready once transformed
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint64_t adesc = make_smem_desc_sw<ROWB>(smem_u32(smA + s * A_BYTES));
                     const uint64_t bdesc = make_smem_desc_sw<ROWB>(smem_u32(smB + s * B_BYTES));
@@ -168,196 +140,43 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 }
                 umma_commit(smem_u32(bars + 2 * STAGES));              // accumulator complete -> epilogue
             }
-        } else if (CS > 1) {   // ===== epilogue warps, cluster split-K: TMEM -> own shared-memory partial tile =====
-            const int q = warp & 3;
-            mbar_wait(smem_u32(bars + 2 * STAGES), 0);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const int row = q * 32 + lane;
-            float* Pt = reinterpret_cast<float*>(smem);                // [128][BN] fp32, 16-byte chunks XOR-swizzled by row
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int chunk = (c0 >> 2) + j;
-                    *reinterpret_cast<float4*>(Pt + row * BN + ((chunk ^ (row & 7)) << 2)) =
-                        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        } else {
+          if (XF) {      // ===== warps 2-5 first normalise the A operand of every k-block in place, then become the epilogue =====
+            const int te = threadIdx.x - 64;                              // 0..127 = tile row (pixel) this thread owns
+            // the affine is applied with packed half2 arithmetic (HFMA2, tanh.approx.f16x2): the operand is f16 anyway, the
+            // in-place pass costs a third of the fp32 version's issue slots and half its MUFU slots
+            __half* hA = reinterpret_cast<__half*>(xf_A);
+            __half* hB = hA + p.xf_C;
+            double2* chs = reinterpret_cast<double2*>(xf_A + 2 * p.xf_C); // per-channel (sum, sum of squares) folded over the replicas
+            xf_build_coef(p, n, te, hA, hB, chs);
+            const bool silu = p.xf_act == ACT_SILU || p.xf_act == ACT_SILU_FAST;
+            const int ry = te / TILE_W, rx = te % TILE_W;
+            constexpr int NCH = ROWB / 16;                               // 16-byte chunks (8 channels) per operand row
+            const int swz = ROWB == 128 ? (te & 7) : ((te >> 1) & 3);    // the row's XOR term of the TMA / UMMA swizzle (stage bases are 1024-aligned)
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(smem_u32(bars + s), (i / STAGES) & 1);          // TMA bytes of this stage have landed
+                const int kt = kb + i;
+                const int tap = kt / p.cpt;
+                const int c0 = (kt - tap * p.cpt) * KCE;
+                const int iy = (y0 + ry) * p.in_mul + p.dy[phase][tap], ix = (x0 + rx) * p.in_mul + p.dx[phase][tap];
+                // rows outside the image are the convolution's zero padding (TMA filled them with zeros): they stay zero
+                if (iy >= 0 && iy < p.inH && ix >= 0 && ix < p.inW) {
+                    xf_row<ROWB>(smA + s * A_BYTES + te * ROWB, swz, c0, p, hA, hB, silu);
                 }
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(smem_u32(bars + 2 * STAGES + 1 + s));
             }
-        } else {               // ===== epilogue warps: TMEM -> registers -> global =====
-            const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
-            mbar_wait(smem_u32(bars + 2 * STAGES), 0);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const int row = q * 32 + lane;
-            const bool lead = (split == 0);
-            float* scratch = reinterpret_cast<float*>(smA) + q * (32 * 33);   // pipeline smem is idle once tmem_full fired
-            const int my = y0 + row / TILE_W, mx = x0 + row % TILE_W;
-            const bool valid = my < p.MH && mx < p.MW;
-            const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
-            float* orow = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                const int cbase = n0 + c0;
-                if (cbase >= p.outC) continue;                         // warp-uniform
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.acc_scale;
-                const int cn = min(32, p.outC - cbase);
-                const bool to_ws = p.ksplit > 1 && p.ws;
-                if (valid) {
-                    if (lead && !to_ws) {
-                        if (p.bias) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
-                        }
-                        if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
-                            const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
-                            const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + cbase;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) if (j < cn) v[j] += rr[j];
-                        } else if (p.res_mode == RES_DOWN2) {
-                            const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + cbase;
-                            const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < cn) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
-                        }
-                    }
-                    if (to_ws) {
-                        float* wrow = p.ws + ((long)blockIdx.z * p.ws_rows + (long)blockIdx.x * 128 + row) * p.ws_ld + cbase;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(wrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else if (p.ksplit > 1) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (j < cn) atomicAdd(orow + cbase + j, v[j]);
-                    } else if (cn == 32) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(orow + cbase + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (j < cn) orow[cbase + j] = v[j];
-                    }
-                }
-                if (p.stats && p.ksplit == 1) {
-                    // per-channel sum / sum of squares over this warp's 32 pixels: transpose through shared memory,
-                    // then lane j reduces channel j; one double atomic pair per (warp, channel).
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = valid ? v[j] : 0.0f;
-                    __syncwarp();
-                    float su = 0.0f, sq = 0.0f;
-#pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr) { const float t = scratch[rr * 33 + lane]; su += t; sq += t * t; }
-                    __syncwarp();
-                    float2* part = reinterpret_cast<float2*>(reinterpret_cast<float*>(smA) + 4 * 32 * 33);   // [4 warps][BN]
-                    part[q * BN + c0 + lane] = make_float2(su, sq);
-                }
-            }
-            if (p.stats && p.ksplit == 1) {
-                // combine the four warps' partial sums: one double atomic pair per (tile, channel), spread over replicas
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                const float2* part = reinterpret_cast<const float2*>(reinterpret_cast<float*>(smA) + 4 * 32 * 33);
-                double* base = p.stats + (long)(blockIdx.x % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + n0) * 2;
-                for (int c = (warp - 2) * 32 + lane; c < BN; c += 128) {
-                    if (n0 + c >= p.outC) break;
-                    const float2 a = part[c], b = part[BN + c], cc = part[2 * BN + c], d = part[3 * BN + c];
-                    atomicAdd(base + 2 * c, (double)a.x + (double)b.x + (double)cc.x + (double)d.x);
-                    atomicAdd(base + 2 * c + 1, (double)a.y + (double)b.y + (double)cc.y + (double)d.y);
-                }
-            }
+          }
+          if (CS > 1) epi_stage_partial<BN>(tmem_base, smem, smem_u32(bars + 2 * STAGES), warp, lane);
+          else epi_direct<BN, TILE_W>(p, tmem_base, smem, smem_u32(bars + 2 * STAGES), n, y0, x0, n0, phase, split, warp, lane);
         }
     }
     if (CS > 1) {
         // ---- cluster split-K reduction through distributed shared memory ----
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-        if (warp >= 2) {
-            constexpr int SL = BN / CS, SC = SL / 4;                   // columns / 16-byte chunks finished by this CTA
-            static_assert(SL >= 4 && 128 % SC == 0, "cluster slice");
-            const int te = threadIdx.x - 64;                           // 0..127
-            const int cc = te % SC;
-            const int chunk = split * SC + cc;                         // split == rank in the cluster
-            const int col = n0 + chunk * 4;
-            const uint32_t p_local = smem_u32(smem);
-            float su[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
-#pragma unroll 1
-            for (int row = te / SC; row < 128; row += 128 / SC) {
-                const uint32_t off = (uint32_t)(row * BN + ((chunk ^ (row & 7)) << 2)) * 4u;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int pr = 0; pr < CS; ++pr) {
-                    uint32_t remote;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(p_local + off), "r"(pr));
-                    float4 v;
-                    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
-                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                }
-                acc.x *= p.acc_scale; acc.y *= p.acc_scale; acc.z *= p.acc_scale; acc.w *= p.acc_scale;
-                const int my = y0 + row / TILE_W, mx = x0 + row % TILE_W;
-                if (my >= p.MH || mx >= p.MW || col >= p.outC) continue;
-                const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
-                float v[4] = {acc.x, acc.y, acc.z, acc.w};
-                const int cn = min(4, p.outC - col);
-                if (p.bias) for (int j = 0; j < cn; ++j) v[j] += __ldg(p.bias + col + j);
-                if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
-                    const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
-                    const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + col;
-                    for (int j = 0; j < cn; ++j) v[j] += rr[j];
-                } else if (p.res_mode == RES_DOWN2) {
-                    const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + col;
-                    const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
-                    for (int j = 0; j < cn; ++j) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
-                }
-                float* o = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld + col;
-                if (cn == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                else for (int j = 0; j < cn; ++j) o[j] = v[j];
-                for (int j = 0; j < cn; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
-            }
-            if (p.stats) {
-                // per-column sums of this CTA's slice: thread te holds partials of chunk te % SC; fold the 128 / SC row
-                // threads of each chunk in two short steps (8 floats per thread, then <= 16 doubles per output)
-                float* red = reinterpret_cast<float*>(smem) + 128 * BN;          // [128][8], behind the partial tile
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { red[te * 8 + k] = su[k]; red[te * 8 + 4 + k] = sq[k]; }
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                constexpr int NOUT = SC * 8;                                     // (chunk, {4 sums, 4 sums of squares})
-                double* dbase = p.stats + (long)(blockIdx.x % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + n0 + split * SL) * 2;
-                if constexpr (NOUT <= 128) {
-                    constexpr int G = 128 / NOUT;                                // threads per output
-                    constexpr int PER = 128 / SC / G;                            // entries per thread (= 8)
-                    float* red2 = red + 128 * 8;                                 // [G][NOUT]
-                    const int o = te % NOUT, g = te / NOUT;
-                    const int oc = o >> 3, ok = o & 7;
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < PER; ++i) acc += red[(oc + SC * (g * PER + i)) * 8 + ok];
-                    red2[g * NOUT + o] = acc;
-                    asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                    if (te < NOUT) {
-                        const int c = n0 + split * SL + oc * 4 + (ok & 3);
-                        if (c < p.outC) {
-                            double a = 0.0;
-#pragma unroll
-                            for (int gg = 0; gg < G; ++gg) a += (double)red2[gg * NOUT + o];
-                            atomicAdd(dbase + 2 * (oc * 4 + (ok & 3)) + (ok >> 2), a);
-                        }
-                    }
-                } else {
-                    for (int o = te; o < NOUT; o += 128) {
-                        const int oc = o >> 3, ok = o & 7;
-                        const int c = n0 + split * SL + oc * 4 + (ok & 3);
-                        if (c >= p.outC) continue;
-                        double a = 0.0;
-                        for (int t2 = oc; t2 < 128; t2 += SC) a += (double)red[t2 * 8 + ok];
-                        atomicAdd(dbase + 2 * (oc * 4 + (ok & 3)) + (ok >> 2), a);
-                    }
-                }
-            }
-        }
+        if (warp >= 2) epi_cluster_reduce<BN, CS, TILE_W>(p, smem, n, y0, x0, n0, phase, split, warp);
         // peers may still be reading this CTA's shared memory: leave together
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -408,9 +227,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcParams p, in
                 const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
                 for (int j = 0; j < cn; ++j) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
             }
-            float* o = p.out + (((long)n * p.outH + oy) * p.outW + ox) * p.out_ld + c;
-            if (cn == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            else for (int j = 0; j < cn; ++j) o[j] = v[j];
+            const long opix = ((long)n * p.outH + oy) * p.outW + ox;
+            if (p.out) {
+                float* o = p.out + opix * p.out_ld + c;
+                if (cn == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                else for (int j = 0; j < cn; ++j) o[j] = v[j];
+            }
+            if (p.out16) {
+                __half* o16 = p.out16 + opix * p.out16_ld + c;
+                for (int j = 0; j < cn; ++j) o16[j] = __float2half_rn(v[j]);
+            }
             for (int j = 0; j < cn; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
         }
     }
@@ -493,50 +319,53 @@ const CUtensorMap& weight_map(const ConvWeights& cw, int bn, int op) {
     return g_maps.emplace(key, m).first->second;
 }
 
-template <int OP, int BN, int STAGES_, int CS = 1>
+template <int OP, int BN, int STAGES_, int CS = 1, int XF = 0>
 void launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
     constexpr int STAGES = op_stages(OP, STAGES_);
     constexpr int STAGE_BYTES = (128 + BN) * op_row_bytes(OP);
-    constexpr size_t smem = 1024 + (size_t)STAGES * STAGE_BYTES + (2 * STAGES + 1) * 8 + 16;
-    static_assert(smem <= 227 * 1024, "shared memory budget");
+    constexpr size_t smem0 = 1024 + (size_t)STAGES * STAGE_BYTES + (3 * STAGES + 1) * 8 + 16;
+    static_assert(smem0 <= 227 * 1024, "shared memory budget");
+    // XF: per-channel affine (2 floats) + folded statistics (1 double2) of the normalised input channels
+    const size_t smem = smem0 + (XF ? (size_t)24 * p.xf_C + 32 : 0);
+    THA4_REQUIRE(smem <= 227 * 1024, "conv_tc: shared memory budget (fused input normalisation)");
     static_assert((size_t)STAGES * STAGE_BYTES >= (size_t)4 * 32 * 33 * 4 + 4 * BN * 8, "epilogue scratch must fit in the pipeline buffers");
     static_assert(CS == 1 || (size_t)STAGES * STAGE_BYTES >= (size_t)128 * BN * 4 + 128 * 8 * 4 + 128 * 4, "partial tile + statistics scratch must fit");
-    THA4_ENSURE_SMEM((conv_tc_kernel<BN, STAGES_, CS, OP>), smem);
-    launch_pdl(conv_tc_kernel<BN, STAGES_, CS, OP>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, p);
+    THA4_ENSURE_SMEM((conv_tc_kernel<BN, STAGES_, CS, OP, XF>), smem);
+    launch_pdl(conv_tc_kernel<BN, STAGES_, CS, OP, XF>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, p);
     THA4_LAUNCH_CHECK();
 }
 
-template <int OP, int BN, int STAGES>
+template <int OP, int BN, int STAGES, int XF>
 void launch_tc_cluster(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
-    if (cs == 8) launch_tc<OP, BN, STAGES, 8>(ma, mb, p, grid, s);
-    else if (cs == 4) launch_tc<OP, BN, STAGES, 4>(ma, mb, p, grid, s);
-    else launch_tc<OP, BN, STAGES, 2>(ma, mb, p, grid, s);
+    if (cs == 8) launch_tc<OP, BN, STAGES, 8, XF>(ma, mb, p, grid, s);
+    else if (cs == 4) launch_tc<OP, BN, STAGES, 4, XF>(ma, mb, p, grid, s);
+    else launch_tc<OP, BN, STAGES, 2, XF>(ma, mb, p, grid, s);
 }
 
 // all launch shapes of one operand format: cluster split-K, deep / mid / shallow TMA rings
-template <int OP>
+template <int OP, int XF>
 void launch_variants(bool cluster, int stages_mode, int bn, int ksplit, const CUtensorMap& ma, const CUtensorMap& mb,
                      const TcParams& p, dim3 grid, cudaStream_t s) {
     if (cluster) {
-        if (bn == 256) launch_tc_cluster<OP, 256, 4>(ksplit, ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc_cluster<OP, 128, 6>(ksplit, ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc_cluster<OP, 64, 8>(ksplit, ma, mb, p, grid, s);
-        else launch_tc_cluster<OP, 32, 8>(ksplit, ma, mb, p, grid, s);
+        if (bn == 256) launch_tc_cluster<OP, 256, 4, XF>(ksplit, ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc_cluster<OP, 128, 6, XF>(ksplit, ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc_cluster<OP, 64, 8, XF>(ksplit, ma, mb, p, grid, s);
+        else launch_tc_cluster<OP, 32, 8, XF>(ksplit, ma, mb, p, grid, s);
     } else if (stages_mode == 0) {
-        if (bn == 256) launch_tc<OP, 256, 4>(ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc<OP, 128, 6>(ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc<OP, 64, 8>(ma, mb, p, grid, s);
-        else launch_tc<OP, 32, 8>(ma, mb, p, grid, s);
+        if (bn == 256) launch_tc<OP, 256, 4, 1, XF>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<OP, 128, 6, 1, XF>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<OP, 64, 8, 1, XF>(ma, mb, p, grid, s);
+        else launch_tc<OP, 32, 8, 1, XF>(ma, mb, p, grid, s);
     } else if (stages_mode == 1) {
-        if (bn == 256) launch_tc<OP, 256, 2>(ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc<OP, 128, 3>(ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc<OP, 64, 4>(ma, mb, p, grid, s);
-        else launch_tc<OP, 32, 5>(ma, mb, p, grid, s);
+        if (bn == 256) launch_tc<OP, 256, 2, 1, XF>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<OP, 128, 3, 1, XF>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<OP, 64, 4, 1, XF>(ma, mb, p, grid, s);
+        else launch_tc<OP, 32, 5, 1, XF>(ma, mb, p, grid, s);
     } else {
-        if (bn == 256) launch_tc<OP, 256, 2>(ma, mb, p, grid, s);
-        else if (bn == 128) launch_tc<OP, 128, 2>(ma, mb, p, grid, s);
-        else if (bn == 64) launch_tc<OP, 64, 2>(ma, mb, p, grid, s);
-        else launch_tc<OP, 32, 3>(ma, mb, p, grid, s);
+        if (bn == 256) launch_tc<OP, 256, 2, 1, XF>(ma, mb, p, grid, s);
+        else if (bn == 128) launch_tc<OP, 128, 2, 1, XF>(ma, mb, p, grid, s);
+        else if (bn == 64) launch_tc<OP, 64, 2, 1, XF>(ma, mb, p, grid, s);
+        else launch_tc<OP, 32, 3, 1, XF>(ma, mb, p, grid, s);
     }
 }
 
@@ -610,7 +439,7 @@ TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
 }  // namespace
 
 size_t conv_workspace_floats(const ConvWeights& cw, const ConvArgs& a) {
-    if (!conv_tc_supported(cw, a)) return 0;
+    if (!conv_tc_supported(cw, a) || conv_halo_supported(cw, a)) return 0;
     const TcPlan pl = tc_plan(cw, a);
     if (pl.ksplit <= 1 || pl.cluster) return 0;
     return (size_t)cw.nphase * pl.ksplit * pl.tiles_m * 128 * cw.cout_pad;
@@ -654,7 +483,10 @@ bool conv_tc_supported(const ConvWeights& cw, const ConvArgs& a) {
     if (a.in_up || a.strict) return false;
     if (cw.stride != 1 && !(g_use_s2 && cw.stride == 2 && cw.nphase == 1 && a.in.H % 2 == 0 && a.in.W % 2 == 0)) return false;
     if (a.in.ld % (a.in.f16 ? 8 : 4) != 0 || (((uintptr_t)a.in.p) & 15) != 0) return false;
-    if (a.out.ld % 4 != 0 || (((uintptr_t)a.out.p) & 15) != 0) return false;
+    if (a.out.p && (a.out.ld % 4 != 0 || (((uintptr_t)a.out.p) & 15) != 0)) return false;
+    if (a.out16.p && (a.out16.ld % 8 != 0 || (((uintptr_t)a.out16.p) & 15) != 0)) return false;
+    if (!a.out.p && !a.out16.p) return false;
+    if (a.nin.on && !a.in.f16) return false;       // the fused input normalisation transforms f16 operand tiles
     if (cw.cout_pad % 32 != 0) return false;
     return true;
 }
@@ -664,6 +496,18 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     THA4_REQUIRE(a.in.C == cw.cin && a.out.C == cw.cout && a.in.N == a.out.N, "conv_tc: shapes");
     TcParams p{};
     p.out = a.out.p; p.outH = a.out.H; p.outW = a.out.W; p.outC = a.out.C; p.out_ld = a.out.ld;
+    p.out16 = a.out16.p ? a.out16.hp() : nullptr; p.out16_ld = a.out16.ld;
+    if (a.out16.p) THA4_REQUIRE(a.out16.f16 && a.out16.N == a.out.N && a.out16.H == a.out.H && a.out16.W == a.out.W && a.out16.C == a.out.C, "conv_tc: f16 output copy geometry");
+    p.inH = a.in.H; p.inW = a.in.W; p.inC = a.in.C;
+    if (a.nin.on) {
+        const ConvNormIn& ni = a.nin;
+        THA4_REQUIRE(ni.stats != nullptr && ni.gamma != nullptr && ni.beta != nullptr, "conv_tc: fused input normalisation needs statistics and affine parameters");
+        THA4_REQUIRE(ni.C > 0 && ni.C <= a.in.C && ni.C % 8 == 0 && ni.C <= 1024, "conv_tc: normalised channel count");
+        THA4_REQUIRE(ni.groups == 0 || (ni.C == a.in.C && ni.C % ni.groups == 0), "conv_tc: GroupNorm spans the whole input");
+        p.in_stats = ni.stats; p.in_stats_ld = ni.stats_ld; p.in_stats_rep = std::max(1, ni.stats_rep); p.in_stats_rep_stride = ni.stats_rep_stride;
+        p.xf_C = ni.C; p.xf_groups = ni.groups; p.xf_act = ni.act;
+        p.xf_gamma = ni.gamma; p.xf_beta = ni.beta; p.xf_film0 = ni.film0; p.xf_film1 = ni.film1; p.xf_film1_ld = ni.film1_ld;
+    }
     p.bias = cw.bias;
     p.res = a.res.p; p.res_mode = a.res.p ? a.res_mode : RES_NONE;
     p.resH = a.res.H; p.resW = a.res.W; p.res_ld = a.res.ld;
@@ -697,6 +541,7 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     p.stats_rep = std::max(1, a.out.stats_rep); p.stats_rep_stride = a.out.stats_rep_stride;
     ProfScope prof(PROF_CONV, s);
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * cw.ntaps * cw.nphase, 0.0);
+    THA4_REQUIRE(!(ksplit > 1 && !use_ws && !pl.cluster) || (a.out.p && !a.out16.p), "conv_tc: atomic split-K accumulates into an fp32 output only");
     if (ksplit > 1 && !use_ws && !pl.cluster)
         THA4_CUDA_CHECK(cudaMemset2DAsync(a.out.p, (size_t)a.out.ld * sizeof(float), 0, (size_t)a.out.C * sizeof(float), a.out.pixels(), s));
     const CUtensorMap& ma = activation_map(a.in, op, cw.stride);
@@ -712,9 +557,14 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     }
     const long total_ctas = (long)grid.x * grid.y * grid.z;
     const int stages_mode = forced >= 0 ? forced : (total_ctas <= 160 ? 0 : 2);
-    if (op == OP_TF32) launch_variants<OP_TF32>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
-    else if (op == OP_F16) launch_variants<OP_F16>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
-    else launch_variants<OP_F16N>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
+    if (op == OP_TF32) launch_variants<OP_TF32, 0>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
+    else if (op == OP_F16) {
+        if (a.nin.on) launch_variants<OP_F16, 1>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
+        else launch_variants<OP_F16, 0>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
+    } else {
+        if (a.nin.on) launch_variants<OP_F16N, 1>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
+        else launch_variants<OP_F16N, 0>(pl.cluster, stages_mode, bn, ksplit, ma, mb, p, grid, s);
+    }
     if (use_ws) {
         const int cq = (p.outC + 3) / 4;
         THA4_REQUIRE(cq <= 256, "split-K reduce: Cout <= 1024");

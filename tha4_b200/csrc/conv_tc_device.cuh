@@ -1,0 +1,353 @@
+// Device-side pieces shared by the tcgen05 convolution kernels (conv_tc.cu: one TMA box per tap; conv_halo.cu: one halo box
+// per channel chunk, taps as row-shifted descriptors): launch parameters, operand formats, and the three epilogues
+// (direct TMEM -> global; cluster split-K: TMEM -> own shared-memory partial, then the DSMEM reduction).
+// TW: pixels per tile row of the 128-pixel CTA tile (16 x 8 tiles: 16; 8 x 16 tiles: 8); row r of the accumulator is
+// pixel (y0 + r / TW, x0 + r % TW).
+#pragma once
+#include "conv.cuh"
+#include "tc_common.cuh"
+
+namespace tha4 {
+namespace tcdev {
+
+using namespace tc;
+
+
+
+constexpr int TILE_W = 16, TILE_H = 8;          // 128 output pixels per CTA
+constexpr int TC_THREADS = 192;                  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+struct TcParams {
+    float* out; int outH, outW, outC, out_ld;
+    const float* bias;
+    const float* res; int resH, resW, res_ld, res_mode;
+    int N, MH, MW, tiles_x, tiles_y;
+    int ntaps, cpt, ksplit, out_mul, in_mul;       // in_mul: input stride (2 for the 4x4 stride-2 conv: element-strided TMA boxes)
+    int pre_b;                                     // weight tiles may be fetched before the programmatic-dependency wait
+    float acc_scale;                               // accumulator scale (undoes the power-of-two normalisation of the f16 weights)
+    float* ws; long ws_rows; int ws_ld;            // split-K partials: ws[z][tile*128 + row][cout_pad]
+    double* stats; int stats_ld; int stats_rep; long stats_rep_stride;   // per-(n,c) sum / sum-of-squares of the output (optional)
+    __half* out16; int out16_ld;                   // optional f16 copy of the output (the operand format of a consumer conv); out may be null then
+    // ---- fused input normalisation (XF kernels): the A operand is the RAW f16 output of the producing conv; its pending
+    // InstanceNorm / GroupNorm (+FiLM) affine and activation are applied in shared memory between TMA and tcgen05.mma
+    const double* in_stats; int in_stats_ld, in_stats_rep; long in_stats_rep_stride;
+    int inH, inW, inC;                             // geometry of the input tensor (zero padding must stay zero; statistics count)
+    int xf_C;                                      // channels [0, xf_C) are normalised, the rest (pose planes, padding) pass through
+    int xf_groups, xf_act;                         // 0: InstanceNorm (one group per channel); activation (ACT_*)
+    const float* xf_gamma; const float* xf_beta; const float* xf_film0; const float* xf_film1; int xf_film1_ld;
+    signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
+    signed char dx[CONV_MAX_PHASES][CONV_MAX_TAPS];
+    signed char ph_oy[CONV_MAX_PHASES], ph_ox[CONV_MAX_PHASES];
+};
+
+// CS > 1: the K dimension is split over a thread-block cluster of CS CTAs (cluster dims {1,1,CS} along blockIdx.z); the
+// partial accumulators are exchanged through distributed shared memory and every CTA finishes 1/CS of the columns.
+// OP selects the operand format of one k-block (one TMA box row per pixel / per cout):
+//   OP_TF32: 32 fp32 channels  = 128-byte rows, SWIZZLE_128B, kind::tf32 (4 MMAs of K = 8)
+//   OP_F16 : 64 f16 channels   = 128-byte rows, SWIZZLE_128B, kind::f16  (4 MMAs of K = 16)
+//   OP_F16N: 32 f16 channels   =  64-byte rows, SWIZZLE_64B,  kind::f16  (2 MMAs of K = 16)  -- Cin % 64 == 32 layers
+// f16 operands carry the same 10-bit mantissa as TF32 (the normalisation kernels that produce conv inputs write them),
+// so the products are as exact as the TF32 path's while every operand byte count -- HBM, L2 -> smem, smem -> tensor
+// core -- is halved, and the tensor pipe runs at twice the TF32 rate.
+enum { OP_TF32 = 0, OP_F16 = 1, OP_F16N = 2 };
+__host__ __device__ constexpr int op_row_bytes(int op) { return op == OP_F16N ? 64 : 128; }
+__host__ __device__ constexpr int op_kch(int op) { return op == OP_TF32 ? 32 : (op == OP_F16 ? 64 : 32); }   // channels per k-block
+__host__ __device__ constexpr int op_stages(int op, int stages) { return op == OP_F16N ? 2 * stages : stages; }
+
+
+// ===== fused input normalisation (XF kernels) =====
+// Per-channel affine of sample n's pending normalisation, as packed halves (the operand is f16; HFMA2 / tanh.approx.f16x2
+// keep the in-place pass cheap).  Called by the 128 threads of warps 2-5 (te = 0..127); chs: scratch [xf_C] double2.
+__device__ __forceinline__ void xf_build_coef(const TcParams& p, int n, int te, __half* hA, __half* hB, double2* chs) {
+    const int cpg = p.xf_groups == 0 ? 1 : p.xf_C / p.xf_groups;
+    for (int c = te; c < p.xf_C; c += 128) {
+        double su = 0.0, sq = 0.0;
+        for (int r = 0; r < p.in_stats_rep; ++r) {
+            const double2 v = *reinterpret_cast<const double2*>(p.in_stats + r * p.in_stats_rep_stride + ((long)n * p.in_stats_ld + c) * 2);
+            su += v.x; sq += v.y;
+        }
+        chs[c] = make_double2(su, sq);
+    }
+    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    const bool silu = p.xf_act == ACT_SILU || p.xf_act == ACT_SILU_FAST;
+    for (int c = te; c < p.xf_C; c += 128) {
+        const int g0 = (c / cpg) * cpg;
+        double su = 0.0, sq = 0.0;
+        for (int j = 0; j < cpg; ++j) { const double2 v = chs[g0 + j]; su += v.x; sq += v.y; }
+        const double cnt = (double)p.inH * p.inW * cpg;
+        const double mean = su / cnt;
+        double var = sq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float A = (float)(1.0 / sqrt(var + 1e-5)) * __ldg(p.xf_gamma + c);
+        float B = __ldg(p.xf_beta + c) - (float)mean * A;
+        if (p.xf_film0) { const float sc = 1.0f + __ldg(p.xf_film0 + c), sh = __ldg(p.xf_film0 + p.xf_C + c); A *= sc; B = B * sc + sh; }
+        if (p.xf_film1) { const float* f = p.xf_film1 + (long)n * p.xf_film1_ld; const float sc = 1.0f + __ldg(f + c), sh = __ldg(f + p.xf_C + c); A *= sc; B = B * sc + sh; }
+        if (silu) { A *= 0.5f; B *= 0.5f; }                      // silu(v) = h + h * tanh(h) with h = v / 2
+        hA[c] = __float2half_rn(fminf(fmaxf(A, -65504.0f), 65504.0f)); hB[c] = __float2half_rn(fminf(fmaxf(B, -65504.0f), 65504.0f));
+    }
+    asm volatile("bar.sync 1, 128;\n" ::: "memory");
+}
+
+// One operand row (ROWB bytes = ROWB / 2 channels starting at channel c0) normalised + activated in place.  swz: the
+// row's XOR term of the TMA / UMMA swizzle; every thread walks the LOGICAL chunks in the same order, so the coefficient
+// reads are broadcasts and the data accesses of 8 consecutive rows hit 8 different 16-byte bank groups.
+template <int ROWB>
+__device__ __forceinline__ void xf_row(uint8_t* rowp, int swz, int c0, const TcParams& p, const __half* hA, const __half* hB, bool silu) {
+    constexpr int NCH = ROWB / 16;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int cb = c0 + j * 8;
+        if (cb >= p.xf_C) break;
+        uint4* dp = reinterpret_cast<uint4*>(rowp + ((j ^ swz) << 4));
+        uint4 d = *dp;
+        const uint4 a4 = *reinterpret_cast<const uint4*>(hA + cb), b4 = *reinterpret_cast<const uint4*>(hB + cb);
+        __half2* x2 = reinterpret_cast<__half2*>(&d);
+        const __half2* a2 = reinterpret_cast<const __half2*>(&a4);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&b4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            __half2 h = __hfma2(x2[e], a2[e], b2[e]);
+            if (silu) {
+                uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
+                asm("tanh.approx.f16x2 %0, %1;\n" : "=r"(tu) : "r"(hu));
+                h = __hfma2(h, *reinterpret_cast<__half2*>(&tu), h);
+            } else if (p.xf_act == ACT_RELU) {
+                h = __hmax2(h, __float2half2_rn(0.0f));
+            }
+            x2[e] = h;
+        }
+        *dp = d;
+    }
+}
+
+// ===== cluster split-K, step 1 (epilogue warps): TMEM -> this CTA's shared-memory partial tile =====
+template <int BN>
+__device__ __forceinline__ void epi_stage_partial(uint32_t tmem_base, uint8_t* smem, uint32_t tmem_full_bar, int warp, int lane) {
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int row = q * 32 + lane;
+    float* Pt = reinterpret_cast<float*>(smem);                // [128][BN] fp32, 16-byte chunks XOR-swizzled by row
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int chunk = (c0 >> 2) + j;
+            *reinterpret_cast<float4*>(Pt + row * BN + ((chunk ^ (row & 7)) << 2)) =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+    }
+}
+
+// ===== unsplit / workspace split-K epilogue (epilogue warps): TMEM -> registers -> global (+ statistics) =====
+template <int BN, int TW>
+__device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base, uint8_t* smem, uint32_t tmem_full_bar, int n, int y0, int x0,
+                                           int n0, int phase, int split, int warp, int lane) {
+    const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int row = q * 32 + lane;
+    const bool lead = (split == 0);
+    float* scratch = reinterpret_cast<float*>(smem) + q * (32 * 33);   // pipeline smem is idle once tmem_full fired
+    const int my = y0 + row / TW, mx = x0 + row % TW;
+    const bool valid = my < p.MH && mx < p.MW;
+    const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
+    const long opix = ((long)n * p.outH + oy) * p.outW + ox;
+    float* orow = p.out + opix * p.out_ld;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        const int cbase = n0 + c0;
+        if (cbase >= p.outC) continue;                         // warp-uniform
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.acc_scale;
+        const int cn = min(32, p.outC - cbase);
+        const bool to_ws = p.ksplit > 1 && p.ws;
+        if (valid) {
+            if (lead && !to_ws) {
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
+                }
+                if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
+                    const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
+                    const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + cbase;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (j < cn) v[j] += rr[j];
+                } else if (p.res_mode == RES_DOWN2) {
+                    const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + cbase;
+                    const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < cn) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+                }
+            }
+            if (to_ws) {
+                float* wrow = p.ws + ((long)blockIdx.z * p.ws_rows + (long)blockIdx.x * 128 + row) * p.ws_ld + cbase;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(wrow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else if (p.ksplit > 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < cn) atomicAdd(orow + cbase + j, v[j]);
+            } else {
+                if (p.out) {
+                    if (cn == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(orow + cbase + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) orow[cbase + j] = v[j];
+                    }
+                }
+                if (p.out16) {          // f16 copy: the operand a consumer conv loads by TMA (raw value; its norm is applied there)
+                    __half* hrow = p.out16 + opix * p.out16_ld + cbase;
+                    if (cn == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __half2* h2 = reinterpret_cast<__half2*>(&pk);
+                            h2[0] = __floats2half2_rn(v[j], v[j + 1]); h2[1] = __floats2half2_rn(v[j + 2], v[j + 3]);
+                            h2[2] = __floats2half2_rn(v[j + 4], v[j + 5]); h2[3] = __floats2half2_rn(v[j + 6], v[j + 7]);
+                            *reinterpret_cast<uint4*>(hrow + j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) hrow[j] = __float2half_rn(v[j]);
+                    }
+                }
+            }
+        }
+        if (p.stats && p.ksplit == 1) {
+            // per-channel sum / sum of squares over this warp's 32 pixels: transpose through shared memory,
+            // then lane j reduces channel j; one double atomic pair per (warp, channel).
+#pragma unroll
+            for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = valid ? v[j] : 0.0f;
+            __syncwarp();
+            float su = 0.0f, sq = 0.0f;
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) { const float t = scratch[rr * 33 + lane]; su += t; sq += t * t; }
+            __syncwarp();
+            float2* part = reinterpret_cast<float2*>(reinterpret_cast<float*>(smem) + 4 * 32 * 33);   // [4 warps][BN]
+            part[q * BN + c0 + lane] = make_float2(su, sq);
+        }
+    }
+    if (p.stats && p.ksplit == 1) {
+        // combine the four warps' partial sums: one double atomic pair per (tile, channel), spread over replicas
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        const float2* part = reinterpret_cast<const float2*>(reinterpret_cast<float*>(smem) + 4 * 32 * 33);
+        double* base = p.stats + (long)(blockIdx.x % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + n0) * 2;
+        for (int c = (warp - 2) * 32 + lane; c < BN; c += 128) {
+            if (n0 + c >= p.outC) break;
+            const float2 a = part[c], b = part[BN + c], cc = part[2 * BN + c], d = part[3 * BN + c];
+            atomicAdd(base + 2 * c, (double)a.x + (double)b.x + (double)cc.x + (double)d.x);
+            atomicAdd(base + 2 * c + 1, (double)a.y + (double)b.y + (double)cc.y + (double)d.y);
+        }
+    }
+}
+
+// ===== cluster split-K, step 2 (epilogue warps, after the cluster barrier): DSMEM reduction of this CTA's column slice =====
+template <int BN, int CS, int TW>
+__device__ __forceinline__ void epi_cluster_reduce(const TcParams& p, uint8_t* smem, int n, int y0, int x0, int n0, int phase, int split, int warp) {
+    constexpr int SL = BN / CS, SC = SL / 4;                   // columns / 16-byte chunks finished by this CTA
+    static_assert(SL >= 4 && 128 % SC == 0, "cluster slice");
+    const int te = threadIdx.x - 64;                           // 0..127
+    const int cc = te % SC;
+    const int chunk = split * SC + cc;                         // split == rank in the cluster
+    const int col = n0 + chunk * 4;
+    const uint32_t p_local = smem_u32(smem);
+    float su[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int row = te / SC; row < 128; row += 128 / SC) {
+        const uint32_t off = (uint32_t)(row * BN + ((chunk ^ (row & 7)) << 2)) * 4u;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int pr = 0; pr < CS; ++pr) {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(p_local + off), "r"(pr));
+            float4 v;
+            asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        acc.x *= p.acc_scale; acc.y *= p.acc_scale; acc.z *= p.acc_scale; acc.w *= p.acc_scale;
+        const int my = y0 + row / TW, mx = x0 + row % TW;
+        if (my >= p.MH || mx >= p.MW || col >= p.outC) continue;
+        const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
+        float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        const int cn = min(4, p.outC - col);
+        if (p.bias) for (int j = 0; j < cn; ++j) v[j] += __ldg(p.bias + col + j);
+        if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
+            const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
+            const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + col;
+            for (int j = 0; j < cn; ++j) v[j] += rr[j];
+        } else if (p.res_mode == RES_DOWN2) {
+            const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + col;
+            const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
+            for (int j = 0; j < cn; ++j) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+        }
+        const long opix = ((long)n * p.outH + oy) * p.outW + ox;
+        if (p.out) {
+            float* o = p.out + opix * p.out_ld + col;
+            if (cn == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            else for (int j = 0; j < cn; ++j) o[j] = v[j];
+        }
+        if (p.out16) {
+            __half* o16 = p.out16 + opix * p.out16_ld + col;
+            if (cn == 4) {
+                uint2 pk;
+                __half2* h2 = reinterpret_cast<__half2*>(&pk);
+                h2[0] = __floats2half2_rn(v[0], v[1]); h2[1] = __floats2half2_rn(v[2], v[3]);
+                *reinterpret_cast<uint2*>(o16) = pk;
+            } else for (int j = 0; j < cn; ++j) o16[j] = __float2half_rn(v[j]);
+        }
+        for (int j = 0; j < cn; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
+    }
+    if (p.stats) {
+        // per-column sums of this CTA's slice: thread te holds partials of chunk te % SC; fold the 128 / SC row
+        // threads of each chunk in two short steps (8 floats per thread, then <= 16 doubles per output)
+        float* red = reinterpret_cast<float*>(smem) + 128 * BN;          // [128][8], behind the partial tile
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { red[te * 8 + k] = su[k]; red[te * 8 + 4 + k] = sq[k]; }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        constexpr int NOUT = SC * 8;                                     // (chunk, {4 sums, 4 sums of squares})
+        double* dbase = p.stats + (long)(blockIdx.x % p.stats_rep) * p.stats_rep_stride + ((long)n * p.stats_ld + n0 + split * SL) * 2;
+        if constexpr (NOUT <= 128) {
+            constexpr int G = 128 / NOUT;                                // threads per output
+            constexpr int PER = 128 / SC / G;                            // entries per thread (= 8)
+            float* red2 = red + 128 * 8;                                 // [G][NOUT]
+            const int o = te % NOUT, g = te / NOUT;
+            const int oc = o >> 3, ok = o & 7;
+            float acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) acc += red[(oc + SC * (g * PER + i)) * 8 + ok];
+            red2[g * NOUT + o] = acc;
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            if (te < NOUT) {
+                const int c = n0 + split * SL + oc * 4 + (ok & 3);
+                if (c < p.outC) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int gg = 0; gg < G; ++gg) a += (double)red2[gg * NOUT + o];
+                    atomicAdd(dbase + 2 * (oc * 4 + (ok & 3)) + (ok >> 2), a);
+                }
+            }
+        } else {
+            for (int o = te; o < NOUT; o += 128) {
+                const int oc = o >> 3, ok = o & 7;
+                const int c = n0 + split * SL + oc * 4 + (ok & 3);
+                if (c >= p.outC) continue;
+                double a = 0.0;
+                for (int t2 = oc; t2 < 128; t2 += SC) a += (double)red[t2 * 8 + ok];
+                atomicAdd(dbase + 2 * (oc * 4 + (ok & 3)) + (ok >> 2), a);
+            }
+        }
+    }
+}
+
+}  // namespace tcdev
+}  // namespace tha4

@@ -150,6 +150,64 @@ void run_conv(Runtime& rt, const ConvWeights& cw, const View& in, const View& ou
     if (out.stats && !fused) norm_stats(out, rt.stream);      // mma.sync path (strict mode, stride-2 convs)
 }
 
+// ---- default (tensor-core) mode: activations in up to two precisions, normalisations fused into the consumer conv ----
+// An activation tensor as the default mode stores it: `f` always carries the geometry and the statistics slot; f.p is the
+// fp32 copy (residual streams, inputs of the few remaining normalisation passes) or null; h is the f16 copy (the operand
+// a tcgen05 conv loads by TMA) or empty.  RAW conv outputs whose only consumer is a conv with a pending normalisation
+// exist in f16 only.
+struct Tens { View f; View h; };
+
+Tens make_act(Pool* pool, Runtime& rt, int N, int H, int W, int C, bool want_f32, bool want_f16, bool stats = true) {
+    Tens a;
+    if (want_f32) a.f = make_view(pool, N, H, W, C, stats ? &rt : nullptr);
+    else {
+        View v; v.N = N; v.H = H; v.W = W; v.C = C; v.ld = C;
+        if (stats) {   // same replica rule as make_view
+            const int tiles = ((W + 15) / 16) * ((H + 7) / 8);
+            int rep = 1;
+            while (rep < 16 && rep * 32 <= tiles) rep *= 2;
+            v.stats_rep = rep; v.stats_rep_stride = (long)N * C * 2;
+            v.stats = rt.alloc_stats((size_t)rep * N * C * 2); v.stats_ld = C;
+        }
+        a.f = v;
+    }
+    if (want_f16) a.h = make_view16(pool, N, H, W, C);
+    return a;
+}
+Tens slice_act(const Tens& a, int c0, int c) {
+    Tens r;
+    if (a.f.p) r.f = a.f.slice(c0, c);
+    else { r.f = a.f; r.f.C = c; if (r.f.stats) r.f.stats = a.f.stats + 2 * c0; }
+    if (a.h.p) r.h = a.h.slice(c0, c);
+    return r;
+}
+
+// pending normalisation of `src` (its statistics) with the weights of the layer that follows it in the reference graph
+ConvNormIn norm_in(const View& src_stats, const NormW& nw, int groups, int act, const float* film0 = nullptr,
+                   const float* film1 = nullptr, int film1_ld = 0, int C = 0) {
+    THA4_REQUIRE(src_stats.stats != nullptr, "fused normalisation: the producer did not accumulate statistics");
+    ConvNormIn n;
+    n.on = true; n.C = C > 0 ? C : src_stats.C; n.groups = groups; n.act = act;
+    THA4_REQUIRE(nw.C == n.C, "fused normalisation: channel mismatch");
+    n.gamma = nw.gamma; n.beta = nw.beta; n.film0 = film0; n.film1 = film1; n.film1_ld = film1_ld;
+    n.stats = src_stats.stats; n.stats_ld = src_stats.stats_ld; n.stats_rep = src_stats.stats_rep; n.stats_rep_stride = src_stats.stats_rep_stride;
+    return n;
+}
+
+// conv on the tcgen05 kernel: `in` is an f16 operand view (or fp32 for the first layer of a network), `nin` its pending
+// normalisation (nullptr: none), `out` receives the fp32 and / or f16 copies it has storage for, plus statistics
+void run_conv_tc(Runtime& rt, const ConvWeights& cw, const View& in, const ConvNormIn* nin, const Tens& out,
+                 const View* res = nullptr, int res_mode = RES_NONE) {
+    ConvArgs a;
+    a.in = in; a.out = out.f; a.out16 = out.h; a.strict = 0;
+    if (nin) a.nin = *nin;
+    if (res) { a.res = *res; a.res_mode = res_mode; }
+    const size_t ws = conv_workspace_floats(cw, a);
+    if (ws) { a.ws = rt.scratch->alloc(ws); a.ws_floats = ws; }
+    THA4_REQUIRE(!out.f.stats || conv_fuses_stats(cw, a), "conv: statistics must be fused on the tensor-core path");
+    conv_forward(cw, a, rt.stream);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ EncDecNet
@@ -196,6 +254,7 @@ void EncDecNet::load(const StateDict& sd, cudaStream_t s) {
         tail_add_head(tail_, sd, "eye_color_change.0", true, s);
         tail_add_head(tail_, sd, "eye_alpha.0", true, s);
     }
+    if (conv_pack_rounding()) tail_make_half(tail_, s);       // default mode: the tcgen05 tail's f16 head weights
     THA4_CUDA_CHECK(cudaStreamSynchronize(s));
     loaded_ = true;
 }
@@ -216,9 +275,10 @@ void EncDecNet::forward(Runtime& rt, const ImgView& image0, const ImgView& image
     } else {
         nchw_to_nhwc(image0, x0, s);
     }
+    if (rt.f16) { forward_fused(rt, x0, image0, image1, pose, pose_ld, outputs); return; }
     // conv -> InstanceNorm -> ReLU; the activated tensor goes to `dst`, or to a fresh f16 tensor when its only consumer is
     // a tcgen05 conv (to16), or back in place
-    const bool h16 = rt.f16 != 0;
+    const bool h16 = false;
     auto conv_in_relu = [&](const ConvWeights& cw, const NormW& nw, const View& in, int oh, const View* dst, bool to16) -> View {
         View raw = make_view(P, B, oh, oh, cw.cout, &rt);
         run_conv(rt, cw, in, raw);
@@ -254,6 +314,77 @@ void EncDecNet::forward(Runtime& rt, const ImgView& image0, const ImgView& image
     run_conv(rt, up_[2], x, raw);
     float* coef = tail_coef(rt, raw, up_n_[2], 0);
     tail_forward(kind_, tail_, raw, coef, ACT_RELU, image0, image1, outputs, s, rt.strict);
+}
+
+// Default mode (poser_encoder_decoder_00.py:99-121 / face_morpher_08.py:158-168): every InstanceNorm + ReLU between two
+// convs is applied by the CONSUMER conv to its operand tiles (ConvNormIn); raw conv outputs live in f16.  What remains as
+// a pass: the bottleneck entry (its result is both a residual stream and an operand) and the end of each ResnetBlock
+// (x + IN(conv(...)), resnet_block.py:64-67).
+void EncDecNet::forward_fused(Runtime& rt, const View& x0, const ImgView& image0, const ImgView& image1, const float* pose,
+                              int pose_ld, float* const* outputs) {
+    const int B = x0.N;
+    cudaStream_t s = rt.stream;
+    Pool* P = rt.persist;
+    Tens r0 = make_act(P, rt, B, S_, S_, 64, false, true);
+    run_conv_tc(rt, down_[0], x0, nullptr, r0);                                  // fp32 image operand (kind::tf32)
+    Tens prev = r0;
+    for (int i = 1; i < 3; ++i) {
+        Tens r = make_act(P, rt, B, S_ >> i, S_ >> i, down_[i].cout, false, true);
+        const ConvNormIn ni = norm_in(prev.f, down_n_[i - 1], 0, ACT_RELU);
+        run_conv_tc(rt, down_[i], prev.h, &ni, r);
+        prev = r;
+    }
+    const int b = S_ / 8;
+    View bin16 = make_view16(P, B, b, b, 512 + pose_pad_);
+    Tens r3 = make_act(P, rt, B, b, b, 512, false, false);                        // statistics slot; the data goes into bin16[:, 0:512]
+    r3.h = bin16.slice(0, 512);
+    {
+        const ConvNormIn ni = norm_in(prev.f, down_n_[2], 0, ACT_RELU);
+        run_conv_tc(rt, down_[3], prev.h, &ni, r3);
+    }
+    if (pose_pad_ > 0) tile_vector(pose, pose_ld, pose_ch_, bin16.slice(512, pose_pad_), s);   // poser_encoder_decoder_00.py:110-113
+    // bottleneck entry: conv -> IN -> ReLU; the result x is a residual stream (fp32) and a conv operand (f16 copy)
+    View x = make_view(P, B, b, b, bott0_.cout, &rt);
+    View x16 = make_view16(P, B, b, b, bott0_.cout);
+    {
+        Tens xr; xr.f = x;
+        const ConvNormIn ni = norm_in(r3.f, down_n_[3], 0, ACT_RELU, nullptr, nullptr, 0, 512);
+        run_conv_tc(rt, bott0_, bin16, &ni, xr);
+        run_norm(rt, x, bott0_n_, 0, nullptr, nullptr, 0, ACT_RELU, 0, nullptr, x, &x16);
+    }
+    for (int i = 0; i < 5; ++i) {   // ResnetBlock: x + IN(conv(relu(IN(conv(x)))))  (resnet_block.py:52-67)
+        Tens ha = make_act(P, rt, B, b, b, 512, false, true);
+        run_conv_tc(rt, res_[i][0], x16, nullptr, ha);
+        Tens hb = make_act(P, rt, B, b, b, 512, true, false);
+        const ConvNormIn ni = norm_in(ha.f, res_n_[i][0], 0, ACT_RELU);
+        run_conv_tc(rt, res_[i][1], ha.h, &ni, hb);
+        View n16 = make_view16(P, B, b, b, 512);
+        run_norm(rt, hb.f, res_n_[i][1], 0, nullptr, nullptr, 0, ACT_NONE, 0, &x, hb.f, &n16);
+        x = hb.f; x16 = n16;
+    }
+    Tens u0 = make_act(P, rt, B, 2 * b, 2 * b, up_[0].cout, false, true);
+    run_conv_tc(rt, up_[0], x16, nullptr, u0);
+    Tens u1 = make_act(P, rt, B, 4 * b, 4 * b, up_[1].cout, false, true);
+    {
+        const ConvNormIn ni = norm_in(u0.f, up_n_[0], 0, ACT_RELU);
+        run_conv_tc(rt, up_[1], u0.h, &ni, u1);
+    }
+    // last block: InstanceNorm + ReLU stay pending; the tail kernel applies them while staging its halo tile
+    const bool tc_tail = tail_.w16 != nullptr;
+    Tens feat = make_act(P, rt, B, S_, S_, 64, !tc_tail, tc_tail);
+    {
+        const ConvNormIn ni = norm_in(u1.f, up_n_[1], 0, ACT_RELU);
+        run_conv_tc(rt, up_[2], u1.h, &ni, feat);
+    }
+    if (tc_tail) {
+        View fv = feat.h;                                 // f16 data + the statistics slot of the tensor
+        fv.stats = feat.f.stats; fv.stats_ld = feat.f.stats_ld; fv.stats_rep = feat.f.stats_rep; fv.stats_rep_stride = feat.f.stats_rep_stride;
+        NormSpecTail ns; ns.groups = 0; ns.act = ACT_RELU; ns.gamma = up_n_[2].gamma; ns.beta = up_n_[2].beta;
+        tail_tc_forward(kind_, tail_, fv, ns, image0, image1, outputs, s);
+    } else {
+        float* coef = tail_coef(rt, feat.f, up_n_[2], 0);
+        tail_forward(kind_, tail_, feat.f, coef, ACT_RELU, image0, image1, outputs, s, rt.strict);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ UNetNet
@@ -376,6 +507,7 @@ void UNetNet::load(const StateDict& sd, cudaStream_t s) {
         THA4_CUDA_CHECK(cudaMemcpyAsync(film1_b_ + w->film1_off, sd_get(sd, e.second + ".cond1_layers.1.bias").p,
                                         2 * w->cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
+    if (conv_pack_rounding()) tail_make_half(tail_, s);       // default mode: the tcgen05 tail's f16 head weights
     THA4_CUDA_CHECK(cudaStreamSynchronize(s));
     cudaFree(d_t0); cudaFree(d_t1); cudaFree(d_t2);
     loaded_ = true;
@@ -424,6 +556,7 @@ void UNetNet::forward(Runtime& rt, const ImgView& image, const float* coarse_pos
                       const float* pose, int pose_ld, float* const* outputs) {
     THA4_REQUIRE(loaded_, "network weights not loaded");
     THA4_REQUIRE(image.H == S_ && image.W == S_ && image.C == 4, "unet: image size");
+    if (rt.f16) { forward_fused(rt, image, coarse_posed, coarse_grid, coarse_size, pose, pose_ld, outputs); return; }
     const int B = image.N;
     cudaStream_t s = rt.stream;
     Pool* P = rt.persist;
@@ -521,6 +654,166 @@ void UNetNet::forward(Runtime& rt, const ImgView& image, const float* coarse_pos
     float* coef = tail_coef(rt, feat, last_n_, 32);
     ImgView none{};
     tail_forward(TAIL_UNET, tail_, feat, coef, rt.strict ? ACT_SILU : ACT_SILU_FAST, image, none, outputs, s, rt.strict);
+}
+
+// ------------------------------------------------------------------------------------------------ UNetNet, default mode
+// Every GroupNorm (+FiLM) + SiLU that sits between two convs is applied by the consumer conv to its operand tiles
+// (ConvNormIn); block outputs (the residual streams) are written once in fp32 and once in f16 by the producing conv.
+// Only the down-sampling blocks keep a normalisation pass (SiLU must precede the 2x2 mean, unet.py:58,158).
+namespace {
+
+struct UNetFused {
+    Runtime& rt;
+    const float* film1;
+    int film1_total;
+
+    // ResBlock (unet.py:154-165).  mode: 0 same, 1 up (nearest x2), 2 down (AvgPool2d(2)).
+    void res_block(const ResBlockW& w, const Tens& x, int mode, const Tens& out) {
+        rt.scratch->reset();
+        THA4_REQUIRE(x.f.C == w.cin && out.f.C == w.cout && x.f.p && x.h.p, "res_block: stream tensors carry both precisions");
+        const int B = x.f.N;
+        const int act = ACT_SILU_FAST;
+        Tens h0 = make_act(rt.scratch, rt, B, out.f.H, out.f.W, w.cout, false, true);
+        if (mode == 2) {          // norm0 -> SiLU -> 2x2 mean as a pass (f16 result), then a plain conv
+            View t0 = make_view16(rt.scratch, B, x.f.H / 2, x.f.W / 2, w.cin);
+            run_norm(rt, x.f, w.norm0, 32, nullptr, nullptr, 0, act, 1, nullptr, t0);
+            run_conv_tc(rt, w.conv0, t0, nullptr, h0);
+        } else {                  // mode 1: conv0 was packed as CONV_UP2_3x3 (the upsample is folded into 4 phases of the low-res input)
+            const ConvNormIn n0 = norm_in(x.f, w.norm0, 32, act);
+            run_conv_tc(rt, w.conv0, x.h, &n0, h0);
+        }
+        // norm1 -> FiLM(time) -> FiLM(pose) -> SiLU, folded into one per-(n,c) affine inside conv1
+        const ConvNormIn n1 = norm_in(h0.f, w.norm1, 32, act, w.film0, film1 + w.film1_off, film1_total);
+        if (w.has_skip) {
+            THA4_REQUIRE(mode == 0, "res_block: skip conv only on same-resolution blocks");
+            Tens sk = make_act(rt.scratch, rt, B, x.f.H, x.f.W, w.cout, true, false, false);
+            run_conv_tc(rt, w.skip, x.h, nullptr, sk);
+            run_conv_tc(rt, w.conv1, h0.h, &n1, out, &sk.f, RES_SAME);
+        } else {
+            run_conv_tc(rt, w.conv1, h0.h, &n1, out, &x.f, mode == 0 ? RES_SAME : (mode == 1 ? RES_UP2 : RES_DOWN2));
+        }
+    }
+
+    // AttentionBlock (unet.py:230-239): GroupNorm fused into the qkv conv
+    void attn_block(const AttnW& w, const Tens& x, const Tens& out) {
+        rt.scratch->reset();
+        Tens qkv = make_act(rt.scratch, rt, x.f.N, x.f.H, x.f.W, 3 * x.f.C, true, false, false);
+        const ConvNormIn n = norm_in(x.f, w.norm, 32, ACT_NONE);
+        run_conv_tc(rt, w.qkv, x.h, &n, qkv);
+        View a = make_view(rt.scratch, x.f.N, x.f.H, x.f.W, x.f.C);
+        attention_forward(qkv.f, 8, a, rt.stream);
+        run_conv_tc(rt, w.proj, a, nullptr, out, &x.f, RES_SAME);
+    }
+};
+
+}  // namespace
+
+void UNetNet::forward_fused(Runtime& rt, const ImgView& image, const float* coarse_posed, const float* coarse_grid, int coarse_size,
+                            const float* pose, int pose_ld, float* const* outputs) {
+    const int B = image.N;
+    cudaStream_t s = rt.stream;
+    Pool* P = rt.persist;
+    rt.scratch->reset();
+
+    float* c1 = P->alloc((size_t)B * 256);
+    float* c2 = P->alloc((size_t)B * 256);
+    float* film1 = P->alloc((size_t)B * film1_total_);
+    linear_forward(pose, pose_ld, B, 6, cond_w0_, cond_b0_, 256, 0, c1, 256, s);
+    linear_forward(c1, 256, B, 256, cond_w2_, cond_b2_, 256, 1, c2, 256, s);
+    linear_forward(c2, 256, B, 256, film1_w_, film1_b_, film1_total_, 1, film1, film1_total_, s);
+    UNetFused F{rt, film1, film1_total_};
+
+    View x0;
+    if (upscaler_) {
+        x0 = make_view(P, B, S_, S_, 16);
+        upscaler_prologue(image, coarse_posed, coarse_grid, coarse_size, x0, s);
+    } else {
+        x0 = make_view(P, B, S_, S_, 4);
+        nchw_to_nhwc(image, x0, s);
+    }
+
+    // ---- plan the skip concatenations: up res-block j reads cat(h_j, hs[2L-1-j]) from one buffer (both precisions) ----
+    const int NH = 2 * L_;
+    std::vector<int> hs_ch(NH);
+    hs_ch[0] = mc_;
+    for (int i = 0; i < L_; ++i) {
+        hs_ch[2 * i + 1] = mc_ * mults_[i];
+        if (i < L_ - 1) hs_ch[2 * i + 2] = mc_ * mults_[i];
+    }
+    std::vector<Tens> cat(NH), hs(NH);
+    std::vector<int> ch_h(NH);
+    for (int j = 0; j < NH; ++j) {
+        const int lvl = L_ - 1 - j / 2;
+        const int sp = S_ >> lvl;
+        ch_h[j] = (j == 0) ? mc_ * mults_[L_ - 1] : ((j & 1) ? mc_ * mults_[lvl] : mc_ * mults_[lvl + 1]);
+        const int cs = hs_ch[NH - 1 - j];
+        THA4_REQUIRE(ch_h[j] + cs == up_res_[j].cin, "unet: concat plan does not match weights");
+        cat[j] = make_act(P, rt, B, sp, sp, ch_h[j] + cs, true, true);
+        hs[NH - 1 - j] = slice_act(cat[j], ch_h[j], cs);
+    }
+
+    // ---- down path (unet.py:534-536) ----
+    run_conv_tc(rt, first_, x0, nullptr, hs[0]);
+    Tens cur = hs[0];
+    for (int i = 0; i < L_; ++i) {
+        if (i == L_ - 1) {
+            Tens tmp = make_act(P, rt, B, cur.f.H, cur.f.W, down_res_[i].cout, true, true);
+            F.res_block(down_res_[i], cur, 0, tmp);
+            F.attn_block(down_attn_, tmp, hs[2 * i + 1]);
+        } else {
+            F.res_block(down_res_[i], cur, 0, hs[2 * i + 1]);
+        }
+        cur = hs[2 * i + 1];
+        if (i < L_ - 1) {
+            F.res_block(down_ds_[i], cur, 2, hs[2 * i + 2]);
+            cur = hs[2 * i + 2];
+        }
+    }
+    // ---- middle: Res, Attn, Res, Attn, Res, Attn, Res (unet.py:481-498) ----
+    for (int j = 0; j < 4; ++j) {
+        const bool last = (j == 3);
+        Tens r = last ? slice_act(cat[0], 0, ch_h[0]) : make_act(P, rt, B, cur.f.H, cur.f.W, cur.f.C, true, true);
+        F.res_block(mid_res_[j], cur, 0, r);
+        cur = r;
+        if (!last) {
+            Tens a = make_act(P, rt, B, cur.f.H, cur.f.W, cur.f.C, true, true);
+            F.attn_block(mid_attn_[j], cur, a);
+            cur = a;
+        }
+    }
+    // ---- up path (unet.py:540-544) ----
+    Tens feat;
+    for (int j = 0; j < NH; ++j) {
+        const int lvl = L_ - 1 - j / 2;
+        const bool second = (j & 1);
+        const int co = up_res_[j].cout;
+        Tens dst;
+        if (!second) dst = slice_act(cat[j + 1], 0, ch_h[j + 1]);
+        else dst = make_act(P, rt, B, cat[j].f.H, cat[j].f.W, co, true, true);   // goes to the upsampler or is the final feature
+        if (lvl == L_ - 1) {
+            Tens tmp = make_act(P, rt, B, cat[j].f.H, cat[j].f.W, co, true, true);
+            F.res_block(up_res_[j], cat[j], 0, tmp);
+            F.attn_block(up_attn_[second ? 1 : 0], tmp, dst);
+        } else {
+            F.res_block(up_res_[j], cat[j], 0, dst);
+        }
+        if (second) {
+            if (lvl > 0) F.res_block(up_us_[L_ - 1 - lvl], dst, 1, slice_act(cat[j + 1], 0, ch_h[j + 1]));
+            else feat = dst;
+        }
+    }
+    // ---- last: GroupNorm + SiLU pending, applied inside the fused tail (unet.py:526-529; morpher_00.py:53-58) ----
+    rt.scratch->reset();
+    ImgView none{};
+    if (tail_.w16 != nullptr && feat.h.ld == feat.h.C) {
+        View fv = feat.h;
+        fv.stats = feat.f.stats; fv.stats_ld = feat.f.stats_ld; fv.stats_rep = feat.f.stats_rep; fv.stats_rep_stride = feat.f.stats_rep_stride;
+        NormSpecTail ns; ns.groups = 32; ns.act = ACT_SILU_FAST; ns.gamma = last_n_.gamma; ns.beta = last_n_.beta;
+        tail_tc_forward(TAIL_UNET, tail_, fv, ns, image, none, outputs, s);
+    } else {
+        float* coef = tail_coef(rt, feat.f, last_n_, 32);
+        tail_forward(TAIL_UNET, tail_, feat.f, coef, ACT_SILU_FAST, image, none, outputs, s, rt.strict);
+    }
 }
 
 }  // namespace tha4

@@ -62,6 +62,8 @@ public:
     int num_outputs() const { return kind_ == TAIL_DECOMPOSER ? 6 : 8; }
     bool loaded() const { return loaded_; }
 private:
+    void forward_fused(Runtime& rt, const View& x0, const ImgView& image0, const ImgView& image1, const float* pose, int pose_ld,
+                       float* const* outputs);
     AllocSink owned_;          // every device allocation made by load()
     TailKind kind_;
     int S_, in_ch_, pose_ch_, pose_pad_;
@@ -95,6 +97,8 @@ public:
     bool loaded() const { return loaded_; }
 private:
     AllocSink owned_;          // every device allocation made by load()
+    void forward_fused(Runtime& rt, const ImgView& image, const float* coarse_posed, const float* coarse_grid, int coarse_size,
+                       const float* pose, int pose_ld, float* const* outputs);
     void res_block(Runtime& rt, const ResBlockW& w, const View& x, int mode, const float* film1, const View& out);
     void attn_block(Runtime& rt, const AttnW& w, const View& x, const View& out);
     bool upscaler_;

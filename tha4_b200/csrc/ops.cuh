@@ -71,7 +71,11 @@ struct TailWeights {
     float* w = nullptr;      // [9][C][CO_PAD] fp32
     float* bias = nullptr;   // [CO_PAD]
     int C = 0, CO = 0;
+    __half* w16 = nullptr;   // [9][16][C] f16, K-major B operand of the tcgen05 tail (tail_make_half), scaled by w16_scale
+    float w16_scale = 1.0f;
 };
+// pending normalisation of the tail's feature map (applied inside the tcgen05 tail from the feature view's statistics)
+struct NormSpecTail { int groups = 0; int act = ACT_NONE; const float* gamma = nullptr; const float* beta = nullptr; };
 constexpr int TAIL_CO_PAD = 12;
 // Head weights: tail_init allocates zeroed storage (recorded in the active AllocSink), tail_add appends one reference
 // head conv (weight [cout, C, 3, 3], bias [cout] or nullptr) in the channel order the kernel expects for its kind.
@@ -82,5 +86,10 @@ void tail_add(TailWeights& tw, const float* w_ref, const float* b_ref, int cout,
 // outputs: NCHW contiguous, order/meaning per kind (see tail.cu).
 void tail_forward(TailKind kind, const TailWeights& tw, const View& feature, const float* coef, int act,
                   const ImgView& image0, const ImgView& image1, float* const* outputs, cudaStream_t s, int strict);
+// tcgen05 variant (tail_tc.cu): `feature` is the RAW f16 feature map with the statistics its producer accumulated
+void tail_make_half(TailWeights& tw, cudaStream_t s);     // f16 B-operand copy of the head weights (recorded in the active AllocSink)
+bool tail_tc_supported(const TailWeights& tw, const View& feature);
+void tail_tc_forward(TailKind kind, const TailWeights& tw, const View& feature, const NormSpecTail& ns, const ImgView& image0,
+                     const ImgView& image1, float* const* outputs, cudaStream_t s);
 
 }  // namespace tha4

@@ -12,6 +12,7 @@
 // HBM-bound by design: feature map + image read once, every returned tensor written once.
 #include "ops.cuh"
 #include "gridsample.cuh"
+#include "tail_epilogue.cuh"
 #include "profiler.cuh"
 
 namespace tha4 {
@@ -23,11 +24,6 @@ constexpr int CO_PAD = TAIL_CO_PAD;
 constexpr int OPITCH = 17;      // floats per pixel of the transposed accumulators
 // floats per (tap, channel) row of the staged weights, chosen for conflict-free B-fragment loads: bank = pitch*t + g
 __host__ __device__ constexpr int wpitch(int nt) { return nt == 1 ? 8 : 24; }
-
-__device__ __forceinline__ void store4(float* out, long plane, long pix, const float (&v)[4]) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) out[c * plane + pix] = v[c];
-}
 
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
     asm volatile(
@@ -177,92 +173,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(const float* __restr
 #pragma unroll
     for (int j = 0; j < CO_PAD; ++j) o[j] = (j < NT * 8) ? osm[tid * OPITCH + j] + bg[j] : 0.0f;     // 128 threads = 128 pixels
 
-    const int y = by0 + ty, x = bx0 + tx;
-    const long plane = (long)S * S, pix = (long)y * S + x;
-    float* p0 = o0 + n * 4 * plane;   // most outputs are 4-channel; single/dual-channel ones are offset below
-    if (KIND == TAIL_UNET) {
-        // o: direct(0..3) grid_change(4,5) alpha-logit(6)
-        float direct[4] = {o[0], o[1], o[2], o[3]};
-        const float alpha = sigmoid_f(o[6]);
-        const GsTap t = gs_locate(base[x], base[y], o[4], o[5], S, S);
-        float warped[4], merged[4];
-        gs_sample<4>(img0.p + n * img0.sn, img0.sc, img0.sh, S, S, t, warped);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) merged[c] = direct[c] * alpha + warped[c] * (1.0f - alpha);
-        store4(p0, plane, pix, merged);
-        o1[n * plane + pix] = alpha;
-        store4(o2 + n * 4 * plane, plane, pix, warped);
-        o3[(n * 2L) * plane + pix] = o[4];
-        o3[(n * 2L + 1) * plane + pix] = o[5];
-        store4(o4 + n * 4 * plane, plane, pix, direct);
-    } else if (KIND == TAIL_DECOMPOSER) {
-        // o: bg_alpha(0) bg_color(1..4) eb_alpha(5) eb_color(6..9)
-        float img[4], bgc[4], ebc[4], bgl[4], ebl[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) img[c] = __ldg(img0.p + n * img0.sn + c * img0.sc + (long)y * img0.sh + x);
-        const float bga = sigmoid_f(o[0]), eba = sigmoid_f(o[5]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            bgc[c] = tanhf(o[1 + c]); ebc[c] = tanhf(o[6 + c]);
-            bgl[c] = bgc[c] * bga + img[c] * (1.0f - bga);
-            ebl[c] = img[c] * eba + ebc[c] * (1.0f - eba);     // apply_color_change(alpha, image, color): roles swapped
-        }
-        store4(p0, plane, pix, ebl);
-        o1[n * plane + pix] = eba;
-        store4(o2 + n * 4 * plane, plane, pix, ebc);
-        store4(o3 + n * 4 * plane, plane, pix, bgl);
-        o4[n * plane + pix] = bga;
-        store4(o5 + n * 4 * plane, plane, pix, bgc);
-    } else if (KIND == TAIL_COMBINER) {
-        // o: grid(0,1) alpha(2) color(3..6) combine_alpha(7); img0 = eyebrow layer (warped), img1 = background layer
-        const GsTap t = gs_locate(base[x], base[y], o[0], o[1], S, S);
-        float warped[4], color[4], morphed[4], bgv[4], e0[4], e1[4];
-        gs_sample<4>(img0.p + n * img0.sn, img0.sc, img0.sh, S, S, t, warped);
-        const float alpha = sigmoid_f(o[2]), ca = sigmoid_f(o[7]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            color[c] = tanhf(o[3 + c]);
-            morphed[c] = color[c] * alpha + warped[c] * (1.0f - alpha);
-            bgv[c] = __ldg(img1.p + n * img1.sn + c * img1.sc + (long)y * img1.sh + x);
-        }
-        const float a2 = (morphed[3] + 1.0f) / 2.0f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            e0[c] = morphed[c] * ca + bgv[c] * (1.0f - ca);
-            e1[c] = morphed[c] * a2 + bgv[c] * (1.0f - a2);
-        }
-        e0[3] = bgv[3]; e1[3] = bgv[3];
-        store4(p0, plane, pix, e0);
-        o1[n * plane + pix] = ca;
-        store4(o2 + n * 4 * plane, plane, pix, e1);
-        store4(o3 + n * 4 * plane, plane, pix, morphed);
-        o4[n * plane + pix] = alpha;
-        store4(o5 + n * 4 * plane, plane, pix, color);
-        store4(o6 + n * 4 * plane, plane, pix, warped);
-        o7[(n * 2L) * plane + pix] = o[0];
-        o7[(n * 2L + 1) * plane + pix] = o[1];
-    } else {  // TAIL_FACE
-        // o: grid(0,1) im_color(2..5) im_alpha(6) eye_color(7..10) eye_alpha(11)
-        const GsTap t = gs_locate(base[x], base[y], o[0], o[1], S, S);
-        float im0[4], imc[4], im1[4], eyc[4], outv[4];
-        gs_sample<4>(img0.p + n * img0.sn, img0.sc, img0.sh, S, S, t, im0);
-        const float ima = sigmoid_f(o[6]), eya = sigmoid_f(o[11]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            imc[c] = tanhf(o[2 + c]); eyc[c] = tanhf(o[7 + c]);
-            im1[c] = imc[c] * ima + im0[c] * (1.0f - ima);
-            outv[c] = eyc[c] * eya + im1[c] * (1.0f - eya);
-        }
-        store4(p0, plane, pix, outv);
-        o1[n * plane + pix] = eya;
-        store4(o2 + n * 4 * plane, plane, pix, eyc);
-        store4(o3 + n * 4 * plane, plane, pix, im1);
-        o4[n * plane + pix] = ima;
-        store4(o5 + n * 4 * plane, plane, pix, imc);
-        store4(o6 + n * 4 * plane, plane, pix, im0);
-        o7[(n * 2L) * plane + pix] = o[0];
-        o7[(n * 2L + 1) * plane + pix] = o[1];
-    }
+    tail_epilogue<KIND>(o, n, by0 + ty, bx0 + tx, S, img0, img1, base, o0, o1, o2, o3, o4, o5, o6, o7);
 }
 
 template <int KIND, int NT, bool STRICT>
