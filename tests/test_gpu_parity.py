@@ -200,6 +200,41 @@ def test_mode_07_eyebrow_cache_semantics(teacher_sds):
         _assert_close('mode_07 after cache miss', o2, ref, 3e-2, 3e-4)
 
 
+def test_mode_07_graph_replay_matches_eager(teacher_sds):
+    """Single-chunk teacher forwards whose buffer addresses repeat are replayed as ONE captured CUDA graph (capi.cu): the
+    replayed frames must equal the eagerly launched ones (same kernels, same order; statistics use atomics, so equality is
+    to 1e-5) and follow the pose that is passed, and the launch counter must keep counting the graph's kernels."""
+    import tha4_b200._lib as L
+    poser = mode_07.create_poser(DEV, state_dicts=teacher_sds)
+    ctx = poser.get_context()
+    img = synth.synthetic_image(0, 1).to(DEV)
+    poses = synth.random_poses(3, seed=17).to(DEV)
+    pose_buf = torch.empty(1, 45, device=DEV)
+    with torch.no_grad():
+        ctx.set_option('cuda_graphs', 0)
+        eager = []
+        for i in range(3):
+            pose_buf.copy_(poses[i:i + 1])
+            eager.append([t.clone() for t in poser.get_posing_outputs(img, pose_buf)])
+        ctx.set_option('cuda_graphs', 1)
+        # a caller that reuses its buffers: outputs of the previous call are dropped before the next call allocates
+        outs = None
+        l_prev = ctx.counter('kernel_launches')
+        per_call = []
+        for rep in range(3):
+            for i in range(3):
+                pose_buf.copy_(poses[i:i + 1])
+                outs = None
+                outs = poser.get_posing_outputs(img, pose_buf)
+                torch.cuda.synchronize()
+                l_now = ctx.counter('kernel_launches')
+                per_call.append(l_now - l_prev)
+                l_prev = l_now
+                for a, b in zip(outs, eager[i]):
+                    assert G.err(a.cpu(), b.cpu())[0] <= 1e-4, (rep, i)
+        assert min(per_call) > 100, 'replayed graphs must keep counting their kernels: %s' % per_call
+
+
 @pytest.mark.parametrize('strict', [1, 0])
 def test_mode_12_parity(teacher_sds, strict):
     poser = mode_12.create_poser(DEV, state_dicts={k: teacher_sds[k] for k in ('eyebrow_decomposer', 'eyebrow_morphing_combiner', 'face_morpher')})
@@ -269,6 +304,27 @@ def test_student_modules_standalone(student_sds):
         b = body(img.to(DEV), pose.to(DEV))
         br = O.siren_morpher_03(student_sds['body_morpher'], img, pose)
         _check_student('siren body standalone', b + [f], br + [fr])
+
+
+def test_student_tcgen05_and_mma_paths_agree(lambda00_sds):
+    """The student runs on TMA + tcgen05 + TMEM by default (siren_tc.cu); the mma.sync kernels (siren.cu, option
+    "siren_tc" = 0) are the same math in the same precision class (fp16 operands, fp32 accumulate): both must satisfy the
+    student tolerances against the oracle and agree with each other."""
+    poser = mode_14.create_poser(DEV, state_dicts=lambda00_sds)
+    img = image_io.load_rgba_png(os.path.join(os.path.dirname(__file__), 'golden', 'data', 'lambda_00.png'))
+    poses = synth.random_poses(3, seed=31)
+    imgs = img.unsqueeze(0).expand(3, -1, -1, -1).contiguous()
+    ctx = poser.get_context()
+    with torch.no_grad():
+        refs = O.mode_14_outputs(lambda00_sds, imgs, poses)
+        outs = {}
+        for flag in (1, 0):
+            ctx.set_option('siren_tc', flag)
+            outs[flag] = [t.cpu() for t in poser.get_posing_outputs(imgs.to(DEV), poses.to(DEV))]
+            _check_student('mode_14 siren_tc=%d' % flag, outs[flag], refs)
+        ctx.set_option('siren_tc', 1)
+    for i, (a, b) in enumerate(zip(outs[1], outs[0])):
+        assert G.err(a, b)[1] <= 2e-3, (i, G.err(a, b))
 
 
 def test_default_mode_error_class_vs_torch_cuda_tf32(teacher_poser, teacher_sds):

@@ -146,7 +146,16 @@ class Context:
         self.epoch += 1
 
     def _empty(self, specs, B: int) -> List[Tensor]:
-        return [torch.empty((B, c, s, s), dtype=torch.float32, device=self.device) for c, s in specs]
+        """Fresh output tensors for one call, carved out of ONE allocation (one allocator round trip instead of 33; and
+        a loop that drops its previous outputs gets the same block -- hence the same addresses -- back from PyTorch's
+        caching allocator, which is what lets the library replay a captured CUDA graph)."""
+        sizes = [B * c * s * s for c, s in specs]
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 63) // 64 * 64                     # 256-byte aligned views (TMA / vector stores)
+        flat = torch.empty((total,), dtype=torch.float32, device=self.device)
+        return [flat[o:o + n].view(B, c, s, s) for o, n, (c, s) in zip(offs, sizes, specs)]
 
     # ------------------------------------------------------------------ module level
     def eyebrow_decomposer(self, image: Tensor) -> List[Tensor]:

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <tuple>
+#include <vector>
 
 namespace tha4 {
 std::atomic<long> g_kernel_launches{0};
@@ -23,34 +24,31 @@ void* tracked_malloc(size_t bytes) {
 
 using namespace tha4;
 
-// A whole single-chunk teacher forward captured as a CUDA graph (the B <= micro-batch calls are bound by the ~415 host
-// launches, not by the GPU).  The graph works on library-owned staging buffers so that its pointers never change; the
-// caller's tensors are copied in / out around the launch (~30 MB per frame of device-to-device traffic).
+// A whole single-chunk teacher forward captured as a CUDA graph, ZERO-COPY: the graph is captured on the caller's own
+// buffers and keyed by their addresses (image, pose, every output, the cached decomposer tensors).  In a steady loop
+// -- an app posing into the same tensors, PyTorch's caching allocator handing back the same blocks -- the key repeats and
+// the ~260 launches of a frame become one cudaGraphLaunch; a key seen for the second time is captured, at most
+// GRAPH_CACHE graphs are kept (least recently used is dropped), and a context whose keys never repeat stops trying.
 struct TeacherGraph {
     cudaGraphExec_t exec = nullptr;
-    int calls = 0;
-    bool failed = false;
-    float* image = nullptr; float* pose = nullptr;
-    float* out[33] = {}; size_t out_bytes[33] = {};
-    float* cached[6] = {}; size_t cached_bytes[6] = {};
-    size_t stats_end = 0;      // statistics-arena bytes the last pass of the graph leaves dirty
+    size_t stats_end = 0;      // statistics-arena doubles the pass leaves dirty
     long launches = 0;         // kernels per replay (for the launch counter)
+    long last_use = 0;
 };
+constexpr int GRAPH_CACHE = 8;
 
 struct tha4_ctx {
     int device = 0;
-    int use_graphs = 0;        // option "cuda_graphs": validated (the GPU test-suite passes with it on) but no gain measured -- the
-                               // device-resident loop is GPU-bound (156 vs 156 frames/s) and the host-buffer loop got slower (116 vs 129)
-    std::map<std::tuple<int, int, int, int>, TeacherGraph> graphs;
+    int use_graphs = 1;        // option "cuda_graphs" (default on): single-chunk teacher forwards replay as one graph launch
+    std::map<std::vector<uintptr_t>, TeacherGraph> graphs;
+    std::map<std::vector<uintptr_t>, int> graph_seen;      // how often a key was seen before it was captured
+    long graph_clock = 0, graph_misses = 0;
     void drop_graphs() {
-        for (auto& kv : graphs) {
-            TeacherGraph& g = kv.second;
-            if (g.exec) cudaGraphExecDestroy(g.exec);
-            cudaFree(g.image); cudaFree(g.pose);
-            for (float* p : g.out) cudaFree(p);
-            for (float* p : g.cached) cudaFree(p);
-        }
+        for (auto& kv : graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         graphs.clear();
+        graph_seen.clear();
+        graph_misses = 0;
     }
     std::string err;
     int strict = 0;
@@ -239,6 +237,7 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         else if (!strcmp(name, "tcgen05")) conv_enable_tc(value != 0);
         else if (!strcmp(name, "cluster_splitk")) conv_tc_enable_cluster(value != 0);
         else if (!strcmp(name, "halo_conv")) conv_halo_enable(value != 0);
+        else if (!strcmp(name, "siren_tc")) siren_tc_enable(value != 0);
         else if (!strcmp(name, "tc_stride2")) conv_tc_enable_stride2(value != 0);
         else if (!strcmp(name, "small_bn")) conv_tc_enable_small_bn(value != 0);
         else if (!strcmp(name, "attn_split16")) attention_enable_split16(value != 0);
@@ -398,67 +397,65 @@ int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, int64_t im
                               eyebrow_morphed_image_index, cached_p ? cd : nullptr);
             });
         };
-        // ---- CUDA-graph path: single-chunk calls, from the second identical call on ----
+        // ---- CUDA-graph path: single-chunk calls whose buffer addresses repeat ----
         cudaStream_t s = rt.stream;
-        if (ctx->use_graphs && B <= ctx->microbatch && !prof_enabled() && img_sn != 0) {
-            TeacherGraph& g = ctx->graphs[std::make_tuple(mode, B, eyebrow_morphed_image_index, cached_decomposer ? 1 : 0)];
-            if (!g.failed && ++g.calls >= 2) {
-                if (!g.image) {
-                    THA4_CUDA_CHECK(cudaMalloc(&g.image, (size_t)B * 4 * 512 * 512 * sizeof(float)));
-                    THA4_CUDA_CHECK(cudaMalloc(&g.pose, (size_t)B * 45 * sizeof(float)));
-                    for (int i = 0; i < nout; ++i) {
-                        g.out_bytes[i] = (size_t)B * spec[i].c * spec[i].s * spec[i].s * sizeof(float);
-                        THA4_CUDA_CHECK(cudaMalloc(&g.out[i], g.out_bytes[i]));
-                    }
-                    if (cached_decomposer)
-                        for (int i = 0; i < 6; ++i) {
-                            g.cached_bytes[i] = (size_t)B * kEncDecDecomposer[i].c * 128 * 128 * sizeof(float);
-                            THA4_CUDA_CHECK(cudaMalloc(&g.cached[i], g.cached_bytes[i]));
-                        }
-                }
-                THA4_CUDA_CHECK(cudaMemcpyAsync(g.image, image, (size_t)B * 4 * 512 * 512 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-                THA4_CUDA_CHECK(cudaMemcpyAsync(g.pose, pose, (size_t)B * 45 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-                if (cached_decomposer)
-                    for (int i = 0; i < 6; ++i)
-                        THA4_CUDA_CHECK(cudaMemcpyAsync(g.cached[i], cached_decomposer[i], g.cached_bytes[i], cudaMemcpyDeviceToDevice, s));
-                bool launched = false;
-                if (!g.exec) {
-                    const long l0 = g_kernel_launches.load();
-                    cudaGraph_t graph = nullptr;
-                    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess;
-                    if (ok) {
-                        try { run(g.image, g.pose, g.out, cached_decomposer ? g.cached : nullptr); }
-                        catch (const std::exception&) { ok = false; }
-                        const cudaError_t e = cudaStreamEndCapture(s, &graph);
-                        ok = ok && e == cudaSuccess && graph != nullptr;
-                    }
-                    if (ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
-                    if (graph) cudaGraphDestroy(graph);
-                    if (!ok) {                       // not capturable here: stay on the eager path for this shape
-                        cudaGetLastError();
-                        g.exec = nullptr; g.failed = true;
-                        ctx->persist.reset(); ctx->scratch.reset();
-                    } else {
-                        g.launches = g_kernel_launches.load() - l0;
-                        g.stats_end = ctx->stats_off;
-                        g_kernel_launches.fetch_sub(g.launches);          // counted again below, per replay
-                    }
-                } else if (ctx->stats_off > 0) {
-                    // the arena must be clean when the graph starts; its own first memset only knows the dirt that
-                    // preceded the capture
-                    THA4_CUDA_CHECK(cudaMemsetAsync(ctx->stats_base, 0, ctx->stats_off * sizeof(double), s));
-                }
-                if (g.exec) {
-                    THA4_CUDA_CHECK(cudaGraphLaunch(g.exec, s));
-                    g_kernel_launches.fetch_add(g.launches);
-                    ctx->stats_off = g.stats_end;
-                    const int ncopy = cached_decomposer ? nout - 6 : nout;     // with a cache hit the last six ARE the cached tensors
-                    for (int i = 0; i < ncopy; ++i)
-                        if (outputs[i]) THA4_CUDA_CHECK(cudaMemcpyAsync(outputs[i], g.out[i], g.out_bytes[i], cudaMemcpyDeviceToDevice, s));
-                    launched = true;
-                }
-                if (launched) return;
+        if (ctx->use_graphs && B <= ctx->microbatch && !prof_enabled() && ctx->graph_misses < 64) {
+            std::vector<uintptr_t> key;
+            key.reserve(nout + 12);
+            key.push_back((uintptr_t)mode); key.push_back((uintptr_t)B); key.push_back((uintptr_t)eyebrow_morphed_image_index);
+            key.push_back((uintptr_t)img_sn); key.push_back((uintptr_t)image); key.push_back((uintptr_t)pose); key.push_back((uintptr_t)s);
+            for (int i = 0; i < nout; ++i) key.push_back((uintptr_t)outputs[i]);
+            for (int i = 0; i < 6; ++i) key.push_back(cached_decomposer ? (uintptr_t)cached_decomposer[i] : 0);
+            ++ctx->graph_clock;
+            auto it = ctx->graphs.find(key);
+            if (it != ctx->graphs.end()) {
+                TeacherGraph& g = it->second;
+                // the arena must be clean when the graph starts; its own first memset only knows the dirt that preceded the capture
+                if (ctx->stats_off > 0) THA4_CUDA_CHECK(cudaMemsetAsync(ctx->stats_base, 0, ctx->stats_off * sizeof(double), s));
+                ctx->stats_off = 0;
+                THA4_CUDA_CHECK(cudaGraphLaunch(g.exec, s));
+                g_kernel_launches.fetch_add(g.launches);
+                ctx->stats_off = g.stats_end;
+                g.last_use = ctx->graph_clock;
+                ctx->graph_misses = 0;
+                return;
             }
+            ++ctx->graph_misses;
+            if (++ctx->graph_seen[key] >= 2) {           // second sight of this set of buffers: worth a capture
+                ctx->graph_seen.erase(key);
+                const long l0 = g_kernel_launches.load();
+                cudaGraph_t graph = nullptr;
+                cudaGraphExec_t exec = nullptr;
+                bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+                if (ok) {
+                    try { run(image, pose, outputs, cached_decomposer); }
+                    catch (const std::exception&) { ok = false; }
+                    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+                    ok = ok && e == cudaSuccess && graph != nullptr;
+                }
+                if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+                if (!ok) {                               // not capturable here: run this call eagerly, stop trying for a while
+                    cudaGetLastError();
+                    ctx->graph_misses = 64;
+                    ctx->persist.reset(); ctx->scratch.reset();
+                } else {
+                    if ((int)ctx->graphs.size() >= GRAPH_CACHE) {
+                        auto victim = ctx->graphs.begin();
+                        for (auto jt = ctx->graphs.begin(); jt != ctx->graphs.end(); ++jt)
+                            if (jt->second.last_use < victim->second.last_use) victim = jt;
+                        cudaGraphExecDestroy(victim->second.exec);
+                        ctx->graphs.erase(victim);
+                    }
+                    TeacherGraph g;
+                    g.exec = exec; g.launches = g_kernel_launches.load() - l0; g.stats_end = ctx->stats_off; g.last_use = ctx->graph_clock;
+                    ctx->graphs[key] = g;
+                    // the capture recorded the work without running it: replay it now for this call
+                    THA4_CUDA_CHECK(cudaGraphLaunch(exec, s));
+                    return;
+                }
+            }
+            if (ctx->graph_seen.size() > 256) ctx->graph_seen.clear();
         }
         run(image, pose, outputs, cached_decomposer);
     });

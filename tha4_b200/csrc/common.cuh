@@ -158,5 +158,20 @@ __device__ __forceinline__ float round_tf32(float v) {
     return __uint_as_float(r);
 }
 __device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + expf(-v)); }
+// (sum, sum of squares) of one channel folded over the statistics replicas.  The loads are issued eight at a time before
+// any of them is consumed: a dependent chain of up to 16 L2 round trips (~0.4 us each) per channel was the single
+// largest item in the prologue of every kernel that rebuilds a normalisation affine (profiles/r02_ncu_tail_tc_v1.txt).
+__device__ __forceinline__ double2 fold_stat_replicas(const double* __restrict__ p, long rep_stride, int rep) {
+    double su = 0.0, sq = 0.0;
+    for (int r0 = 0; r0 < rep; r0 += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            v[j] = (r0 + j < rep) ? __ldg(reinterpret_cast<const double2*>(p + (long)(r0 + j) * rep_stride)) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { su += v[j].x; sq += v[j].y; }
+    }
+    return make_double2(su, sq);
+}
 
 }  // namespace tha4

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : 4u;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic (not an integer round trip) keeps the shared address space: LDS / STS, not generic LD / ST
     uint8_t* smA = smem;
     uint8_t* smB = smem + SA * A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smB + SB * B_BYTES);
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
     uint64_t* b_full = bars + 3 * SA, *b_empty = b_full + SB;
     uint64_t* t_full = b_empty + SB;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
-    float* xf_A = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
+    float* xf_A = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot + 4) + ((16u - (tc::smem_u32(tmem_slot + 4) & 15u)) & 15u));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int tile = blockIdx.x;
@@ -278,22 +278,24 @@ void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p
     THA4_LAUNCH_CHECK();
 }
 
-template <int OP, int BN, int SA, int SB, int XF>
+// SBD: weight-ring depth of the cluster split-K launches (few CTAs per SM, the ring is what hides the DRAM latency of weights
+// that are fetched ahead of the dependency wait); SBS: depth of the unsplit launches (many tiles: a shallow ring keeps
+// the CTA small so that 2 - 4 of them share an SM and overlap each other's load -> transform -> MMA -> drain chains).
+template <int OP, int BN, int SA, int SBD, int SBS, int XF>
 void launch_halo_cs(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
-    if (cs == 8) launch_halo<OP, BN, SA, SB, 8, XF>(ma, mb, p, grid, s);
-    else if (cs == 4) launch_halo<OP, BN, SA, SB, 4, XF>(ma, mb, p, grid, s);
-    else if (cs == 2) launch_halo<OP, BN, SA, SB, 2, XF>(ma, mb, p, grid, s);
-    else launch_halo<OP, BN, SA, SB, 1, XF>(ma, mb, p, grid, s);
+    if (cs == 8) launch_halo<OP, BN, SA, SBD, 8, XF>(ma, mb, p, grid, s);
+    else if (cs == 4) launch_halo<OP, BN, SA, SBD, 4, XF>(ma, mb, p, grid, s);
+    else if (cs == 2) launch_halo<OP, BN, SA, SBD, 2, XF>(ma, mb, p, grid, s);
+    else launch_halo<OP, BN, SA, SBS, 1, XF>(ma, mb, p, grid, s);
 }
 
-// ring depths: 2-3 halo stages (23 / 12 KB each), weight stages sized to the N tile (a halo feeds 9 weight tiles)
 template <int OP, int XF>
 void launch_halo_bn(int bn, int cs, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
     constexpr int M = OP == OP_F16N ? 2 : 1;        // 64-byte rows: twice the stages for the same bytes in flight
-    if (bn == 256) launch_halo_cs<OP, 256, 2 * M, 4 * M, XF>(cs, ma, mb, p, grid, s);
-    else if (bn == 128) launch_halo_cs<OP, 128, 2 * M, 6 * M, XF>(cs, ma, mb, p, grid, s);
-    else if (bn == 64) launch_halo_cs<OP, 64, 2 * M, 8 * M, XF>(cs, ma, mb, p, grid, s);
-    else launch_halo_cs<OP, 32, 2 * M, 9 * M, XF>(cs, ma, mb, p, grid, s);
+    if (bn == 256) launch_halo_cs<OP, 256, 2 * M, 4 * M, 2 * M, XF>(cs, ma, mb, p, grid, s);        // unsplit: 111 KB -> 2 CTAs / SM
+    else if (bn == 128) launch_halo_cs<OP, 128, 2 * M, 6 * M, 3 * M, XF>(cs, ma, mb, p, grid, s);   // unsplit:  95 KB -> 2 CTAs / SM
+    else if (bn == 64) launch_halo_cs<OP, 64, 2 * M, 8 * M, 3 * M, XF>(cs, ma, mb, p, grid, s);     // unsplit:  71 KB -> 3 CTAs / SM
+    else launch_halo_cs<OP, 32, 2 * M, 9 * M, 5 * M, XF>(cs, ma, mb, p, grid, s);                    // unsplit:  67 KB -> 3 CTAs / SM
 }
 
 bool g_use_halo = true;

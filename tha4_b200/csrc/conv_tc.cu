@@ -44,12 +44,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     constexpr int A_BYTES = A_BYTES1;
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic (not an integer round trip) keeps the shared address space: LDS / STS, not generic LD / ST
     uint8_t* smA = smem;
     uint8_t* smB = smem + STAGES * A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smB + STAGES * B_BYTES);   // full[STAGES], empty[STAGES], tmem_full, xf[STAGES]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
-    float* xf_A = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // XF: per-channel affine y = act(A * x + B), [xf_C] each
+    float* xf_A = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot + 4) + ((16u - (tc::smem_u32(tmem_slot + 4) & 15u)) & 15u));   // XF: per-channel affine y = act(A * x + B), [xf_C] each
     static_assert(XF == 0 || OP != OP_TF32, "the fused input normalisation works on f16 operands");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -60,14 +60,8 @@ __host__ __device__ constexpr int op_stages(int op, int stages) { return op == O
 // keep the in-place pass cheap).  Called by the 128 threads of warps 2-5 (te = 0..127); chs: scratch [xf_C] double2.
 __device__ __forceinline__ void xf_build_coef(const TcParams& p, int n, int te, __half* hA, __half* hB, double2* chs) {
     const int cpg = p.xf_groups == 0 ? 1 : p.xf_C / p.xf_groups;
-    for (int c = te; c < p.xf_C; c += 128) {
-        double su = 0.0, sq = 0.0;
-        for (int r = 0; r < p.in_stats_rep; ++r) {
-            const double2 v = *reinterpret_cast<const double2*>(p.in_stats + r * p.in_stats_rep_stride + ((long)n * p.in_stats_ld + c) * 2);
-            su += v.x; sq += v.y;
-        }
-        chs[c] = make_double2(su, sq);
-    }
+    for (int c = te; c < p.xf_C; c += 128)
+        chs[c] = fold_stat_replicas(p.in_stats + ((long)n * p.in_stats_ld + c) * 2, p.in_stats_rep_stride, p.in_stats_rep);
     asm volatile("bar.sync 1, 128;\n" ::: "memory");
     const bool silu = p.xf_act == ACT_SILU || p.xf_act == ACT_SILU_FAST;
     for (int c = te; c < p.xf_C; c += 128) {

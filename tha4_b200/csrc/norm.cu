@@ -113,14 +113,8 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
         const int ng = groups == 0 ? C : groups, cpg = C / ng;
         double2* sm_ch = reinterpret_cast<double2*>(sm_coef + 2 * C);   // [C] per-channel (sum, sum of squares) over the replicas
         if (cpg > 1) {                                         // GroupNorm: all threads fold the replicas, then one thread per group
-            for (int c = threadIdx.x; c < C; c += blockDim.x) {
-                double su = 0.0, sq = 0.0;
-                for (int r = 0; r < rep; ++r) {
-                    const double2 v = *reinterpret_cast<const double2*>(sums + r * rep_stride + ((long)n_fixed * stats_ld + c) * 2);
-                    su += v.x; sq += v.y;
-                }
-                sm_ch[c] = make_double2(su, sq);
-            }
+            for (int c = threadIdx.x; c < C; c += blockDim.x)
+                sm_ch[c] = fold_stat_replicas(sums + ((long)n_fixed * stats_ld + c) * 2, rep_stride, rep);
             __syncthreads();
         }
         for (int g = threadIdx.x; g < ng; g += blockDim.x) {
@@ -128,10 +122,8 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
             if (cpg > 1) {
                 for (int j = 0; j < cpg; ++j) { const double2 v = sm_ch[g * cpg + j]; su += v.x; sq += v.y; }
             } else {
-                for (int r = 0; r < rep; ++r) {
-                    const double2 v = *reinterpret_cast<const double2*>(sums + r * rep_stride + ((long)n_fixed * stats_ld + g) * 2);
-                    su += v.x; sq += v.y;
-                }
+                const double2 v = fold_stat_replicas(sums + ((long)n_fixed * stats_ld + g) * 2, rep_stride, rep);
+                su = v.x; sq = v.y;
             }
             const double cnt = (double)HW * cpg;
             const double mean = su / cnt;

@@ -489,6 +489,16 @@ void SirenFaceNet::forward(Runtime& rt, const float* pose, int pose_ld, int B, f
     THA4_REQUIRE(loaded_, "network weights not loaded");
     const int R = 128;
     float* pb = pose_bias(rt, layers_[0], pose, pose_ld, B);
+    if (siren_tc_enabled()) {       // TMA + tcgen05 + TMEM path (siren_tc.cu)
+        SirenTcPlan plan;
+        for (int i = 1; i < 8; ++i) plan.add(layers_[i], 128, 1, 0);
+        plan.add(head_, 16, 0, 0);
+        SirenTcLevel lv;
+        lv.R = R; lv.B = B; lv.e_npad = layers_[0].NPAD; lv.e_pb = pb; lv.e_pb_ld = layers_[0].NPAD; lv.e_wxy = layers_[0].wxy;
+        lv.face_out = out; lv.head_bias = head_.bias;
+        siren_tc_run(rt, 3, plan, lv);
+        return;
+    }
     FaceLayers L;
     L.l[0] = lw(layers_[0], pb);
     for (int i = 1; i < 8; ++i) L.l[i] = lw(layers_[i]);
@@ -528,6 +538,34 @@ void SirenBodyNet::forward(Runtime& rt, const ImgView& image, const float* pose,
     float* pb2 = pose_bias(rt, l_[2][0], pose, pose_ld, B);
     __half* f0 = reinterpret_cast<__half*>(rt.persist->alloc((size_t)B * 128 * 128 * 192 / 2));
     __half* f1 = reinterpret_cast<__half*>(rt.persist->alloc((size_t)B * 256 * 256 * 96 / 2));
+    if (siren_tc_enabled()) {       // TMA + tcgen05 + TMEM path (siren_tc.cu): one persistent kernel per level
+        {
+            SirenTcPlan plan;
+            plan.add(l_[0][1], 192, 1, 0); plan.add(l_[0][2], 192, 1, 0);
+            SirenTcLevel lv;
+            lv.R = 128; lv.B = B; lv.e_npad = 384; lv.e_pb = pb0; lv.e_pb_ld = 384; lv.e_wxy = l_[0][0].wxy;
+            lv.out = f0; lv.out_c = 192;
+            siren_tc_run(rt, 0, plan, lv);
+        }
+        {
+            SirenTcPlan plan;
+            plan.add(l_[1][0], 96, 1, 1); plan.add(l_[1][1], 96, 1, 0); plan.add(l_[1][2], 96, 1, 0);
+            SirenTcLevel lv;
+            lv.R = 256; lv.B = B; lv.f_pb = pb1; lv.f_pb_ld = 192; lv.f_wxy = l_[1][0].wxy;
+            lv.prev = f0; lv.prev_c = 192; lv.out = f1; lv.out_c = 96;
+            siren_tc_run(rt, 1, plan, lv);
+        }
+        {
+            SirenTcPlan plan;
+            plan.add(l_[2][0], 96, 1, 1); plan.add(l_[2][1], 96, 1, 0); plan.add(l_[2][2], 96, 1, 0); plan.add(head_, 16, 0, 0);
+            SirenTcLevel lv;
+            lv.R = 512; lv.B = B; lv.f_pb = pb2; lv.f_pb_ld = 96; lv.f_wxy = l_[2][0].wxy;
+            lv.prev = f1; lv.prev_c = 96; lv.image = image; lv.head_bias = head_.bias;
+            for (int i = 0; i < 5; ++i) lv.o[i] = outputs[i];
+            siren_tc_run(rt, 2, plan, lv);
+        }
+        return;
+    }
     using SM0 = Smem<384, 384, 2>;
     using SM1 = Smem<192, 192, 3>;
     using SM2 = Smem<96, 96, 3>;

@@ -13,6 +13,25 @@ struct SirenLayer {
     void load(const StateDict& sd, const std::string& prefix, int feat, int pose, int kpad, int npad, float scale, cudaStream_t s);
 };
 
+// ---- tcgen05 path (siren_tc.cu): a level = a chain of GEMM layers on 128-pixel tiles, weights streamed by TMA ----
+struct SirenTcPlan {          // the GEMM layers of one kernel, in order
+    int nl = 0;
+    int kpad[8], npad[8], nb[8], sine[8], first[8], rows[8];
+    const void* W[8]; const float* bias[8];
+    void add(const SirenLayer& l, int nb, int sine, int first);
+};
+struct SirenTcLevel {
+    int R = 0, B = 0;
+    int e_npad = 0; const float* e_pb = nullptr; int e_pb_ld = 0; const float* e_wxy = nullptr;     // elementwise first layer (level 0, face)
+    const float* f_pb = nullptr; int f_pb_ld = 0; const float* f_wxy = nullptr;                       // first GEMM layer of levels 1 / 2
+    const __half* prev = nullptr; int prev_c = 0; __half* out = nullptr; int out_c = 0;
+    ImgView image; float* o[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* face_out = nullptr; const float* head_bias = nullptr;
+};
+void siren_tc_run(Runtime& rt, int mode, const SirenTcPlan& plan, const SirenTcLevel& lv);   // mode 0..2: body levels, 3: face
+void siren_tc_enable(bool on);
+bool siren_tc_enabled();
+
 class SirenFaceNet {
 public:
     void load(const StateDict& sd, cudaStream_t s);

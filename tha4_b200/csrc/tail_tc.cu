@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(TT_THREADS) tail_tc_kernel(const __grid_consta
     using Cfg = TailCfg<C>;
     constexpr int ROWB = Cfg::ROWB, TR = Cfg::TR, NCH = ROWB / 16;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic (not an integer round trip) keeps the shared address space: LDS / STS, not generic LD / ST
     uint8_t* smA = smem;
     uint8_t* smB = smem + Cfg::A_BYTES;
     double* chs = reinterpret_cast<double*>(smB + Cfg::B_BYTES);         // [C][2] folded statistics
@@ -102,12 +102,8 @@ __global__ void __launch_bounds__(TT_THREADS) tail_tc_kernel(const __grid_consta
     // ---- per-channel affine of the pending normalisation, from the producer's statistics ----
     const int cpg = p.groups == 0 ? 1 : C / p.groups;
     for (int c = tid; c < C; c += TT_THREADS) {
-        double su = 0.0, sq = 0.0;
-        for (int r = 0; r < p.stats_rep; ++r) {
-            const double2 v = *reinterpret_cast<const double2*>(p.stats + r * p.stats_rep_stride + ((long)n * p.stats_ld + c) * 2);
-            su += v.x; sq += v.y;
-        }
-        chs[2 * c] = su; chs[2 * c + 1] = sq;
+        const double2 v = fold_stat_replicas(p.stats + ((long)n * p.stats_ld + c) * 2, p.stats_rep_stride, p.stats_rep);
+        chs[2 * c] = v.x; chs[2 * c + 1] = v.y;
     }
     __syncthreads();
     const bool silu = p.act == ACT_SILU || p.act == ACT_SILU_FAST;

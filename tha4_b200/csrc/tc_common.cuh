@@ -19,14 +19,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar) : "memory");
 }
+// try_wait SUSPENDS the thread in hardware for up to the time hint (it is not a poll), so the loop body runs rarely; the
+// watchdog is an iteration count (a clock64() comparison per iteration made a waiting producer / MMA warp burn ~20 % of its
+// scheduler's issue slots in the persistent kernels: profiles/r02_ncu_siren_tc_v1.txt).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    const long long t0 = clock64();
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    for (uint32_t spins = 0; ; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");      // suspend-time hint: 20 us
         if (ok) break;
-        if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s watchdog: fail loudly instead of hanging the GPU
+        if (spins > 4000000u) __trap();                    // >= seconds without progress: fail loudly instead of hanging the GPU
     }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
