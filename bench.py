@@ -525,6 +525,8 @@ def main():
         if s.get('us', 0) > 0:
             ach = 37.89e9 * B * args.steps / (s['us'] * 1e-6) / 1e12
             line['roofline'].update(achieved=ach, frac=ach / peaks['tflops'])
+    line['cuda_graphs'] = {'replays': ctx.counter('graph_replays'), 'captures': ctx.counter('graph_captures'), 'failures': ctx.counter('graph_failures'),
+                           'note': 'single-chunk teacher forwards whose buffer addresses repeat are replayed as one captured graph (zero-copy)'}
     line.update(extras)
     if 'value' in extras.get('torch_cuda_eager', {}):
         line['torch_cuda_eager_fps'] = extras['torch_cuda_eager']['value']

@@ -112,6 +112,10 @@ int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, int64_t im
                          float* const* outputs, int eyebrow_morphed_image_index, const float* const* cached_decomposer, void* stream);
 /* mode 14: TwoStepPoserComputationProtocol (src/tha4/poser/modes/mode_14.py:40-90): body(5) + face(1) */
 int tha4_student_forward(tha4_ctx* ctx, const float* image, const float* pose, int B, float* const* outputs, void* stream);
+/* same with a storage type for the image and the six outputs: io_dtype 0 = fp32 (identical to the call above), 1 = fp16
+ * ("fp16 I/O + fp32 accumulate", BASELINE configs[2]: image [B,4,512,512] __half in, __half planes out; the pose stays
+ * fp32).  The arithmetic is the same: fp16 operands, fp32 accumulation, results rounded once on the store. */
+int tha4_student_forward_io(tha4_ctx* ctx, const void* image, const float* pose, int B, void* const* outputs, int io_dtype, void* stream);
 /* ---- distillation inner loop of the body student (replaces the autograd part of
  * SirenMorpherTrainingProtocol03.run_training_iteration, src/tha4/nn/siren/morpher/siren_morpher_protocols_03.py:178-214) ---- */
 /* number of fp32 parameters of SirenMorpher03 in state_dict order (331 567) */

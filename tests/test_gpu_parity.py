@@ -233,6 +233,17 @@ def test_mode_07_graph_replay_matches_eager(teacher_sds):
                 for a, b in zip(outs, eager[i]):
                     assert G.err(a.cpu(), b.cpu())[0] <= 1e-4, (rep, i)
         assert min(per_call) > 100, 'replayed graphs must keep counting their kernels: %s' % per_call
+        assert ctx.counter('graph_captures') >= 1 and ctx.counter('graph_replays') >= 6, \
+            (ctx.counter('graph_captures'), ctx.counter('graph_replays'))
+        # the pose is staged into a library buffer ahead of the graph, so a pose living at a new address every call
+        # (slices of a pose table) still replays
+        r0 = ctx.counter('graph_replays')
+        for i in range(3):
+            outs = None
+            outs = poser.get_posing_outputs(img, poses[i:i + 1])
+            for a, b in zip(outs, eager[i]):
+                assert G.err(a.cpu(), b.cpu())[0] <= 1e-4, i
+        assert ctx.counter('graph_replays') >= r0 + 3
 
 
 @pytest.mark.parametrize('strict', [1, 0])
@@ -325,6 +336,26 @@ def test_student_tcgen05_and_mma_paths_agree(lambda00_sds):
         ctx.set_option('siren_tc', 1)
     for i, (a, b) in enumerate(zip(outs[1], outs[0])):
         assert G.err(a, b)[1] <= 2e-3, (i, G.err(a, b))
+
+
+def test_student_fp16_io(lambda00_sds):
+    """BASELINE configs[2] "fp16 I/O + fp32 accumulate": a float16 image selects tha4_student_forward_io(io_dtype = 1).
+    Outputs are float16 and equal the fp32-I/O outputs up to one fp16 rounding of the image and of each result
+    (values in [-1, 1]: half an ulp = 2.5e-4; the image rounding moves warped pixels by at most the same)."""
+    poser = mode_14.create_poser(DEV, state_dicts=lambda00_sds)
+    img = image_io.load_rgba_png(os.path.join(os.path.dirname(__file__), 'golden', 'data', 'lambda_00.png'))
+    poses = synth.random_poses(3, seed=32)
+    imgs = img.unsqueeze(0).expand(3, -1, -1, -1).contiguous()
+    with torch.no_grad():
+        refs = O.mode_14_outputs(lambda00_sds, imgs, poses)
+        full = [t.cpu() for t in poser.get_posing_outputs(imgs.to(DEV), poses.to(DEV))]
+        half = poser.get_posing_outputs(imgs.to(DEV).half(), poses.to(DEV))
+    assert all(t.dtype == torch.float16 for t in half)
+    half = [t.float().cpu() for t in half]
+    _check_student('mode_14 fp16 I/O', half, refs)
+    for i, (a, b) in enumerate(zip(half, full)):
+        assert a.shape == b.shape
+        assert G.err(a, b)[0] <= 1.5e-3 and G.err(a, b)[1] <= 2e-4, (i, G.err(a, b))
 
 
 def test_default_mode_error_class_vs_torch_cuda_tf32(teacher_poser, teacher_sds):

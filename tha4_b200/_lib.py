@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     'tha4_ctx_create', 'tha4_ctx_destroy', 'tha4_last_error', 'tha4_set_option', 'tha4_get_counter', 'tha4_load_net',
     'tha4_eyebrow_decomposer_forward', 'tha4_eyebrow_morphing_combiner_forward', 'tha4_face_morpher_forward',
     'tha4_morpher_forward', 'tha4_upscaler_forward', 'tha4_siren_face_morpher_forward', 'tha4_siren_morpher_forward',
-    'tha4_teacher_forward', 'tha4_student_forward', 'tha4_siren_morpher_param_count', 'tha4_siren_morpher_train_step',
+    'tha4_teacher_forward', 'tha4_student_forward', 'tha4_student_forward_io', 'tha4_siren_morpher_param_count', 'tha4_siren_morpher_train_step',
     'tha4_siren_face_morpher_param_count', 'tha4_siren_face_morpher_train_step',
     'tha4_adam_step', 'tha4_images_differ', 'tha4_frame_to_srgb8', 'tha4_rgba8_to_poser_image', 'tha4_grid_sample', 'tha4_resize_bilinear',
     'tha4_base_grid', 'tha4_test_conv', 'tha4_test_conv_norm', 'tha4_test_norm', 'tha4_test_tail', 'tha4_test_attention', 'tha4_test_linear',
@@ -268,6 +268,24 @@ class Context:
         assert image.shape[1:] == (4, 512, 512) and pose.shape == (B, 45)
         outs = self._empty([(4, 512), (1, 512), (4, 512), (4, 512), (2, 512), (4, 128)], B)
         self._call('tha4_student_forward', _ptr(image), _ptr(pose), B, _ptr_array(outs), self._stream())
+        return outs
+
+    def student_forward_half(self, image: Tensor, pose: Tensor) -> List[Tensor]:
+        """fp16 I/O variant (io_dtype = 1): half image in, half outputs out; the pose stays float32."""
+        if image.device != self.device or image.dtype != torch.float16:
+            raise Tha4Error('image must be a float16 tensor on %s' % self.device)
+        image = image.contiguous()
+        pose = _check_input(pose, self.device, 'pose')
+        B = image.shape[0]
+        assert image.shape[1:] == (4, 512, 512) and pose.shape == (B, 45)
+        shapes = [(4, 512), (1, 512), (4, 512), (4, 512), (2, 512), (4, 128)]
+        flat = torch.empty(sum(B * c * r * r for c, r in shapes), dtype=torch.float16, device=self.device)
+        outs, o = [], 0
+        for c, r in shapes:
+            n = B * c * r * r
+            outs.append(flat[o:o + n].view(B, c, r, r))
+            o += n
+        self._call('tha4_student_forward_io', _ptr(image), _ptr(pose), B, _ptr_array(outs), 1, self._stream())
         return outs
 
     # ------------------------------------------------------------------ distillation

@@ -42,13 +42,16 @@ struct tha4_ctx {
     int use_graphs = 1;        // option "cuda_graphs" (default on): single-chunk teacher forwards replay as one graph launch
     std::map<std::vector<uintptr_t>, TeacherGraph> graphs;
     std::map<std::vector<uintptr_t>, int> graph_seen;      // how often a key was seen before it was captured
-    long graph_clock = 0, graph_misses = 0;
+    long graph_clock = 0, graph_misses = 0, graph_pause = 0, graph_replays = 0, graph_captures = 0, graph_failures = 0;
+    cudaStream_t capture_stream = nullptr;   // the legacy default stream cannot be captured: its graphs are recorded here and launched there
+    float* pose_stage = nullptr;   // [1024][45]: graphs read the pose from here, so the caller's pose address is not part of the key
     void drop_graphs() {
         for (auto& kv : graphs)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         graphs.clear();
         graph_seen.clear();
         graph_misses = 0;
+        graph_pause = 0;
     }
     std::string err;
     int strict = 0;
@@ -220,6 +223,8 @@ int tha4_ctx_destroy(tha4_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->flag) cudaFree(ctx->flag);
     if (ctx->loss_acc) cudaFree(ctx->loss_acc);
+    if (ctx->pose_stage) cudaFree(ctx->pose_stage);
+    if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
     if (ctx->stats_base) cudaFree(ctx->stats_base);
     ctx->drop_graphs();
     delete ctx;
@@ -261,6 +266,9 @@ int64_t tha4_get_counter(const tha4_ctx* ctx, const char* name) {
                         try { return (int64_t)prof_read(c, w); } catch (...) { return -1; }
                     }
     }
+    if (ctx && !strcmp(name, "graph_replays")) return (int64_t)ctx->graph_replays;
+    if (ctx && !strcmp(name, "graph_captures")) return (int64_t)ctx->graph_captures;
+    if (ctx && !strcmp(name, "graph_failures")) return (int64_t)ctx->graph_failures;
     if (ctx && !strcmp(name, "workspace_bytes")) return (int64_t)(ctx->persist.bytes() + ctx->scratch.bytes());
     return -1;
 }
@@ -399,11 +407,13 @@ int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, int64_t im
         };
         // ---- CUDA-graph path: single-chunk calls whose buffer addresses repeat ----
         cudaStream_t s = rt.stream;
-        if (ctx->use_graphs && B <= ctx->microbatch && !prof_enabled() && ctx->graph_misses < 64) {
+        if (ctx->graph_pause > 0) --ctx->graph_pause;
+        if (ctx->use_graphs && B <= ctx->microbatch && B <= 1024 && !prof_enabled() && ctx->graph_pause == 0) {
+            if (!ctx->pose_stage) THA4_CUDA_CHECK(cudaMalloc(&ctx->pose_stage, 1024 * 45 * sizeof(float)));
             std::vector<uintptr_t> key;
             key.reserve(nout + 12);
             key.push_back((uintptr_t)mode); key.push_back((uintptr_t)B); key.push_back((uintptr_t)eyebrow_morphed_image_index);
-            key.push_back((uintptr_t)img_sn); key.push_back((uintptr_t)image); key.push_back((uintptr_t)pose); key.push_back((uintptr_t)s);
+            key.push_back((uintptr_t)img_sn); key.push_back((uintptr_t)image); key.push_back((uintptr_t)s);
             for (int i = 0; i < nout; ++i) key.push_back((uintptr_t)outputs[i]);
             for (int i = 0; i < 6; ++i) key.push_back(cached_decomposer ? (uintptr_t)cached_decomposer[i] : 0);
             ++ctx->graph_clock;
@@ -413,31 +423,45 @@ int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, int64_t im
                 // the arena must be clean when the graph starts; its own first memset only knows the dirt that preceded the capture
                 if (ctx->stats_off > 0) THA4_CUDA_CHECK(cudaMemsetAsync(ctx->stats_base, 0, ctx->stats_off * sizeof(double), s));
                 ctx->stats_off = 0;
+                THA4_CUDA_CHECK(cudaMemcpyAsync(ctx->pose_stage, pose, (size_t)B * 45 * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 THA4_CUDA_CHECK(cudaGraphLaunch(g.exec, s));
                 g_kernel_launches.fetch_add(g.launches);
                 ctx->stats_off = g.stats_end;
                 g.last_use = ctx->graph_clock;
                 ctx->graph_misses = 0;
+                ++ctx->graph_replays;
                 return;
             }
-            ++ctx->graph_misses;
+            if (++ctx->graph_misses >= 64) { ctx->graph_misses = 0; ctx->graph_pause = 512; }   // buffers keep moving: eager for a while
             if (++ctx->graph_seen[key] >= 2) {           // second sight of this set of buffers: worth a capture
                 ctx->graph_seen.erase(key);
                 const long l0 = g_kernel_launches.load();
                 cudaGraph_t graph = nullptr;
                 cudaGraphExec_t exec = nullptr;
-                bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-                if (ok) {
-                    try { run(image, pose, outputs, cached_decomposer); }
-                    catch (const std::exception&) { ok = false; }
-                    const cudaError_t e = cudaStreamEndCapture(s, &graph);
-                    ok = ok && e == cudaSuccess && graph != nullptr;
+                THA4_CUDA_CHECK(cudaMemcpyAsync(ctx->pose_stage, pose, (size_t)B * 45 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                std::string why;
+                cudaStream_t cap = s;
+                if (s == nullptr || s == cudaStreamLegacy || s == cudaStreamPerThread) {
+                    if (!ctx->capture_stream) THA4_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
+                    cap = ctx->capture_stream;
                 }
-                if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+                bool ok = e == cudaSuccess;
+                if (!ok) why = std::string("begin: ") + cudaGetErrorString(e);
+                if (ok) {
+                    rt.stream = cap;
+                    try { run(image, ctx->pose_stage, outputs, cached_decomposer); }
+                    catch (const std::exception& ex) { ok = false; why = std::string("launch: ") + ex.what(); }
+                    rt.stream = s;
+                    e = cudaStreamEndCapture(cap, &graph);
+                    if (e != cudaSuccess || graph == nullptr) { if (ok) why = std::string("end: ") + cudaGetErrorString(e); ok = false; }
+                }
+                if (ok) { e = cudaGraphInstantiate(&exec, graph, 0); if (e != cudaSuccess) { ok = false; why = std::string("instantiate: ") + cudaGetErrorString(e); } }
                 if (graph) cudaGraphDestroy(graph);
                 if (!ok) {                               // not capturable here: run this call eagerly, stop trying for a while
+                    if (ctx->graph_failures++ == 0) fprintf(stderr, "tha4: CUDA graph capture failed (%s); launching eagerly\n", why.c_str());
                     cudaGetLastError();
-                    ctx->graph_misses = 64;
+                    ctx->graph_misses = 0; ctx->graph_pause = 512;
                     ctx->persist.reset(); ctx->scratch.reset();
                 } else {
                     if ((int)ctx->graphs.size() >= GRAPH_CACHE) {
@@ -450,6 +474,7 @@ int tha4_teacher_forward(tha4_ctx* ctx, int mode, const float* image, int64_t im
                     TeacherGraph g;
                     g.exec = exec; g.launches = g_kernel_launches.load() - l0; g.stats_end = ctx->stats_off; g.last_use = ctx->graph_clock;
                     ctx->graphs[key] = g;
+                    ++ctx->graph_captures;
                     // the capture recorded the work without running it: replay it now for this call
                     THA4_CUDA_CHECK(cudaGraphLaunch(exec, s));
                     return;
@@ -472,6 +497,26 @@ int tha4_student_forward(tha4_ctx* ctx, const float* image, const float* pose, i
         copy_window(make_img(image, B, 4, 512, 512), body_in, 4L * 512 * 512, 512L * 512, 512, s);
         copy_window(make_img(outputs[5], B, 4, 128, 128), body_in + 80 * 512 + 192, 4L * 512 * 512, 512L * 512, 512, s);
         ctx->sbody->forward(rt, make_img(body_in, B, 4, 512, 512), pose, 45, outputs);
+    });
+}
+
+int tha4_student_forward_io(tha4_ctx* ctx, const void* image, const float* pose, int B, void* const* outputs, int io_dtype, void* stream) {
+    if (io_dtype == 0) return tha4_student_forward(ctx, (const float*)image, pose, B, (float* const*)outputs, stream);
+    return guarded(ctx, [&] {
+        THA4_REQUIRE(io_dtype == 1, "student forward: io_dtype must be 0 (fp32) or 1 (fp16)");
+        Runtime rt = make_rt(ctx, stream);
+        cudaStream_t s = rt.stream;
+        begin_pass(ctx, (cudaStream_t)stream);
+        // fp16 image in, fp16 planes out; the sampled image and the face patch stay fp32 inside (the gather reads them four
+        // times per pixel from L2, the conversion is one pass over 4 MB per frame)
+        const long img_n = (long)B * 4 * 512 * 512, face_n = (long)B * 4 * 128 * 128;
+        float* body_in = ctx->persist.alloc((size_t)img_n);
+        float* face32 = ctx->persist.alloc((size_t)face_n);
+        ctx->sface->forward(rt, pose, 45, B, face32);
+        convert_flat_f32((const __half*)image, body_in, img_n, s);
+        copy_window(make_img(face32, B, 4, 128, 128), body_in + 80 * 512 + 192, 4L * 512 * 512, 512L * 512, 512, s);
+        convert_flat_f16(face32, (__half*)outputs[5], face_n, s);
+        ctx->sbody->forward(rt, make_img(body_in, B, 4, 512, 512), pose, 45, (float* const*)outputs, true);
     });
 }
 
@@ -651,6 +696,7 @@ int tha4_test_conv_norm(tha4_ctx* ctx, int kind, const float* x, int N, int Cin,
         const size_t wsf = conv_workspace_floats(cw, a);
         if (wsf) { a.ws = ctx->scratch.alloc(wsf); a.ws_floats = wsf; }
         conv_forward(cw, a, s);
+        if (getenv("THA4_HALO_DEBUG")) { conv_forward(cw, a, s); conv_halo_debug_dump(); }
         nhwc_to_nchw(yo, y, s);
         if (y_from_f16) {
             View back = mk(N, Ho, Wo, Cout);

@@ -22,6 +22,8 @@
 #include <tuple>
 
 namespace tha4 {
+static long long* g_dbg_buf = nullptr;   // THA4_HALO_DEBUG phase stamps
+
 namespace {
 
 using namespace tc;
@@ -62,6 +64,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
     float* xf_A = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot + 4) + ((16u - (tc::smem_u32(tmem_slot + 4) & 15u)) & 15u));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // developer timing: CTA `slot` of every 97 records clock64 at its phase boundaries (8 stamps per role: dbg[slot][role][8])
+    const bool dbg_on = p.dbg != nullptr && (blockIdx.x % 97) == 0 && blockIdx.y == 0 && (blockIdx.x / 97) * CS + blockIdx.z < 32;
+    long long* dbg = dbg_on ? p.dbg + ((blockIdx.x / 97) * CS + blockIdx.z) * 32 : nullptr;
+#define HSTAMP(role, i) do { if (dbg) dbg[(role) * 8 + (i)] = clock64(); } while (0)
+    if (threadIdx.x == 0) HSTAMP(0, 0);
     int tile = blockIdx.x;
     const int tx = tile % p.tiles_x; tile /= p.tiles_x;
     const int ty = tile % p.tiles_y;
@@ -90,6 +97,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) HSTAMP(0, 1);
     pdl_trigger();
     // weight tiles of the first ring pass do not depend on the previous kernel: fetch them ahead of the dependency wait
     const int npre = p.pre_b ? min(nb, SB) : 0;
@@ -101,6 +109,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
         }
     }
     pdl_wait();
+    if (threadIdx.x == 0) HSTAMP(0, 2);
 
     if (nc > 0) {
         if (warp == 0) {
@@ -127,6 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
                 for (int ci = 0; ci < nc; ++ci) {
                     const int sa = ci % SA;
                     mbar_wait(smem_u32((XF ? a_xf : a_full) + sa), (ci / SA) & 1);
+                    if (ci == 0) HSTAMP(1, 0);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint32_t a_base = smem_u32(smA + sa * A_BYTES);
                     for (int tap = 0; tap < 9; ++tap, ++bi) {
@@ -144,6 +154,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
                     umma_commit(smem_u32(a_empty + sa));                  // the halo of this chunk is free when its 9 taps retire
                 }
                 umma_commit(smem_u32(t_full));
+                HSTAMP(1, 1);
             }
         } else {
             if (XF) {          // ===== warps 2-5: normalise each chunk's halo ONCE, in place; then they are the epilogue =====
@@ -151,11 +162,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
                 __half* hA = reinterpret_cast<__half*>(xf_A);
                 __half* hB = hA + p.xf_C;
                 double2* chs = reinterpret_cast<double2*>(xf_A + 2 * p.xf_C);
-                xf_build_coef(p, n, te, hA, hB, chs);
+                xf_build_coef(p, n, te, hA, hB, chs, cb0 * KCE, (cb0 + nc) * KCE);
+                if (te == 0) HSTAMP(2, 0);
                 const bool silu = p.xf_act == ACT_SILU || p.xf_act == ACT_SILU_FAST;
                 for (int ci = 0; ci < nc; ++ci) {
                     const int sa = ci % SA;
                     mbar_wait(smem_u32(a_full + sa), (ci / SA) & 1);
+                    if (te == 0 && ci == 0) HSTAMP(2, 1);
                     const int c0 = (cb0 + ci) * KCE;
                     for (int row = te; row < HALO_ROWS; row += 128) {
                         const int hy = row / HALO_W, hx = row - hy * HALO_W;
@@ -166,24 +179,34 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
                     }
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                     mbar_arrive(smem_u32(a_xf + sa));
+                    if (te == 0 && ci == nc - 1) HSTAMP(2, 2);
                 }
             }
+            if (threadIdx.x == 64) { mbar_wait(smem_u32(t_full), 0); HSTAMP(2, 3); }
             if (CS > 1) epi_stage_partial<BN>(tmem_base, smem, smem_u32(t_full), warp, lane);
             else epi_direct<BN, HT_W>(p, tmem_base, smem, smem_u32(t_full), n, y0, x0, n0, 0, 0, warp, lane);
+            if (threadIdx.x == 64) HSTAMP(2, 4);
         }
     }
     if (CS > 1) {
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if (threadIdx.x == 64) HSTAMP(2, 5);
         if (warp >= 2) epi_cluster_reduce<BN, CS, HT_W>(p, smem, n, y0, x0, n0, 0, split, warp);
-        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if (threadIdx.x == 64) HSTAMP(2, 6);
+        // nothing is published through this barrier (it only keeps the partial tiles alive until every peer has read them):
+        // a relaxed arrive does not have to wait for this CTA's global stores
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");
+        if (threadIdx.x == 64) HSTAMP(2, 7);
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+    if (threadIdx.x == 0) HSTAMP(0, 3);
+#undef HSTAMP
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -253,8 +276,13 @@ HaloPlan halo_plan(const ConvWeights& cw, const ConvArgs& a, int op) {
     if (a.ksplit > 1) {
         while (pl.cs * 2 <= std::min(8, a.ksplit)) pl.cs *= 2;
     } else if (a.ksplit <= 0 && ctas < 120) {
-        // too few tiles to fill the GPU: split the channel chunks over a cluster and narrow the N tiles
-        int want = (int)((148 + ctas - 1) / ctas);
+        // Too few tiles to fill the GPU.  Narrow the N tiles first (down to 64 columns: more CTAs and nothing to exchange),
+        // then split the channel chunks over a cluster.  The DSMEM exchange moves 128 x bn x 4 x (cs-1)/cs bytes per CTA at
+        // ~11 B/clk: at bn = 256, cs = 4..8 it took twice as long as the MMA phase it parallelised (10 000 vs 4 700 cycles,
+        // profiles/r02_halo_phase_stamps.txt).
+        while (pl.bn > 64 && (long)pl.tiles_m * (cw.cout_pad / pl.bn) < 148 && cw.cout_pad % (pl.bn / 2) == 0) pl.bn /= 2;
+        ctas = (long)pl.tiles_m * (cw.cout_pad / pl.bn);
+        const int want = std::max(2, (int)((222 + ctas - 1) / ctas));       // >= 2: the cluster variants carry the deep weight ring
         while (pl.cs < 8 && pl.cs * 2 <= want && pl.cs * 2 <= pl.chunks) pl.cs *= 2;
         while (pl.bn > 32 && (long)pl.tiles_m * (cw.cout_pad / pl.bn) * pl.cs < 96 && cw.cout_pad % (pl.bn / 2) == 0) pl.bn /= 2;
     }
@@ -348,6 +376,12 @@ void conv_halo_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s)
     p.ws = nullptr;
     p.stats = a.out.stats; p.stats_ld = a.out.stats_ld;
     p.stats_rep = std::max(1, a.out.stats_rep); p.stats_rep_stride = a.out.stats_rep_stride;
+    static const bool dbg_env = getenv("THA4_HALO_DEBUG") != nullptr;
+    if (dbg_env) {
+        if (!g_dbg_buf) { THA4_CUDA_CHECK(cudaMalloc(&g_dbg_buf, 32 * 32 * sizeof(long long))); }
+        THA4_CUDA_CHECK(cudaMemsetAsync(g_dbg_buf, 0, 32 * 32 * sizeof(long long), s));
+        p.dbg = g_dbg_buf;
+    }
     ProfScope prof(PROF_CONV, s);
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * 9, 0.0);
     const CUtensorMap& ma = halo_activation_map(a.in, op);
@@ -359,6 +393,21 @@ void conv_halo_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s)
     } else {
         if (a.nin.on) launch_halo_bn<OP_F16N, 1>(pl.bn, pl.cs, ma, mb, p, grid, s);
         else launch_halo_bn<OP_F16N, 0>(pl.bn, pl.cs, ma, mb, p, grid, s);
+    }
+}
+
+// developer helper: prints the phase stamps of the last launch (THA4_HALO_DEBUG=1)
+void conv_halo_debug_dump() {
+    if (!g_dbg_buf) return;
+    std::vector<long long> h(32 * 32);
+    THA4_CUDA_CHECK(cudaDeviceSynchronize());
+    THA4_CUDA_CHECK(cudaMemcpy(h.data(), g_dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < 32; ++c) {
+        const long long* d = h.data() + c * 32;
+        if (!d[0]) continue;
+        auto rel = [&](long long v) { return v ? (long)(v - d[0]) : -1L; };
+        fprintf(stderr, "halo slot %2d: tmem %ld pdl %ld | coef %ld a_full %ld xf_done %ld | mma_first %ld mma_commit %ld | t_full %ld epi_done %ld | cl_bar1 %ld reduce %ld cl_bar2 %ld | end %ld\n",
+                c, rel(d[1]), rel(d[2]), rel(d[16]), rel(d[17]), rel(d[18]), rel(d[8]), rel(d[9]), rel(d[19]), rel(d[20]), rel(d[21]), rel(d[22]), rel(d[23]), rel(d[3]));
     }
 }
 

@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             __half* hA = reinterpret_cast<__half*>(xf_A);
             __half* hB = hA + p.xf_C;
             double2* chs = reinterpret_cast<double2*>(xf_A + 2 * p.xf_C); // per-channel (sum, sum of squares) folded over the replicas
-            xf_build_coef(p, n, te, hA, hB, chs);
+            int c_lo = 0, c_hi = p.xf_C;
+            { const int f = kb % p.cpt; if (f + nk <= p.cpt) { c_lo = f * KCE; c_hi = (f + nk) * KCE; } }   // k-blocks of one tap: a chunk range
+            xf_build_coef(p, n, te, hA, hB, chs, c_lo, c_hi);
             const bool silu = p.xf_act == ACT_SILU || p.xf_act == ACT_SILU_FAST;
             const int ry = te / TILE_W, rx = te % TILE_W;
             constexpr int NCH = ROWB / 16;                               // 16-byte chunks (8 channels) per operand row
@@ -404,6 +406,10 @@ TcPlan tc_plan(const ConvWeights& cw, const ConvArgs& a) {
     const int KT = cw.ntaps * (cw.cin_pad / op_kch(op_for(cw, a)));
     int ksplit = a.ksplit;
     if (ksplit <= 0) {
+        // few tiles: narrow the N tiles first (nothing to exchange), split K only for what is still missing -- the DSMEM
+        // exchange of a cluster split grows with bn (conv_halo.cu, halo_plan)
+        while (pl.bn > 64 && (long)pl.tiles_m * (cw.cout_pad / pl.bn) * cw.nphase < 148 && cw.cout_pad % (pl.bn / 2) == 0) pl.bn /= 2;
+        pl.tiles_n = cw.cout_pad / pl.bn;
         const long ctas = (long)pl.tiles_m * pl.tiles_n * cw.nphase;
         ksplit = 1;
         if (ctas < 120) {

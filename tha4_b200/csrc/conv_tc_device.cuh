@@ -27,6 +27,7 @@ struct TcParams {
     float acc_scale;                               // accumulator scale (undoes the power-of-two normalisation of the f16 weights)
     float* ws; long ws_rows; int ws_ld;            // split-K partials: ws[z][tile*128 + row][cout_pad]
     double* stats; int stats_ld; int stats_rep; long stats_rep_stride;   // per-(n,c) sum / sum-of-squares of the output (optional)
+    long long* dbg;                                // developer option: per-phase clock64 stamps of a few CTAs (conv_halo.cu), else null
     __half* out16; int out16_ld;                   // optional f16 copy of the output (the operand format of a consumer conv); out may be null then
     // ---- fused input normalisation (XF kernels): the A operand is the RAW f16 output of the producing conv; its pending
     // InstanceNorm / GroupNorm (+FiLM) affine and activation are applied in shared memory between TMA and tcgen05.mma
@@ -58,13 +59,17 @@ __host__ __device__ constexpr int op_stages(int op, int stages) { return op == O
 // ===== fused input normalisation (XF kernels) =====
 // Per-channel affine of sample n's pending normalisation, as packed halves (the operand is f16; HFMA2 / tanh.approx.f16x2
 // keep the in-place pass cheap).  Called by the 128 threads of warps 2-5 (te = 0..127); chs: scratch [xf_C] double2.
-__device__ __forceinline__ void xf_build_coef(const TcParams& p, int n, int te, __half* hA, __half* hB, double2* chs) {
+// [c_lo, c_hi): the channels this CTA will transform (its K chunks); widened to whole normalisation groups.  A cluster
+// split-K CTA builds 1 / CS of the table (the fold of the statistic replicas is the expensive part: 4.8 us for 512 channels).
+__device__ __forceinline__ void xf_build_coef(const TcParams& p, int n, int te, __half* hA, __half* hB, double2* chs, int c_lo, int c_hi) {
     const int cpg = p.xf_groups == 0 ? 1 : p.xf_C / p.xf_groups;
-    for (int c = te; c < p.xf_C; c += 128)
+    c_lo = (c_lo / cpg) * cpg;
+    c_hi = min(p.xf_C, ((c_hi + cpg - 1) / cpg) * cpg);
+    for (int c = c_lo + te; c < c_hi; c += 128)
         chs[c] = fold_stat_replicas(p.in_stats + ((long)n * p.in_stats_ld + c) * 2, p.in_stats_rep_stride, p.in_stats_rep);
     asm volatile("bar.sync 1, 128;\n" ::: "memory");
     const bool silu = p.xf_act == ACT_SILU || p.xf_act == ACT_SILU_FAST;
-    for (int c = te; c < p.xf_C; c += 128) {
+    for (int c = c_lo + te; c < c_hi; c += 128) {
         const int g0 = (c / cpg) * cpg;
         double su = 0.0, sq = 0.0;
         for (int j = 0; j < cpg; ++j) { const double2 v = chs[g0 + j]; su += v.x; sq += v.y; }
@@ -256,18 +261,49 @@ __device__ __forceinline__ void epi_cluster_reduce(const TcParams& p, uint8_t* s
     const int col = n0 + chunk * 4;
     const uint32_t p_local = smem_u32(smem);
     float su[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+    // A thread finishes SC rows (rows te / SC + i * 128 / SC).  The CS remote partials of U rows are requested before any is
+    // consumed: a DSMEM load takes ~0.3-0.5 us, and issued one row at a time they were half of the kernel (phase stamps:
+    // 15 000 of 29 000 cycles on 256 channels at 64x64, profiles/r02_halo_phase_stamps.txt).
+    constexpr int RSTEP = 128 / SC;
+    constexpr int U = (SC < (16 / CS > 0 ? 16 / CS : 1)) ? SC : (16 / CS > 0 ? 16 / CS : 1);
+    static_assert(SC % U == 0, "cluster reduce: batch");
 #pragma unroll 1
-    for (int row = te / SC; row < 128; row += 128 / SC) {
-        const uint32_t off = (uint32_t)(row * BN + ((chunk ^ (row & 7)) << 2)) * 4u;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int rb = 0; rb < SC; rb += U) {
+        float4 part[U][CS];
 #pragma unroll
-        for (int pr = 0; pr < CS; ++pr) {
-            uint32_t remote;
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(p_local + off), "r"(pr));
-            float4 v;
-            asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote));
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        for (int u = 0; u < U; ++u) {
+            const int row = te / SC + (rb + u) * RSTEP;
+            const uint32_t off = (uint32_t)(row * BN + ((chunk ^ (row & 7)) << 2)) * 4u;
+#pragma unroll
+            for (int pr = 0; pr < CS; ++pr) {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(p_local + off), "r"(pr));
+                asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                             : "=f"(part[u][pr].x), "=f"(part[u][pr].y), "=f"(part[u][pr].z), "=f"(part[u][pr].w) : "r"(remote));
+            }
         }
+        // the residual rows of the batch are requested up front as well (L2 round trips)
+        float rres[U][4];
+        const bool res_direct = p.res_mode == RES_SAME || p.res_mode == RES_UP2;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            rres[u][0] = rres[u][1] = rres[u][2] = rres[u][3] = 0.0f;
+            const int row = te / SC + (rb + u) * RSTEP;
+            const int my = y0 + row / TW, mx = x0 + row % TW;
+            if (res_direct && my < p.MH && mx < p.MW && col < p.outC) {
+                const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
+                const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
+                const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + col;
+                const int cn = min(4, p.outC - col);
+                for (int j = 0; j < cn; ++j) rres[u][j] = rr[j];
+            }
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int row = te / SC + (rb + u) * RSTEP;
+        float4 acc = part[u][0];
+#pragma unroll
+        for (int pr = 1; pr < CS; ++pr) { acc.x += part[u][pr].x; acc.y += part[u][pr].y; acc.z += part[u][pr].z; acc.w += part[u][pr].w; }
         acc.x *= p.acc_scale; acc.y *= p.acc_scale; acc.z *= p.acc_scale; acc.w *= p.acc_scale;
         const int my = y0 + row / TW, mx = x0 + row % TW;
         if (my >= p.MH || mx >= p.MW || col >= p.outC) continue;
@@ -275,10 +311,8 @@ __device__ __forceinline__ void epi_cluster_reduce(const TcParams& p, uint8_t* s
         float v[4] = {acc.x, acc.y, acc.z, acc.w};
         const int cn = min(4, p.outC - col);
         if (p.bias) for (int j = 0; j < cn; ++j) v[j] += __ldg(p.bias + col + j);
-        if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
-            const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
-            const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + col;
-            for (int j = 0; j < cn; ++j) v[j] += rr[j];
+        if (res_direct) {
+            for (int j = 0; j < cn; ++j) v[j] += rres[u][j];
         } else if (p.res_mode == RES_DOWN2) {
             const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + col;
             const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
@@ -300,6 +334,7 @@ __device__ __forceinline__ void epi_cluster_reduce(const TcParams& p, uint8_t* s
             } else for (int j = 0; j < cn; ++j) o16[j] = __float2half_rn(v[j]);
         }
         for (int j = 0; j < cn; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
+      }
     }
     if (p.stats) {
         // per-column sums of this CTA's slice: thread te holds partials of chunk te % SC; fold the 128 / SC row

@@ -257,6 +257,14 @@ void convert_f16(const View& src, const View& dst, cudaStream_t s) {
     THA4_LAUNCH_CHECK();
 }
 
+void convert_flat_f16(const float* src, __half* dst, long n, cudaStream_t s) {
+    convert_f16_kernel<<<grid_for(n), 256, 0, s>>>(src, 1, dst, 1, 1, n);
+    THA4_LAUNCH_CHECK();
+}
+void convert_flat_f32(const __half* src, float* dst, long n, cudaStream_t s) {
+    convert_f32_kernel<<<grid_for(n), 256, 0, s>>>(src, 1, dst, 1, 1, n);
+    THA4_LAUNCH_CHECK();
+}
 void convert_f32(const View& src, const View& dst, cudaStream_t s) {
     THA4_REQUIRE(src.f16 && !dst.f16 && src.C == dst.C && src.pixels() == dst.pixels(), "convert_f32: views");
     const long total = (long)src.pixels() * src.C;

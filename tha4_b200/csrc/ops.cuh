@@ -45,6 +45,8 @@ void nhwc_to_nchw(const View& src, float* dst, cudaStream_t s);                 
 void copy_window(const ImgView& src, float* dst, long dn, long dc, long dh, cudaStream_t s);  // strided NCHW copy
 void tile_vector(const float* vec, int vec_ld, int P, const View& dst, cudaStream_t s); // dst[n,y,x,c] = c<P ? vec[n][c] : 0  (dst fp32 or f16)
 void convert_f16(const View& src, const View& dst, cudaStream_t s);                      // fp32 view -> f16 view (tests)
+void convert_flat_f16(const float* src, __half* dst, long n, cudaStream_t s);               // element-wise, same layout
+void convert_flat_f32(const __half* src, float* dst, long n, cudaStream_t s);
 void convert_f32(const View& src, const View& dst, cudaStream_t s);                      // f16 view -> fp32 view (tests)
 void resize_bilinear(const ImgView& src, float* dst, int Ho, int Wo, cudaStream_t s);   // align_corners=False
 void grid_sample(const ImgView& image, const float* grid_change, float* out, int* x0, int* y0, float* tx, float* ty,

@@ -528,7 +528,7 @@ void SirenBodyNet::load(const StateDict& sd, cudaStream_t s) {
     loaded_ = true;
 }
 
-void SirenBodyNet::forward(Runtime& rt, const ImgView& image, const float* pose, int pose_ld, float* const* outputs) {
+void SirenBodyNet::forward(Runtime& rt, const ImgView& image, const float* pose, int pose_ld, float* const* outputs, bool outputs_f16) {
     THA4_REQUIRE(loaded_, "network weights not loaded");
     THA4_REQUIRE(image.H == 512 && image.W == 512 && image.C == 4, "siren body: image size");
     const int B = image.N;
@@ -562,10 +562,12 @@ void SirenBodyNet::forward(Runtime& rt, const ImgView& image, const float* pose,
             lv.R = 512; lv.B = B; lv.f_pb = pb2; lv.f_pb_ld = 96; lv.f_wxy = l_[2][0].wxy;
             lv.prev = f1; lv.prev_c = 96; lv.image = image; lv.head_bias = head_.bias;
             for (int i = 0; i < 5; ++i) lv.o[i] = outputs[i];
+            lv.o_f16 = outputs_f16;
             siren_tc_run(rt, 2, plan, lv);
         }
         return;
     }
+    THA4_REQUIRE(!outputs_f16, "siren body: f16 outputs need the tcgen05 path (option siren_tc)");
     using SM0 = Smem<384, 384, 2>;
     using SM1 = Smem<192, 192, 3>;
     using SM2 = Smem<96, 96, 3>;

@@ -25,7 +25,7 @@ struct SirenTcLevel {
     int e_npad = 0; const float* e_pb = nullptr; int e_pb_ld = 0; const float* e_wxy = nullptr;     // elementwise first layer (level 0, face)
     const float* f_pb = nullptr; int f_pb_ld = 0; const float* f_wxy = nullptr;                       // first GEMM layer of levels 1 / 2
     const __half* prev = nullptr; int prev_c = 0; __half* out = nullptr; int out_c = 0;
-    ImgView image; float* o[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ImgView image; float* o[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; bool o_f16 = false;
     float* face_out = nullptr; const float* head_bias = nullptr;
 };
 void siren_tc_run(Runtime& rt, int mode, const SirenTcPlan& plan, const SirenTcLevel& lv);   // mode 0..2: body levels, 3: face
@@ -48,7 +48,8 @@ class SirenBodyNet {
 public:
     void load(const StateDict& sd, cudaStream_t s);
     // image: [B,4,512,512]; pose: [B,45]; outputs: blended(4) alpha(1) colour(4) warped(4) grid_change(2), fp32 NCHW
-    void forward(Runtime& rt, const ImgView& image, const float* pose, int pose_ld, float* const* outputs);
+    // outputs_f16: the five output planes are __half (io_dtype = f16 of tha4_student_forward_io; tcgen05 path only)
+    void forward(Runtime& rt, const ImgView& image, const float* pose, int pose_ld, float* const* outputs, bool outputs_f16 = false);
     bool loaded() const { return loaded_; }
 private:
     AllocSink owned_;

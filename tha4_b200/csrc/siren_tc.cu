@@ -52,7 +52,7 @@ struct StParams {
     const float* base;                              // affine_grid coordinates of this resolution
     const __half* prev; int prev_c;                 // previous level's output [B, R/2, R/2, prev_c] (bilinear x2 prologue)
     __half* out; int out_c;                         // this level's output [B, R, R, out_c] (levels 0 / 1)
-    ImgView image; float* o[5];                     // level 2: tail
+    ImgView image; float* o[5]; int o_f16;          // level 2: tail (o_f16: the five outputs are __half planes, io_dtype = f16)
     float* face_out;                                // face: [B, 4, R, R]
     const float* head_bias;
 };
@@ -308,15 +308,28 @@ __global__ void __launch_bounds__(ST_THREADS) siren_tc_kernel(const __grid_const
                         gs_sample<4>(p.image.p + n * p.image.sn, p.image.sc, p.image.sh, p.R, p.R, t, w);
                         const size_t plane = (size_t)p.R * p.R, pix = (size_t)y * p.R + x;
                         const float alpha = o[2];
+                        if (p.o_f16) {
+                            __half* const* oh = reinterpret_cast<__half* const*>(p.o);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            p.o[0][((size_t)n * 4 + c) * plane + pix] = (1.0f - alpha) * w[c] + alpha * o[3 + c];
-                            p.o[2][((size_t)n * 4 + c) * plane + pix] = o[3 + c];
-                            p.o[3][((size_t)n * 4 + c) * plane + pix] = w[c];
+                            for (int c = 0; c < 4; ++c) {
+                                oh[0][((size_t)n * 4 + c) * plane + pix] = __float2half_rn((1.0f - alpha) * w[c] + alpha * o[3 + c]);
+                                oh[2][((size_t)n * 4 + c) * plane + pix] = __float2half_rn(o[3 + c]);
+                                oh[3][((size_t)n * 4 + c) * plane + pix] = __float2half_rn(w[c]);
+                            }
+                            oh[1][(size_t)n * plane + pix] = __float2half_rn(alpha);
+                            oh[4][((size_t)n * 2) * plane + pix] = __float2half_rn(o[0]);
+                            oh[4][((size_t)n * 2 + 1) * plane + pix] = __float2half_rn(o[1]);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                p.o[0][((size_t)n * 4 + c) * plane + pix] = (1.0f - alpha) * w[c] + alpha * o[3 + c];
+                                p.o[2][((size_t)n * 4 + c) * plane + pix] = o[3 + c];
+                                p.o[3][((size_t)n * 4 + c) * plane + pix] = w[c];
+                            }
+                            p.o[1][(size_t)n * plane + pix] = alpha;
+                            p.o[4][((size_t)n * 2) * plane + pix] = o[0];
+                            p.o[4][((size_t)n * 2 + 1) * plane + pix] = o[1];
                         }
-                        p.o[1][(size_t)n * plane + pix] = alpha;
-                        p.o[4][((size_t)n * 2) * plane + pix] = o[0];
-                        p.o[4][((size_t)n * 2 + 1) * plane + pix] = o[1];
                     }
                     asm volatile("bar.sync 1, 128;\n" ::: "memory");          // sx / sfirst / the operand are rewritten by the next tile
                 }
@@ -407,6 +420,7 @@ void siren_tc_run(Runtime& rt, int mode, const SirenTcPlan& plan, const SirenTcL
     p.prev = lv.prev; p.prev_c = lv.prev_c; p.out = lv.out; p.out_c = lv.out_c;
     p.image = lv.image;
     for (int i = 0; i < 5; ++i) p.o[i] = lv.o[i];
+    p.o_f16 = lv.o_f16 ? 1 : 0;
     p.face_out = lv.face_out; p.head_bias = lv.head_bias;
     cudaStream_t s = rt.stream;
     ProfScope prof(PROF_SIREN, s);

@@ -52,8 +52,10 @@ class TwoStepPoserComputationProtocol(CachedComputationProtocol):
         if key == self.keys.all_outputs:
             for name in (self.keys.face_morpher, self.keys.body_morpher):
                 state.modules[name].sync_weights()
-            outputs = state.context.student_forward(state.batch[self.indices.original_image],
-                                                    state.batch[self.indices.original_pose])
+            image = state.batch[self.indices.original_image]
+            # a float16 image selects the fp16 I/O entry point (tha4_student_forward_io, io_dtype = 1): half outputs
+            forward = state.context.student_forward_half if image.dtype == torch.float16 else state.context.student_forward
+            outputs = forward(image, state.batch[self.indices.original_pose].float())
             state.outputs[self.keys.body_morpher_output] = outputs[0:5]
             state.outputs[self.keys.face_morpher_output] = outputs[5]
             return outputs
