@@ -242,6 +242,7 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         else if (!strcmp(name, "tcgen05")) conv_enable_tc(value != 0);
         else if (!strcmp(name, "cluster_splitk")) conv_tc_enable_cluster(value != 0);
         else if (!strcmp(name, "halo_conv")) conv_halo_enable(value != 0);
+        else if (!strcmp(name, "tma_store")) conv_halo_enable_tma_store(value != 0);
         else if (!strcmp(name, "siren_tc")) siren_tc_enable(value != 0);
         else if (!strcmp(name, "tc_stride2")) conv_tc_enable_stride2(value != 0);
         else if (!strcmp(name, "small_bn")) conv_tc_enable_small_bn(value != 0);

@@ -94,6 +94,7 @@ bool conv_tc_fuses_stats(const ConvWeights& cw, const ConvArgs& a);
 bool conv_halo_supported(const ConvWeights& cw, const ConvArgs& a);
 void conv_halo_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s);
 void conv_halo_enable(bool on);
+void conv_halo_enable_tma_store(bool on);
 void conv_halo_debug_dump();   // developer: THA4_HALO_DEBUG=1 phase stamps of the last halo launch
 void conv_enable_tc(bool on);
 bool conv_tc_enabled();

@@ -44,6 +44,7 @@ __host__ __device__ constexpr int halo_a_bytes(int rowb) { return ((HALO_ROWS * 
 // or OP_F16N (32 channels, 64-byte rows).  p.ksplit = cluster size CS (split over channel chunks), p.cpt = chunks.
 template <int BN, int SA, int SB, int CS, int OP, int XF>
 __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
                                                                 const TcParams p) {
     static_assert(OP != OP_TF32, "halo kernel: f16 operands");
     constexpr int ROWB = op_row_bytes(OP);
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
     constexpr int B_BYTES = BN * ROWB;
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     constexpr uint32_t LAYOUT = ROWB == 128 ? 2u : 4u;
+    constexpr int NSLOT = CS == 1 ? epi_nslot(BN, (size_t)SA * A_BYTES + (size_t)SB * B_BYTES) : 0;     // TMA-store staging slots of the unsplit epilogue
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);      // pointer arithmetic (not an integer round trip) keeps the shared address space: LDS / STS, not generic LD / ST
     uint8_t* smA = smem;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
             }
             if (threadIdx.x == 64) { mbar_wait(smem_u32(t_full), 0); HSTAMP(2, 3); }
             if (CS > 1) epi_stage_partial<BN>(tmem_base, smem, smem_u32(t_full), warp, lane);
-            else epi_direct<BN, HT_W>(p, tmem_base, smem, smem_u32(t_full), n, y0, x0, n0, 0, 0, warp, lane);
+            else epi_direct<BN, HT_W, NSLOT>(p, tmem_base, smem, smem_u32(t_full), n, y0, x0, n0, 0, 0, warp, lane, &tmO32, &tmO16);
             if (threadIdx.x == 64) HSTAMP(2, 4);
         }
     }
@@ -263,6 +265,30 @@ const CUtensorMap& halo_weight_map(const ConvWeights& cw, int bn, int op) {
     return g_halo_maps.emplace(key, m).first->second;
 }
 
+// Output tile of the unsplit epilogue: box {32 channels, 16 x 8 pixels}, rows of 128 bytes (fp32) / 64 bytes (f16), swizzled
+// like the staging writes of epi_direct.  Returns false when the view cannot be described (alignment).
+bool halo_store_map(const View& v, bool f16, const CUtensorMap** out) {
+    const int es = f16 ? 2 : 4;
+    if (!v.p || (reinterpret_cast<uintptr_t>(v.p) & 15) || ((long)v.ld * es) % 16 != 0) return false;
+    HKey key{current_device(), v.p, v.N, v.H, v.W, v.C, v.ld, f16 ? -2 : -3};
+    std::lock_guard<std::mutex> lock(g_halo_mu);
+    auto it = g_halo_maps.find(key);
+    if (it == g_halo_maps.end()) {
+        CUtensorMap m;
+        cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+        cuuint64_t strides[3] = {(cuuint64_t)v.ld * es, (cuuint64_t)v.W * v.ld * es, (cuuint64_t)v.H * v.W * v.ld * es};
+        cuuint32_t box[4] = {32, (cuuint32_t)HT_W, (cuuint32_t)HT_H, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = halo_encode()(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, v.p, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+        it = g_halo_maps.emplace(key, m).first;
+    }
+    *out = &it->second;
+    return true;
+}
+
 struct HaloPlan { int bn, tiles_x, tiles_y, tiles_m, tiles_n, cs, chunks; };
 
 HaloPlan halo_plan(const ConvWeights& cw, const ConvArgs& a, int op) {
@@ -292,7 +318,7 @@ HaloPlan halo_plan(const ConvWeights& cw, const ConvArgs& a, int op) {
 }
 
 template <int OP, int BN, int SA, int SB, int CS, int XF>
-void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
+void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const TcParams& p, dim3 grid, cudaStream_t s) {
     constexpr int ROWB = op_row_bytes(OP);
     constexpr size_t ring = (size_t)SA * halo_a_bytes(ROWB) + (size_t)SB * BN * ROWB;
     constexpr size_t smem0 = 1024 + ring + (3 * SA + 2 * SB + 1) * 8 + 16;
@@ -302,7 +328,7 @@ void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p
     const size_t smem = smem0 + (XF ? (size_t)24 * p.xf_C + 32 : 0);
     THA4_REQUIRE(smem <= 227 * 1024, "conv_halo: shared memory budget (fused input normalisation)");
     THA4_ENSURE_SMEM((conv_halo_kernel<BN, SA, SB, CS, OP, XF>), smem);
-    launch_pdl(conv_halo_kernel<BN, SA, SB, CS, OP, XF>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, p);
+    launch_pdl(conv_halo_kernel<BN, SA, SB, CS, OP, XF>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, mo32, mo16, p);
     THA4_LAUNCH_CHECK();
 }
 
@@ -310,27 +336,29 @@ void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p
 // that are fetched ahead of the dependency wait); SBS: depth of the unsplit launches (many tiles: a shallow ring keeps
 // the CTA small so that 2 - 4 of them share an SM and overlap each other's load -> transform -> MMA -> drain chains).
 template <int OP, int BN, int SA, int SBD, int SBS, int XF>
-void launch_halo_cs(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
-    if (cs == 8) launch_halo<OP, BN, SA, SBD, 8, XF>(ma, mb, p, grid, s);
-    else if (cs == 4) launch_halo<OP, BN, SA, SBD, 4, XF>(ma, mb, p, grid, s);
-    else if (cs == 2) launch_halo<OP, BN, SA, SBD, 2, XF>(ma, mb, p, grid, s);
-    else launch_halo<OP, BN, SA, SBS, 1, XF>(ma, mb, p, grid, s);
+void launch_halo_cs(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const TcParams& p, dim3 grid, cudaStream_t s) {
+    if (cs == 8) launch_halo<OP, BN, SA, SBD, 8, XF>(ma, mb, mo32, mo16, p, grid, s);
+    else if (cs == 4) launch_halo<OP, BN, SA, SBD, 4, XF>(ma, mb, mo32, mo16, p, grid, s);
+    else if (cs == 2) launch_halo<OP, BN, SA, SBD, 2, XF>(ma, mb, mo32, mo16, p, grid, s);
+    else launch_halo<OP, BN, SA, SBS, 1, XF>(ma, mb, mo32, mo16, p, grid, s);
 }
 
 template <int OP, int XF>
-void launch_halo_bn(int bn, int cs, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t s) {
+void launch_halo_bn(int bn, int cs, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const TcParams& p, dim3 grid, cudaStream_t s) {
     constexpr int M = OP == OP_F16N ? 2 : 1;        // 64-byte rows: twice the stages for the same bytes in flight
-    if (bn == 256) launch_halo_cs<OP, 256, 2 * M, 4 * M, 2 * M, XF>(cs, ma, mb, p, grid, s);        // unsplit: 111 KB -> 2 CTAs / SM
-    else if (bn == 128) launch_halo_cs<OP, 128, 2 * M, 6 * M, 3 * M, XF>(cs, ma, mb, p, grid, s);   // unsplit:  95 KB -> 2 CTAs / SM
-    else if (bn == 64) launch_halo_cs<OP, 64, 2 * M, 8 * M, 3 * M, XF>(cs, ma, mb, p, grid, s);     // unsplit:  71 KB -> 3 CTAs / SM
-    else launch_halo_cs<OP, 32, 2 * M, 9 * M, 5 * M, XF>(cs, ma, mb, p, grid, s);                    // unsplit:  67 KB -> 3 CTAs / SM
+    if (bn == 256) launch_halo_cs<OP, 256, 2 * M, 4 * M, 2 * M, XF>(cs, ma, mb, mo32, mo16, p, grid, s);        // unsplit: 111 KB -> 2 CTAs / SM
+    else if (bn == 128) launch_halo_cs<OP, 128, 2 * M, 6 * M, 3 * M, XF>(cs, ma, mb, mo32, mo16, p, grid, s);   // unsplit:  95 KB -> 2 CTAs / SM
+    else if (bn == 64) launch_halo_cs<OP, 64, 2 * M, 8 * M, 3 * M, XF>(cs, ma, mb, mo32, mo16, p, grid, s);     // unsplit:  71 KB -> 3 CTAs / SM
+    else launch_halo_cs<OP, 32, 2 * M, 9 * M, 5 * M, XF>(cs, ma, mb, mo32, mo16, p, grid, s);                    // unsplit:  67 KB -> 3 CTAs / SM
 }
 
 bool g_use_halo = true;
+bool g_tma_store = true;      // option "tma_store": unsplit epilogue through shared-memory staging + TMA stores
 
 }  // namespace
 
 void conv_halo_enable(bool on) { g_use_halo = on; }
+void conv_halo_enable_tma_store(bool on) { g_tma_store = on; }
 
 bool conv_halo_supported(const ConvWeights& cw, const ConvArgs& a) {
     if (!g_use_halo || !conv_tc_supported(cw, a)) return false;
@@ -386,13 +414,22 @@ void conv_halo_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s)
     prof_add_work(PROF_CONV, 2.0 * (double)p.N * p.MH * p.MW * cw.cout * cw.cin * 9, 0.0);
     const CUtensorMap& ma = halo_activation_map(a.in, op);
     const CUtensorMap& mb = halo_weight_map(cw, pl.bn, op);
+    const CUtensorMap* mo32 = &ma;                   // placeholders when an output does not leave through TMA
+    const CUtensorMap* mo16 = &ma;
+    p.st_tma = 0;
+    if (pl.cs == 1 && g_tma_store) {
+        if (a.out.p && halo_store_map(a.out, false, &mo32)) p.st_tma |= 1;
+        if (a.out16.p && halo_store_map(a.out16, true, &mo16)) p.st_tma |= 2;
+    }
+    p.vec4 = ((!cw.bias || (reinterpret_cast<uintptr_t>(cw.bias) & 15) == 0) &&
+              (!a.res.p || ((reinterpret_cast<uintptr_t>(a.res.p) & 15) == 0 && a.res.ld % 4 == 0))) ? 1 : 0;
     dim3 grid(pl.tiles_m, pl.tiles_n, pl.cs);
     if (op == OP_F16) {
-        if (a.nin.on) launch_halo_bn<OP_F16, 1>(pl.bn, pl.cs, ma, mb, p, grid, s);
-        else launch_halo_bn<OP_F16, 0>(pl.bn, pl.cs, ma, mb, p, grid, s);
+        if (a.nin.on) launch_halo_bn<OP_F16, 1>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
+        else launch_halo_bn<OP_F16, 0>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
     } else {
-        if (a.nin.on) launch_halo_bn<OP_F16N, 1>(pl.bn, pl.cs, ma, mb, p, grid, s);
-        else launch_halo_bn<OP_F16N, 0>(pl.bn, pl.cs, ma, mb, p, grid, s);
+        if (a.nin.on) launch_halo_bn<OP_F16N, 1>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
+        else launch_halo_bn<OP_F16N, 0>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
     }
 }
 

@@ -28,6 +28,8 @@ struct TcParams {
     float* ws; long ws_rows; int ws_ld;            // split-K partials: ws[z][tile*128 + row][cout_pad]
     double* stats; int stats_ld; int stats_rep; long stats_rep_stride;   // per-(n,c) sum / sum-of-squares of the output (optional)
     long long* dbg;                                // developer option: per-phase clock64 stamps of a few CTAs (conv_halo.cu), else null
+    int st_tma;                                    // unsplit epilogue: bit 0 / bit 1 = the fp32 / f16 output tile leaves through a TMA store (conv_halo.cu)
+    int vec4;                                      // bias / residual rows may be read as float4 (16-byte aligned, ld % 4 == 0)
     __half* out16; int out16_ld;                   // optional f16 copy of the output (the operand format of a consumer conv); out may be null then
     // ---- fused input normalisation (XF kernels): the A operand is the RAW f16 output of the producing conv; its pending
     // InstanceNorm / GroupNorm (+FiLM) affine and activation are applied in shared memory between TMA and tcgen05.mma
@@ -141,9 +143,26 @@ __device__ __forceinline__ void epi_stage_partial(uint32_t tmem_base, uint8_t* s
 }
 
 // ===== unsplit / workspace split-K epilogue (epilogue warps): TMEM -> registers -> global (+ statistics) =====
-template <int BN, int TW>
+// NSLOT > 0 (and p.st_tma): the finished 128 x 32 tile of each column step is staged in shared memory in the swizzled box
+// layout and written by ONE TMA store per output (fp32 / f16) instead of 12 warp-wide stores whose 32 lanes hit 32 different
+// lines (32 L1 wavefronts per instruction: the store phase was ~1500 LSU cycles per tile, a third of the epilogue).  TMA
+// clips what lies outside the tensor (partial tiles, channel tails).  Slots live behind the statistics scratch in the idle
+// pipeline buffers; a slot is rewritten only after its store has read it (bulk-group wait).
+constexpr int EPI_SLOT_BYTES = 128 * 128 + 128 * 64;           // fp32 stage (128-byte rows) + f16 stage (64-byte rows)
+__host__ __device__ constexpr int epi_slot0(int bn) { return (4 * 32 * 33 * 4 + 4 * bn * 8 + 1023) & ~1023; }
+__host__ __device__ constexpr int epi_nslot(int bn, size_t ring) {
+    return ring < (size_t)epi_slot0(bn) + EPI_SLOT_BYTES ? 0
+         : ((int)((ring - epi_slot0(bn)) / EPI_SLOT_BYTES) < bn / 32 ? (int)((ring - epi_slot0(bn)) / EPI_SLOT_BYTES) : bn / 32);
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n"
+                 :: "l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+template <int BN, int TW, int NSLOT = 0>
 __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base, uint8_t* smem, uint32_t tmem_full_bar, int n, int y0, int x0,
-                                           int n0, int phase, int split, int warp, int lane) {
+                                           int n0, int phase, int split, int warp, int lane,
+                                           const CUtensorMap* tm32 = nullptr, const CUtensorMap* tm16 = nullptr) {
     const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -155,6 +174,8 @@ __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base
     const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
     const long opix = ((long)n * p.outH + oy) * p.outW + ox;
     float* orow = p.out + opix * p.out_ld;
+    const int st_tma = NSLOT > 0 ? p.st_tma : 0;
+    int step = 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -168,15 +189,32 @@ __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base
         const bool to_ws = p.ksplit > 1 && p.ws;
         if (valid) {
             if (lead && !to_ws) {
+                const bool v4 = p.vec4 && cn == 32;
                 if (p.bias) {
+                    if (v4) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += __ldg(p.bias + cbase + j);
+                    }
                 }
                 if (p.res_mode == RES_SAME || p.res_mode == RES_UP2) {
                     const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
                     const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + cbase;
+                    if (v4) {       // 8 requests of 32 sectors instead of 32 requests of 32 sectors
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (j < cn) v[j] += rr[j];
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(rr + j);
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < cn) v[j] += rr[j];
+                    }
                 } else if (p.res_mode == RES_DOWN2) {
                     const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + cbase;
                     const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
@@ -194,7 +232,7 @@ __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base
 #pragma unroll
                 for (int j = 0; j < 32; ++j) if (j < cn) atomicAdd(orow + cbase + j, v[j]);
             } else {
-                if (p.out) {
+                if (p.out && !(st_tma & 1)) {
                     if (cn == 32) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -204,7 +242,7 @@ __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base
                         for (int j = 0; j < 32; ++j) if (j < cn) orow[cbase + j] = v[j];
                     }
                 }
-                if (p.out16) {          // f16 copy: the operand a consumer conv loads by TMA (raw value; its norm is applied there)
+                if (p.out16 && !(st_tma & 2)) {          // f16 copy: the operand a consumer conv loads by TMA (raw value; its norm is applied there)
                     __half* hrow = p.out16 + opix * p.out16_ld + cbase;
                     if (cn == 32) {
 #pragma unroll
@@ -221,6 +259,39 @@ __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base
                     }
                 }
             }
+        }
+        if (NSLOT > 0 && st_tma) {
+            // every row is staged (rows outside the image hold values of zero-padded inputs; the store clips them)
+            if (step >= NSLOT) {
+                if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read %0;\n" :: "n"(NSLOT > 0 ? NSLOT - 1 : 0) : "memory");
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            }
+            uint8_t* slot = smem + epi_slot0(BN) + (NSLOT > 0 ? step % NSLOT : 0) * EPI_SLOT_BYTES;
+            if (st_tma & 1) {
+                uint8_t* rp = slot + row * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(rp + ((j ^ (row & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (st_tma & 2) {
+                uint8_t* rp = slot + 128 * 128 + row * 64;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 pk;
+                    __half2* h2 = reinterpret_cast<__half2*>(&pk);
+                    h2[0] = __floats2half2_rn(v[8 * j], v[8 * j + 1]); h2[1] = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+                    h2[2] = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]); h2[3] = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+                    *reinterpret_cast<uint4*>(rp + ((j ^ ((row >> 1) & 3)) << 4)) = pk;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            if (threadIdx.x == 64) {
+                if (st_tma & 1) tma_store_4d(tm32, smem_u32(slot), cbase, x0, y0, n);
+                if (st_tma & 2) tma_store_4d(tm16, smem_u32(slot + 128 * 128), cbase, x0, y0, n);
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            }
+            ++step;
         }
         if (p.stats && p.ksplit == 1) {
             // per-channel sum / sum of squares over this warp's 32 pixels: transpose through shared memory,
@@ -248,6 +319,7 @@ __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base
             atomicAdd(base + 2 * c + 1, (double)a.y + (double)b.y + (double)cc.y + (double)d.y);
         }
     }
+    if (NSLOT > 0 && st_tma && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // stores complete before the CTA retires
 }
 
 // ===== cluster split-K, step 2 (epilogue warps, after the cluster barrier): DSMEM reduction of this CTA's column slice =====
