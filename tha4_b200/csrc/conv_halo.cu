@@ -17,6 +17,7 @@
 #include "profiler.cuh"
 #include "conv_tc_device.cuh"
 #include <cuda.h>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -42,8 +43,13 @@ __host__ __device__ constexpr int halo_a_bytes(int rowb) { return ((HALO_ROWS * 
 
 // SA / SB: stages of the activation-halo ring / of the weight-tile ring.  OP: OP_F16 (64 channels per chunk, 128-byte rows)
 // or OP_F16N (32 channels, 64-byte rows).  p.ksplit = cluster size CS (split over channel chunks), p.cpt = chunks.
+// MINB: resident CTAs per SM the register allocation must allow (4 for the single-chunk unsplit variants, whose small
+// rings fit four times: the layers at 256x256 / 512x512 are chains of dependent latencies, more CTAs = more overlap)
+__host__ __device__ constexpr int halo_min_ctas(int bn, int sa, int cs, int op) {
+    return cs > 1 ? 1 : ((sa == (op == OP_F16N ? 2 : 1) && bn <= 64) ? 4 : (bn >= 128 ? 2 : 3));
+}
 template <int BN, int SA, int SB, int CS, int OP, int XF>
-__global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+__global__ void __launch_bounds__(TC_THREADS, halo_min_ctas(BN, SA, CS, OP)) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
                                                                 const TcParams p) {
     static_assert(OP != OP_TF32, "halo kernel: f16 operands");
@@ -185,22 +191,23 @@ __global__ void __launch_bounds__(TC_THREADS) conv_halo_kernel(const __grid_cons
                 }
             }
             if (threadIdx.x == 64) { mbar_wait(smem_u32(t_full), 0); HSTAMP(2, 3); }
-            if (CS > 1) epi_stage_partial<BN>(tmem_base, smem, smem_u32(t_full), warp, lane);
+            if (CS > 1) { mbar_wait(smem_u32(t_full), 0); asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }   // own accumulator complete
             else epi_direct<BN, HT_W, NSLOT>(p, tmem_base, smem, smem_u32(t_full), n, y0, x0, n0, 0, 0, warp, lane, &tmO32, &tmO16);
             if (threadIdx.x == 64) HSTAMP(2, 4);
         }
     }
     if (CS > 1) {
+        // barrier A: every CTA of the cluster has its accumulator and idle pipeline buffers -> peers may write into them
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         if (threadIdx.x == 64) HSTAMP(2, 5);
-        if (warp >= 2) epi_cluster_reduce<BN, CS, HT_W>(p, smem, n, y0, x0, n0, 0, split, warp);
-        if (threadIdx.x == 64) HSTAMP(2, 6);
-        // nothing is published through this barrier (it only keeps the partial tiles alive until every peer has read them):
-        // a relaxed arrive does not have to wait for this CTA's global stores
-        asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
-        asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");
+        if (warp >= 2 && nc > 0) epi_push_partial<BN, CS>(tmem_base, smem, split, warp, lane);
+        // barrier B: the pushed slices are visible to their owners; nobody touches a peer's memory afterwards
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         if (threadIdx.x == 64) HSTAMP(2, 7);
+        if (warp >= 2) epi_cluster_reduce<BN, CS, HT_W>(p, smem, n, y0, x0, n0, 0, split, warp, dbg);
+        if (threadIdx.x == 64) HSTAMP(2, 6);
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -337,6 +344,12 @@ void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap
 // the CTA small so that 2 - 4 of them share an SM and overlap each other's load -> transform -> MMA -> drain chains).
 template <int OP, int BN, int SA, int SBD, int SBS, int XF>
 void launch_halo_cs(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const TcParams& p, dim3 grid, cudaStream_t s) {
+    if constexpr (BN <= 64) {
+        if (cs == 1 && p.cpt == 1) {     // one chunk: one halo, ever -> a ring that fits four times per SM
+            launch_halo<OP, BN, (OP == OP_F16N ? 2 : 1), SBS, 1, XF>(ma, mb, mo32, mo16, p, grid, s);
+            return;
+        }
+    }
     if (cs == 8) launch_halo<OP, BN, SA, SBD, 8, XF>(ma, mb, mo32, mo16, p, grid, s);
     else if (cs == 4) launch_halo<OP, BN, SA, SBD, 4, XF>(ma, mb, mo32, mo16, p, grid, s);
     else if (cs == 2) launch_halo<OP, BN, SA, SBD, 2, XF>(ma, mb, mo32, mo16, p, grid, s);
@@ -431,6 +444,13 @@ void conv_halo_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s)
         if (a.nin.on) launch_halo_bn<OP_F16N, 1>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
         else launch_halo_bn<OP_F16N, 0>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
     }
+    static const bool dbg_all = dbg_env && !strcmp(getenv("THA4_HALO_DEBUG"), "2");
+    if (dbg_all) {       // developer: stamps of every launch of a real forward (serialises the stream)
+        fprintf(stderr, "halo launch: N %d %dx%d cin %d cout %d | bn %d cs %d chunks %d grid %d x %d | xf %d groups %d act %d res %d out32 %d out16 %d st_tma %d\n",
+                p.N, p.MH, p.MW, cw.cin, cw.cout, pl.bn, pl.cs, pl.chunks, pl.tiles_m, pl.tiles_n, a.nin.on ? 1 : 0, p.xf_groups, p.xf_act,
+                p.res_mode, p.out ? 1 : 0, p.out16 ? 1 : 0, p.st_tma);
+        conv_halo_debug_dump();
+    }
 }
 
 // developer helper: prints the phase stamps of the last launch (THA4_HALO_DEBUG=1)
@@ -443,8 +463,8 @@ void conv_halo_debug_dump() {
         const long long* d = h.data() + c * 32;
         if (!d[0]) continue;
         auto rel = [&](long long v) { return v ? (long)(v - d[0]) : -1L; };
-        fprintf(stderr, "halo slot %2d: tmem %ld pdl %ld | coef %ld a_full %ld xf_done %ld | mma_first %ld mma_commit %ld | t_full %ld epi_done %ld | cl_bar1 %ld reduce %ld cl_bar2 %ld | end %ld\n",
-                c, rel(d[1]), rel(d[2]), rel(d[16]), rel(d[17]), rel(d[18]), rel(d[8]), rel(d[9]), rel(d[19]), rel(d[20]), rel(d[21]), rel(d[22]), rel(d[23]), rel(d[3]));
+        fprintf(stderr, "halo slot %2d: tmem %ld pdl %ld | coef %ld a_full %ld xf_done %ld | mma_first %ld mma_commit %ld | t_full %ld epi_done %ld | bar_A %ld pushed+bar_B %ld (loads issued %ld stored %ld) reduce_done %ld | end %ld\n",
+                c, rel(d[1]), rel(d[2]), rel(d[16]), rel(d[17]), rel(d[18]), rel(d[8]), rel(d[9]), rel(d[19]), rel(d[20]), rel(d[21]), rel(d[23]), rel(d[25]), rel(d[24]), rel(d[22]), rel(d[3]));
     }
 }
 

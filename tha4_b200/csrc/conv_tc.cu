@@ -170,18 +170,20 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
                 mbar_arrive(smem_u32(bars + 2 * STAGES + 1 + s));
             }
           }
-          if (CS > 1) epi_stage_partial<BN>(tmem_base, smem, smem_u32(bars + 2 * STAGES), warp, lane);
+          if (CS > 1) { mbar_wait(smem_u32(bars + 2 * STAGES), 0); asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }   // own accumulator complete
           else epi_direct<BN, TILE_W>(p, tmem_base, smem, smem_u32(bars + 2 * STAGES), n, y0, x0, n0, phase, split, warp, lane);
         }
     }
     if (CS > 1) {
-        // ---- cluster split-K reduction through distributed shared memory ----
+        // ---- cluster split-K reduction through distributed shared memory (conv_tc_device.cuh) ----
+        // barrier A: every CTA of the cluster has its accumulator and idle pipeline buffers -> peers may write into them
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if (warp >= 2 && nk > 0) epi_push_partial<BN, CS>(tmem_base, smem, split, warp, lane);
+        // barrier B: the pushed slices are visible to their owners; nobody touches a peer's memory afterwards
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
         if (warp >= 2) epi_cluster_reduce<BN, CS, TILE_W>(p, smem, n, y0, x0, n0, phase, split, warp);
-        // peers may still be reading this CTA's shared memory: leave together
-        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -516,6 +518,8 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
     }
     p.bias = cw.bias;
     p.res = a.res.p; p.res_mode = a.res.p ? a.res_mode : RES_NONE;
+    p.vec4 = ((!cw.bias || (reinterpret_cast<uintptr_t>(cw.bias) & 15) == 0) &&
+              (!a.res.p || ((reinterpret_cast<uintptr_t>(a.res.p) & 15) == 0 && a.res.ld % 4 == 0))) ? 1 : 0;
     p.resH = a.res.H; p.resW = a.res.W; p.res_ld = a.res.ld;
     p.N = a.in.N;
     p.out_mul = cw.out_mul;

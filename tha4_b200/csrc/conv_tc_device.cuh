@@ -121,14 +121,20 @@ __device__ __forceinline__ void xf_row(uint8_t* rowp, int swz, int c0, const TcP
     }
 }
 
-// ===== cluster split-K, step 1 (epilogue warps): TMEM -> this CTA's shared-memory partial tile =====
-template <int BN>
-__device__ __forceinline__ void epi_stage_partial(uint32_t tmem_base, uint8_t* smem, uint32_t tmem_full_bar, int warp, int lane) {
+// ===== cluster split-K, step 1 (epilogue warps, after a cluster barrier that says every peer's accumulator is complete and
+// its pipeline buffers are idle): TMEM -> the OWNER's shared memory.  Rank r of the cluster finishes columns
+// [r * SL, (r + 1) * SL); every CTA PUSHES the slice of its partial that belongs to rank r into slot [sender] of rank r's
+// buffer with st.shared::cluster (posted stores).  The pull version (ld.shared::cluster after staging locally) ran one remote
+// load per warp at a time: 16 KB took 6 500 cycles (profiles/r02_halo_phase_stamps.txt).
+// Buffer of a CTA: [CS slots][128 rows x SC 16-byte chunks], chunk index L = row * SC + cc stored at L ^ ((L >> 3) & 7)
+// (writers -- lanes = rows -- and readers -- lanes = consecutive L -- both spread over the banks).
+template <int BN, int CS>
+__device__ __forceinline__ void epi_push_partial(uint32_t tmem_base, uint8_t* smem, int split, int warp, int lane) {
+    constexpr int SL = BN / CS, SC = SL / 4;
+    constexpr uint32_t SLOT_BYTES = 128u * SL * 4u;
     const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const int row = q * 32 + lane;
-    float* Pt = reinterpret_cast<float*>(smem);                // [128][BN] fp32, 16-byte chunks XOR-swizzled by row
+    const uint32_t base = smem_u32(smem) + (uint32_t)split * SLOT_BYTES;       // slot [sender = this rank] in every owner's buffer
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -136,8 +142,16 @@ __device__ __forceinline__ void epi_stage_partial(uint32_t tmem_base, uint8_t* s
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int chunk = (c0 >> 2) + j;
-            *reinterpret_cast<float4*>(Pt + row * BN + ((chunk ^ (row & 7)) << 2)) =
-                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            const int owner = chunk / SC, cc = chunk - owner * SC;
+            const uint32_t L = (uint32_t)(row * SC + cc);
+            const uint32_t addr = base + ((L ^ ((L >> 3) & 7u)) << 4);
+            if (owner == split) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" :: "r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+            } else {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(addr), "r"(owner));
+                asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" :: "r"(remote), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+            }
         }
     }
 }
@@ -322,9 +336,11 @@ __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base
     if (NSLOT > 0 && st_tma && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // stores complete before the CTA retires
 }
 
-// ===== cluster split-K, step 2 (epilogue warps, after the cluster barrier): DSMEM reduction of this CTA's column slice =====
+// ===== cluster split-K, step 2 (epilogue warps, after the cluster barrier that publishes the pushes): sum the CS slots of this
+// CTA's column slice from its own shared memory, finish the columns =====
 template <int BN, int CS, int TW>
-__device__ __forceinline__ void epi_cluster_reduce(const TcParams& p, uint8_t* smem, int n, int y0, int x0, int n0, int phase, int split, int warp) {
+__device__ __forceinline__ void epi_cluster_reduce(const TcParams& p, uint8_t* smem, int n, int y0, int x0, int n0, int phase, int split, int warp,
+                                                   long long* dbg = nullptr) {
     constexpr int SL = BN / CS, SC = SL / 4;                   // columns / 16-byte chunks finished by this CTA
     static_assert(SL >= 4 && 128 % SC == 0, "cluster slice");
     const int te = threadIdx.x - 64;                           // 0..127
@@ -333,71 +349,89 @@ __device__ __forceinline__ void epi_cluster_reduce(const TcParams& p, uint8_t* s
     const int col = n0 + chunk * 4;
     const uint32_t p_local = smem_u32(smem);
     float su[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
-    // A thread finishes SC rows (rows te / SC + i * 128 / SC).  The CS remote partials of U rows are requested before any is
-    // consumed: a DSMEM load takes ~0.3-0.5 us, and issued one row at a time they were half of the kernel (phase stamps:
-    // 15 000 of 29 000 cycles on 256 channels at 64x64, profiles/r02_halo_phase_stamps.txt).
+    // A thread finishes SC rows (rows te / SC + i * 128 / SC), U at a time: the slot reads and the residual rows of a batch
+    // are all requested before the first is consumed.
     constexpr int RSTEP = 128 / SC;
     constexpr int U = (SC < (16 / CS > 0 ? 16 / CS : 1)) ? SC : (16 / CS > 0 ? 16 / CS : 1);
     static_assert(SC % U == 0, "cluster reduce: batch");
+    const int r0 = te / SC;
+    const int cn = max(0, min(4, p.outC - col));
+    const bool fast = cn == 4 && p.vec4;                       // 16-byte bias / residual reads
+    const bool res_direct = p.res_mode == RES_SAME || p.res_mode == RES_UP2, up2 = p.res_mode == RES_UP2;
+    const int poy = p.ph_oy[phase], pox = p.ph_ox[phase];
+    float bias4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (p.bias) for (int j = 0; j < cn; ++j) bias4[j] = __ldg(p.bias + col + j);
 #pragma unroll 1
     for (int rb = 0; rb < SC; rb += U) {
         float4 part[U][CS];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int row = te / SC + (rb + u) * RSTEP;
-            const uint32_t off = (uint32_t)(row * BN + ((chunk ^ (row & 7)) << 2)) * 4u;
+            const int row = r0 + (rb + u) * RSTEP;
+            const uint32_t L = (uint32_t)(row * SC + cc);
+            const uint32_t off = (L ^ ((L >> 3) & 7u)) << 4;
 #pragma unroll
-            for (int pr = 0; pr < CS; ++pr) {
-                uint32_t remote;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(p_local + off), "r"(pr));
-                asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];\n"
-                             : "=f"(part[u][pr].x), "=f"(part[u][pr].y), "=f"(part[u][pr].z), "=f"(part[u][pr].w) : "r"(remote));
-            }
+            for (int pr = 0; pr < CS; ++pr)          // slot pr = the partial pushed by rank pr (fixed summation order)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                             : "=f"(part[u][pr].x), "=f"(part[u][pr].y), "=f"(part[u][pr].z), "=f"(part[u][pr].w)
+                             : "r"(p_local + (uint32_t)pr * (128u * SL * 4u) + off));
         }
-        // the residual rows of the batch are requested up front as well (L2 round trips)
+        if (dbg && threadIdx.x == 64 && rb == 0) dbg[3 * 8 + 1] = clock64();
+        // the residual rows of the batch are requested up front as well (L2 round trips).  Index arithmetic stays in 32 bits up
+        // to the one widening multiply by the row stride: with 64-bit products throughout, this loop was ~250 dependent
+        // instructions per row on one warp per scheduler -- 6 500 cycles, the longest phase of the kernel (phase stamps).
         float rres[U][4];
-        const bool res_direct = p.res_mode == RES_SAME || p.res_mode == RES_UP2;
+        int opix[U];
+        bool ok[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             rres[u][0] = rres[u][1] = rres[u][2] = rres[u][3] = 0.0f;
-            const int row = te / SC + (rb + u) * RSTEP;
+            const int row = r0 + (rb + u) * RSTEP;
             const int my = y0 + row / TW, mx = x0 + row % TW;
-            if (res_direct && my < p.MH && mx < p.MW && col < p.outC) {
-                const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
-                const int ry = p.res_mode == RES_UP2 ? (oy >> 1) : oy, rx = p.res_mode == RES_UP2 ? (ox >> 1) : ox;
-                const float* rr = p.res + (((long)n * p.resH + ry) * p.resW + rx) * p.res_ld + col;
-                const int cn = min(4, p.outC - col);
-                for (int j = 0; j < cn; ++j) rres[u][j] = rr[j];
+            const int oy = my * p.out_mul + poy, ox = mx * p.out_mul + pox;
+            ok[u] = my < p.MH && mx < p.MW && col < p.outC;
+            opix[u] = (n * p.outH + oy) * p.outW + ox;
+            if (res_direct && ok[u]) {
+                const int rpix = up2 ? (n * p.resH + (oy >> 1)) * p.resW + (ox >> 1) : (n * p.resH + oy) * p.resW + ox;
+                const float* rr = p.res + (long)rpix * p.res_ld + col;
+                if (fast) {
+                    const float4 t = *reinterpret_cast<const float4*>(rr);
+                    rres[u][0] = t.x; rres[u][1] = t.y; rres[u][2] = t.z; rres[u][3] = t.w;
+                } else {
+                    for (int j = 0; j < cn; ++j) rres[u][j] = rr[j];
+                }
             }
         }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int row = te / SC + (rb + u) * RSTEP;
         float4 acc = part[u][0];
 #pragma unroll
         for (int pr = 1; pr < CS; ++pr) { acc.x += part[u][pr].x; acc.y += part[u][pr].y; acc.z += part[u][pr].z; acc.w += part[u][pr].w; }
-        acc.x *= p.acc_scale; acc.y *= p.acc_scale; acc.z *= p.acc_scale; acc.w *= p.acc_scale;
-        const int my = y0 + row / TW, mx = x0 + row % TW;
-        if (my >= p.MH || mx >= p.MW || col >= p.outC) continue;
-        const int oy = my * p.out_mul + p.ph_oy[phase], ox = mx * p.out_mul + p.ph_ox[phase];
-        float v[4] = {acc.x, acc.y, acc.z, acc.w};
-        const int cn = min(4, p.outC - col);
-        if (p.bias) for (int j = 0; j < cn; ++j) v[j] += __ldg(p.bias + col + j);
+        if (!ok[u]) continue;
+        float v[4] = {acc.x * p.acc_scale + bias4[0], acc.y * p.acc_scale + bias4[1], acc.z * p.acc_scale + bias4[2], acc.w * p.acc_scale + bias4[3]};
         if (res_direct) {
-            for (int j = 0; j < cn; ++j) v[j] += rres[u][j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] += rres[u][j];
         } else if (p.res_mode == RES_DOWN2) {
-            const float* rr = p.res + (((long)n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + col;
+            const int row = r0 + (rb + u) * RSTEP;
+            const int oy = (y0 + row / TW) * p.out_mul + poy, ox = (x0 + row % TW) * p.out_mul + pox;
+            const float* rr = p.res + (long)((n * p.resH + 2 * oy) * p.resW + 2 * ox) * p.res_ld + col;
             const long dx1 = p.res_ld, dy1 = (long)p.resW * p.res_ld;
-            for (int j = 0; j < cn; ++j) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+            if (fast) {       // four 16-byte loads in flight instead of sixteen dependent scalar ones
+                const float4 a = *reinterpret_cast<const float4*>(rr), b = *reinterpret_cast<const float4*>(rr + dx1);
+                const float4 c = *reinterpret_cast<const float4*>(rr + dy1), d = *reinterpret_cast<const float4*>(rr + dy1 + dx1);
+                v[0] += 0.25f * ((a.x + b.x) + (c.x + d.x)); v[1] += 0.25f * ((a.y + b.y) + (c.y + d.y));
+                v[2] += 0.25f * ((a.z + b.z) + (c.z + d.z)); v[3] += 0.25f * ((a.w + b.w) + (c.w + d.w));
+            } else {
+                for (int j = 0; j < cn; ++j) v[j] += 0.25f * ((rr[j] + rr[dx1 + j]) + (rr[dy1 + j] + rr[dy1 + dx1 + j]));
+            }
         }
-        const long opix = ((long)n * p.outH + oy) * p.outW + ox;
         if (p.out) {
-            float* o = p.out + opix * p.out_ld + col;
+            float* o = p.out + (long)opix[u] * p.out_ld + col;
             if (cn == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
             else for (int j = 0; j < cn; ++j) o[j] = v[j];
         }
         if (p.out16) {
-            __half* o16 = p.out16 + opix * p.out16_ld + col;
+            __half* o16 = p.out16 + (long)opix[u] * p.out16_ld + col;
             if (cn == 4) {
                 uint2 pk;
                 __half2* h2 = reinterpret_cast<__half2*>(&pk);
@@ -408,6 +442,7 @@ __device__ __forceinline__ void epi_cluster_reduce(const TcParams& p, uint8_t* s
         for (int j = 0; j < cn; ++j) { su[j] += v[j]; sq[j] += v[j] * v[j]; }
       }
     }
+    if (dbg && threadIdx.x == 64) dbg[3 * 8 + 0] = clock64();
     if (p.stats) {
         // per-column sums of this CTA's slice: thread te holds partials of chunk te % SC; fold the 128 / SC row
         // threads of each chunk in two short steps (8 floats per thread, then <= 16 doubles per output)
