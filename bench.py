@@ -332,7 +332,8 @@ def roofline_objects(prof, steps, peaks, traffic):
         out['roofline_tail'] = {'kernel': 'fused decoder tail (head conv + grid_sample + blend), all teacher sites of the step', 'bound': 'hbm',
                                 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
                                 'traffic': traffic.get('tail', {}).get('dram_bytes_per_launch'), 'traffic_source': traffic.get('tail', {}).get('source'),
-                                'peak_source': peaks['source'], 'avg_launch_us': t['us'] / max(1, t['launches'])}
+                                'peak_source': peaks['source'], 'avg_launch_us': t['us'] / max(1, t['launches']),
+                                'algorithmic_bytes_per_launch': t['bytes'] / max(1, t['launches'])}
     out['kernel_time_us_per_step'] = {k: v['us'] / steps for k, v in prof.items() if v['us'] > 0}
     return out
 

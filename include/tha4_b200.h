@@ -47,18 +47,27 @@ const char* tha4_last_error(const tha4_ctx* ctx);
 
 /* options: "strict" (0: tensor-core products on 10-bit-mantissa operands (f16 / TF32), fp32 accumulate -- the class of the
  *                       reference's own default on CUDA (cuDNN TF32 convs);
- *                    1: 3xTF32 error-compensated products == fp32 convolution; weights are re-uploaded on change),
+ *                    1: 3xTF32 error-compensated products == fp32 convolution; weights are re-uploaded on change;
+ *                       teacher networks only -- the SIREN students always run fp16 operands / fp32 accumulate),
  *          "microbatch" (frames processed per pass of the teacher pipeline, default 32; bounds the workspace),
+ *          "cuda_graphs" (default 1: a single-chunk teacher forward whose buffer set -- image, stream, output and cached
+ *                         pointers -- repeats is captured once and replayed as one graph launch, writing the caller's
+ *                         tensors directly; the pose is staged, so its address may change),
  *          developer switches, default = the measured-best setting:
- *          "tcgen05" (1: convs on the tcgen05/TMA/TMEM kernel; 0: everything on mma.sync),
- *          "half_operands" (1: tensors between a normalisation layer and a tcgen05 conv are f16),
+ *          "tcgen05" (1: convs on the tcgen05/TMA/TMEM kernels; 0: everything on mma.sync),
+ *          "half_operands" (1: f16 conv operands, normalisations fused into the consumer conv's operand path),
+ *          "halo_conv" (1: 3x3 stride-1 convs on the halo-reuse kernel), "tma_store" (1: unsplit conv epilogue through TMA stores),
  *          "cluster_splitk" (1: K-split convs reduce through a thread-block cluster / DSMEM; 0: workspace + reduce kernel),
- *          "pdl" (1: programmatic dependent launch on conv / norm kernels), "tc_stride2" (1: 4x4 stride-2 convs on tcgen05),
- *          "small_bn" (1: narrower N tiles for unsplit launches with fewer than 64 CTAs),
- *          "stream_conv", "persistent_conv", "conv_mt2", "cuda_graphs" (0: validated alternatives that measured slower),
- *          "profile" (1: time every kernel class with CUDA events on the launching stream, 2: same + reset, 0: off) */
+ *          "pdl" (1: programmatic dependent launch), "tc_stride2" (1: 4x4 stride-2 convs on tcgen05),
+ *          "small_bn" (1: narrower N tiles for small unsplit launches), "siren_tc" (1: students on tcgen05; 0: mma.sync kernels),
+ *          "attn_split16", "profile" (1: time every kernel class with CUDA events on the launching stream, 2: same + reset, 0: off).
+ * "strict", "microbatch", "cuda_graphs" and "half_operands" belong to the context.  The other developer switches select
+ * kernels PROCESS-WIDE (they are statics of the kernel translation units): changing one on any context changes it for all
+ * contexts of the process, and every change drops the captured graphs / cached outputs of the context it was made on.
+ * A context is used by one thread at a time; the tensor-map caches shared between contexts are mutex-protected. */
 int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value);
-/* counters: "kernel_launches" (kernels this library has launched so far), "workspace_bytes",
+/* counters: "kernel_launches" (kernels this library has launched so far, replayed graph nodes included), "workspace_bytes",
+ *           "graph_replays" / "graph_captures" / "graph_failures",
  *           "prof_{us|launches|flops|bytes}_{conv|norm|tail|attn|glue|siren}" (profile mode; synchronises) */
 int64_t tha4_get_counter(const tha4_ctx* ctx, const char* name);
 

@@ -37,12 +37,12 @@ def main(path):
             vals.append('%s=%s%s' % (label, v.replace('.000000', ''), (' ' + unit.get(k, '')) if label in ('us', 'dram_rd', 'dram_wr') else ''))
         print('   ' + '  '.join(vals))
         try:
-            t_us = float(d['gpu__time_duration.sum']) * (1e-3 if unit['gpu__time_duration.sum'] == 'ns' else 1.0)
+            t_us = float(d['gpu__time_duration.sum']) * {'ns': 1e-3, 'us': 1.0, 'usecond': 1.0, 'ms': 1e3, 'msecond': 1e3, 's': 1e6}.get(unit['gpu__time_duration.sum'], 1.0)
             def to_bytes(k):
                 v, u = float(d[k]), unit[k]
                 return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
             tot = to_bytes('dram__bytes_read.sum') + to_bytes('dram__bytes_write.sum')
-            print('   dram traffic %.2f MB  =>  %.0f GB/s over the launch' % (tot / 1e6, tot / t_us / 1e3))
+            print('   dram traffic %.2f MB  =>  %.0f GB/s over the launch (%.1f us)' % (tot / 1e6, tot / t_us / 1e3, t_us))
         except Exception:
             pass
         tensor = [(k, d[k]) for k in h if ('tensor' in k or 'tmem' in k) and 'pct' in k and d.get(k) not in (None, '', 'n/a')]

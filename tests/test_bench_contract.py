@@ -26,6 +26,24 @@ def test_reference_arm_prints_one_json_line():
     assert d['e2e'] == {'value': d['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
 
 
+def test_round2_default_bench_line_has_the_sub_objects():
+    """The round-2 default line (BASELINE configs[1]) carries the other configs as sub-objects and the >= 30x denominator."""
+    f = os.path.join(ROOT, 'profiles', 'r02_final_bench_default.json')
+    d = json.load(open(f))
+    assert BASE_KEYS <= set(d) and d['n_gpus'] == 1 and d['gpu_launches'] > 0
+    assert d['e2e']['value'] > 0 and d['e2e']['d2h_bytes_per_step'] == 512 * 512 * 4       # the uint8 frame
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] > 0
+    for key in ('pose_sweep_512', 'distill', 'student_b64', 'torch_cuda_eager'):
+        assert key in d, key
+    assert d['pose_sweep_512']['scaling'] == 'strong' and d['pose_sweep_512']['frames_total'] == 512
+    assert d['distill']['steps_per_s'] > 0 and d['torch_cuda_eager_fps'] > 0
+    assert d['cuda_graphs']['replays'] > 0 and d['cuda_graphs']['failures'] == 0
+    for r in (d['roofline'], d['roofline_tail']):
+        assert r['bound'] in ('hbm', 'tensor') and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    ref = json.load(open(os.path.join(ROOT, 'profiles', 'r02_final_bench_reference_arm.json')))
+    assert ref['impl'] == 'reference' and ref['config'] == d['config'], 'the two arms must print the same config'
+
+
 def test_committed_bench_lines_are_complete():
     files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r01_final_bench_*.json')))
     assert files, 'round-1 bench lines missing from profiles/'

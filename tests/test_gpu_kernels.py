@@ -175,7 +175,8 @@ CONV_NORM_CASES = [
     (2, 1, 256, 256, 32, 128, 0, 1, False, False, 0, 0),      # transposed 4x4 stride-2 (4 phases)
     (4, 1, 128, 128, 32, 128, 32, 2, True, True, 2, 0),       # up-sampling ResBlock conv0 (phase-decomposed), upsampled residual
     (3, 2, 256, 256, 16, 768, 32, 0, False, True, 0, 0),      # attention: GroupNorm (no activation) -> 1x1 qkv
-    (0, 1, 64, 64, 256, 64, 32, 2, True, True, 1, 0),
+    (0, 1, 64, 64, 256, 64, 32, 2, True, True, 1, 0),          # single-chunk unsplit variant; residual tile by TMA, one staging slot reused
+    (0, 1, 128, 128, 120, 128, 32, 2, True, True, 1, 0),       # 4 column steps over 3 staging slots, residual by TMA, partial tiles in x
 ]
 
 

@@ -43,6 +43,9 @@ struct tha4_ctx {
     std::map<std::vector<uintptr_t>, TeacherGraph> graphs;
     std::map<std::vector<uintptr_t>, int> graph_seen;      // how often a key was seen before it was captured
     long graph_clock = 0, graph_misses = 0, graph_pause = 0, graph_replays = 0, graph_captures = 0, graph_failures = 0;
+    int side_streams = 1;        // option "side_stream": independent DAG branches (ResBlock skip convs) on a second stream
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t capture_stream = nullptr;   // the legacy default stream cannot be captured: its graphs are recorded here and launched there
     float* pose_stage = nullptr;   // [1024][45]: graphs read the pose from here, so the caller's pose address is not part of the key
     void drop_graphs() {
@@ -93,6 +96,14 @@ Runtime make_rt(tha4_ctx* ctx, void* stream) {
     rt.persist = &ctx->persist; rt.scratch = &ctx->scratch; rt.stream = (cudaStream_t)stream; rt.strict = ctx->strict;
     rt.f16 = ctx->half_operands && !ctx->strict && conv_tc_enabled();
     rt.stats_base = ctx->stats_base; rt.stats_cap = ctx->stats_cap; rt.stats_off = &ctx->stats_off;
+    if (ctx->side_streams && !prof_enabled()) {
+        if (!ctx->side) {
+            THA4_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+            THA4_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            THA4_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+        }
+        rt.side = ctx->side; rt.ev_fork = ctx->ev_fork; rt.ev_join = ctx->ev_join;
+    }
     return rt;
 }
 
@@ -225,6 +236,7 @@ int tha4_ctx_destroy(tha4_ctx* ctx) {
     if (ctx->loss_acc) cudaFree(ctx->loss_acc);
     if (ctx->pose_stage) cudaFree(ctx->pose_stage);
     if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
+    if (ctx->side) { cudaStreamDestroy(ctx->side); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
     if (ctx->stats_base) cudaFree(ctx->stats_base);
     ctx->drop_graphs();
     delete ctx;
@@ -239,6 +251,7 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         ctx->drop_graphs();                   // every option can change the launch sequence
         if (!strcmp(name, "strict")) { ctx->strict = value ? 1 : 0; }
         else if (!strcmp(name, "cuda_graphs")) ctx->use_graphs = value ? 1 : 0;
+        else if (!strcmp(name, "side_stream")) ctx->side_streams = value ? 1 : 0;
         else if (!strcmp(name, "tcgen05")) conv_enable_tc(value != 0);
         else if (!strcmp(name, "cluster_splitk")) conv_tc_enable_cluster(value != 0);
         else if (!strcmp(name, "halo_conv")) conv_halo_enable(value != 0);

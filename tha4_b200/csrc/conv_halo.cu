@@ -51,7 +51,7 @@ __host__ __device__ constexpr int halo_min_ctas(int bn, int sa, int cs, int op) 
 template <int BN, int SA, int SB, int CS, int OP, int XF>
 __global__ void __launch_bounds__(TC_THREADS, halo_min_ctas(BN, SA, CS, OP)) conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16,
-                                                                const TcParams p) {
+                                                                const __grid_constant__ CUtensorMap tmR, const TcParams p) {
     static_assert(OP != OP_TF32, "halo kernel: f16 operands");
     constexpr int ROWB = op_row_bytes(OP);
     constexpr int KCE = op_kch(OP);
@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(TC_THREADS, halo_min_ctas(BN, SA, CS, OP)) con
     uint64_t* a_full = bars, *a_empty = bars + SA, *a_xf = bars + 2 * SA;
     uint64_t* b_full = bars + 3 * SA, *b_empty = b_full + SB;
     uint64_t* t_full = b_empty + SB;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
+    uint64_t* res_bars = t_full + 1;                                     // [4]: residual tiles of the unsplit epilogue (epi_direct)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bars + 4);
     float* xf_A = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tmem_slot + 4) + ((16u - (tc::smem_u32(tmem_slot + 4) & 15u)) & 15u));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(TC_THREADS, halo_min_ctas(BN, SA, CS, OP)) con
         for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(a_full + s), 1); mbar_init(smem_u32(a_empty + s), 1); mbar_init(smem_u32(a_xf + s), 128); }
         for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(b_full + s), 1); mbar_init(smem_u32(b_empty + s), 1); }
         mbar_init(smem_u32(t_full), 1);
+        for (int s = 0; s < 4; ++s) mbar_init(smem_u32(res_bars + s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmB) : "memory");
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(TC_THREADS, halo_min_ctas(BN, SA, CS, OP)) con
             }
             if (threadIdx.x == 64) { mbar_wait(smem_u32(t_full), 0); HSTAMP(2, 3); }
             if (CS > 1) { mbar_wait(smem_u32(t_full), 0); asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }   // own accumulator complete
-            else epi_direct<BN, HT_W, NSLOT>(p, tmem_base, smem, smem_u32(t_full), n, y0, x0, n0, 0, 0, warp, lane, &tmO32, &tmO16);
+            else epi_direct<BN, HT_W, NSLOT>(p, tmem_base, smem, smem_u32(t_full), n, y0, x0, n0, 0, 0, warp, lane, &tmO32, &tmO16, &tmR, res_bars);
             if (threadIdx.x == 64) HSTAMP(2, 4);
         }
     }
@@ -325,17 +327,17 @@ HaloPlan halo_plan(const ConvWeights& cw, const ConvArgs& a, int op) {
 }
 
 template <int OP, int BN, int SA, int SB, int CS, int XF>
-void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const TcParams& p, dim3 grid, cudaStream_t s) {
+void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const CUtensorMap& mr, const TcParams& p, dim3 grid, cudaStream_t s) {
     constexpr int ROWB = op_row_bytes(OP);
     constexpr size_t ring = (size_t)SA * halo_a_bytes(ROWB) + (size_t)SB * BN * ROWB;
-    constexpr size_t smem0 = 1024 + ring + (3 * SA + 2 * SB + 1) * 8 + 16;
+    constexpr size_t smem0 = 1024 + ring + (3 * SA + 2 * SB + 1 + 4) * 8 + 16;
     static_assert(smem0 <= 227 * 1024, "shared memory budget");
     static_assert(ring >= (size_t)4 * 32 * 33 * 4 + 4 * BN * 8, "epilogue scratch must fit in the pipeline buffers");
     static_assert(CS == 1 || ring >= (size_t)128 * BN * 4 + 128 * 8 * 4 + 128 * 4 * 4, "partial tile + statistics scratch must fit");
     const size_t smem = smem0 + (XF ? (size_t)24 * p.xf_C + 32 : 0);
     THA4_REQUIRE(smem <= 227 * 1024, "conv_halo: shared memory budget (fused input normalisation)");
     THA4_ENSURE_SMEM((conv_halo_kernel<BN, SA, SB, CS, OP, XF>), smem);
-    launch_pdl(conv_halo_kernel<BN, SA, SB, CS, OP, XF>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, mo32, mo16, p);
+    launch_pdl(conv_halo_kernel<BN, SA, SB, CS, OP, XF>, grid, dim3(TC_THREADS), smem, s, CS, ma, mb, mo32, mo16, mr, p);
     THA4_LAUNCH_CHECK();
 }
 
@@ -343,26 +345,26 @@ void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap
 // that are fetched ahead of the dependency wait); SBS: depth of the unsplit launches (many tiles: a shallow ring keeps
 // the CTA small so that 2 - 4 of them share an SM and overlap each other's load -> transform -> MMA -> drain chains).
 template <int OP, int BN, int SA, int SBD, int SBS, int XF>
-void launch_halo_cs(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const TcParams& p, dim3 grid, cudaStream_t s) {
+void launch_halo_cs(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const CUtensorMap& mr, const TcParams& p, dim3 grid, cudaStream_t s) {
     if constexpr (BN <= 64) {
         if (cs == 1 && p.cpt == 1) {     // one chunk: one halo, ever -> a ring that fits four times per SM
-            launch_halo<OP, BN, (OP == OP_F16N ? 2 : 1), SBS, 1, XF>(ma, mb, mo32, mo16, p, grid, s);
+            launch_halo<OP, BN, (OP == OP_F16N ? 2 : 1), SBS, 1, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
             return;
         }
     }
-    if (cs == 8) launch_halo<OP, BN, SA, SBD, 8, XF>(ma, mb, mo32, mo16, p, grid, s);
-    else if (cs == 4) launch_halo<OP, BN, SA, SBD, 4, XF>(ma, mb, mo32, mo16, p, grid, s);
-    else if (cs == 2) launch_halo<OP, BN, SA, SBD, 2, XF>(ma, mb, mo32, mo16, p, grid, s);
-    else launch_halo<OP, BN, SA, SBS, 1, XF>(ma, mb, mo32, mo16, p, grid, s);
+    if (cs == 8) launch_halo<OP, BN, SA, SBD, 8, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
+    else if (cs == 4) launch_halo<OP, BN, SA, SBD, 4, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
+    else if (cs == 2) launch_halo<OP, BN, SA, SBD, 2, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
+    else launch_halo<OP, BN, SA, SBS, 1, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
 }
 
 template <int OP, int XF>
-void launch_halo_bn(int bn, int cs, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const TcParams& p, dim3 grid, cudaStream_t s) {
+void launch_halo_bn(int bn, int cs, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo32, const CUtensorMap& mo16, const CUtensorMap& mr, const TcParams& p, dim3 grid, cudaStream_t s) {
     constexpr int M = OP == OP_F16N ? 2 : 1;        // 64-byte rows: twice the stages for the same bytes in flight
-    if (bn == 256) launch_halo_cs<OP, 256, 2 * M, 4 * M, 2 * M, XF>(cs, ma, mb, mo32, mo16, p, grid, s);        // unsplit: 111 KB -> 2 CTAs / SM
-    else if (bn == 128) launch_halo_cs<OP, 128, 2 * M, 6 * M, 3 * M, XF>(cs, ma, mb, mo32, mo16, p, grid, s);   // unsplit:  95 KB -> 2 CTAs / SM
-    else if (bn == 64) launch_halo_cs<OP, 64, 2 * M, 8 * M, 3 * M, XF>(cs, ma, mb, mo32, mo16, p, grid, s);     // unsplit:  71 KB -> 3 CTAs / SM
-    else launch_halo_cs<OP, 32, 2 * M, 9 * M, 5 * M, XF>(cs, ma, mb, mo32, mo16, p, grid, s);                    // unsplit:  67 KB -> 3 CTAs / SM
+    if (bn == 256) launch_halo_cs<OP, 256, 2 * M, 4 * M, 2 * M, XF>(cs, ma, mb, mo32, mo16, mr, p, grid, s);        // unsplit: 111 KB -> 2 CTAs / SM
+    else if (bn == 128) launch_halo_cs<OP, 128, 2 * M, 6 * M, 3 * M, XF>(cs, ma, mb, mo32, mo16, mr, p, grid, s);   // unsplit:  95 KB -> 2 CTAs / SM
+    else if (bn == 64) launch_halo_cs<OP, 64, 2 * M, 8 * M, 3 * M, XF>(cs, ma, mb, mo32, mo16, mr, p, grid, s);     // unsplit:  71 KB -> 3 CTAs / SM
+    else launch_halo_cs<OP, 32, 2 * M, 9 * M, 5 * M, XF>(cs, ma, mb, mo32, mo16, mr, p, grid, s);                    // unsplit:  67 KB -> 3 CTAs / SM
 }
 
 bool g_use_halo = true;
@@ -429,20 +431,24 @@ void conv_halo_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s)
     const CUtensorMap& mb = halo_weight_map(cw, pl.bn, op);
     const CUtensorMap* mo32 = &ma;                   // placeholders when an output does not leave through TMA
     const CUtensorMap* mo16 = &ma;
+    const CUtensorMap* mr = &ma;
     p.st_tma = 0;
     if (pl.cs == 1 && g_tma_store) {
         if (a.out.p && halo_store_map(a.out, false, &mo32)) p.st_tma |= 1;
         if (a.out16.p && halo_store_map(a.out16, true, &mo16)) p.st_tma |= 2;
+        // the residual of a ResBlock's second conv has the geometry of the fp32 output: it arrives through the same box
+        if ((p.st_tma & 1) && a.res.p && p.res_mode == RES_SAME && !a.res.f16 && a.res.N == a.out.N && a.res.H == a.out.H &&
+            a.res.W == a.out.W && a.res.C >= a.out.C && halo_store_map(a.res, false, &mr)) p.st_tma |= 4;
     }
     p.vec4 = ((!cw.bias || (reinterpret_cast<uintptr_t>(cw.bias) & 15) == 0) &&
               (!a.res.p || ((reinterpret_cast<uintptr_t>(a.res.p) & 15) == 0 && a.res.ld % 4 == 0))) ? 1 : 0;
     dim3 grid(pl.tiles_m, pl.tiles_n, pl.cs);
     if (op == OP_F16) {
-        if (a.nin.on) launch_halo_bn<OP_F16, 1>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
-        else launch_halo_bn<OP_F16, 0>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
+        if (a.nin.on) launch_halo_bn<OP_F16, 1>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, *mr, p, grid, s);
+        else launch_halo_bn<OP_F16, 0>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, *mr, p, grid, s);
     } else {
-        if (a.nin.on) launch_halo_bn<OP_F16N, 1>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
-        else launch_halo_bn<OP_F16N, 0>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, p, grid, s);
+        if (a.nin.on) launch_halo_bn<OP_F16N, 1>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, *mr, p, grid, s);
+        else launch_halo_bn<OP_F16N, 0>(pl.bn, pl.cs, ma, mb, *mo32, *mo16, *mr, p, grid, s);
     }
     static const bool dbg_all = dbg_env && !strcmp(getenv("THA4_HALO_DEBUG"), "2");
     if (dbg_all) {       // developer: stamps of every launch of a real forward (serialises the stream)

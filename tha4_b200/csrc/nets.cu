@@ -674,6 +674,23 @@ struct UNetFused {
         const int B = x.f.N;
         const int act = ACT_SILU_FAST;
         Tens h0 = make_act(rt.scratch, rt, B, out.f.H, out.f.W, w.cout, false, true);
+        Tens sk;
+        if (w.has_skip) {
+            // skip(x) depends on x only: it runs on the side stream next to norm0 -> conv0 (15 us of a latency-bound chain,
+            // ~30 times per frame) and is joined in front of conv1, which adds it as the residual
+            sk = make_act(rt.scratch, rt, B, x.f.H, x.f.W, w.cout, true, false, false);
+            if (rt.side) {
+                THA4_CUDA_CHECK(cudaEventRecord(rt.ev_fork, rt.stream));
+                THA4_CUDA_CHECK(cudaStreamWaitEvent(rt.side, rt.ev_fork, 0));
+                cudaStream_t main_stream = rt.stream;
+                rt.stream = rt.side;
+                try { run_conv_tc(rt, w.skip, x.h, nullptr, sk); } catch (...) { rt.stream = main_stream; throw; }
+                rt.stream = main_stream;
+                THA4_CUDA_CHECK(cudaEventRecord(rt.ev_join, rt.side));
+            } else {
+                run_conv_tc(rt, w.skip, x.h, nullptr, sk);
+            }
+        }
         if (mode == 2) {          // norm0 -> SiLU -> 2x2 mean as a pass (f16 result), then a plain conv
             View t0 = make_view16(rt.scratch, B, x.f.H / 2, x.f.W / 2, w.cin);
             run_norm(rt, x.f, w.norm0, 32, nullptr, nullptr, 0, act, 1, nullptr, t0);
@@ -686,8 +703,7 @@ struct UNetFused {
         const ConvNormIn n1 = norm_in(h0.f, w.norm1, 32, act, w.film0, film1 + w.film1_off, film1_total);
         if (w.has_skip) {
             THA4_REQUIRE(mode == 0, "res_block: skip conv only on same-resolution blocks");
-            Tens sk = make_act(rt.scratch, rt, B, x.f.H, x.f.W, w.cout, true, false, false);
-            run_conv_tc(rt, w.skip, x.h, nullptr, sk);
+            if (rt.side) THA4_CUDA_CHECK(cudaStreamWaitEvent(rt.stream, rt.ev_join, 0));
             run_conv_tc(rt, w.conv1, h0.h, &n1, out, &sk.f, RES_SAME);
         } else {
             run_conv_tc(rt, w.conv1, h0.h, &n1, out, &x.f, mode == 0 ? RES_SAME : (mode == 1 ? RES_UP2 : RES_DOWN2));
@@ -718,9 +734,18 @@ void UNetNet::forward_fused(Runtime& rt, const ImgView& image, const float* coar
     float* c1 = P->alloc((size_t)B * 256);
     float* c2 = P->alloc((size_t)B * 256);
     float* film1 = P->alloc((size_t)B * film1_total_);
-    linear_forward(pose, pose_ld, B, 6, cond_w0_, cond_b0_, 256, 0, c1, 256, s);
-    linear_forward(c1, 256, B, 256, cond_w2_, cond_b2_, 256, 1, c2, 256, s);
-    linear_forward(c2, 256, B, 256, film1_w_, film1_b_, film1_total_, 1, film1, film1_total_, s);
+    // the pose MLP + FiLM projection (three dependent GEMVs, ~25 us) is first needed by conv1 of the first ResBlock: it runs on
+    // the side stream next to the prologue, the first conv and conv0
+    cudaStream_t ls = s;
+    if (rt.side) {
+        THA4_CUDA_CHECK(cudaEventRecord(rt.ev_fork, s));
+        THA4_CUDA_CHECK(cudaStreamWaitEvent(rt.side, rt.ev_fork, 0));
+        ls = rt.side;
+    }
+    linear_forward(pose, pose_ld, B, 6, cond_w0_, cond_b0_, 256, 0, c1, 256, ls);
+    linear_forward(c1, 256, B, 256, cond_w2_, cond_b2_, 256, 1, c2, 256, ls);
+    linear_forward(c2, 256, B, 256, film1_w_, film1_b_, film1_total_, 1, film1, film1_total_, ls);
+    if (rt.side) THA4_CUDA_CHECK(cudaEventRecord(rt.ev_join, rt.side));
     UNetFused F{rt, film1, film1_total_};
 
     View x0;
@@ -754,6 +779,7 @@ void UNetNet::forward_fused(Runtime& rt, const ImgView& image, const float* coar
 
     // ---- down path (unet.py:534-536) ----
     run_conv_tc(rt, first_, x0, nullptr, hs[0]);
+    if (rt.side) THA4_CUDA_CHECK(cudaStreamWaitEvent(s, rt.ev_join, 0));        // FiLM table ready
     Tens cur = hs[0];
     for (int i = 0; i < L_; ++i) {
         if (i == L_ - 1) {

@@ -39,6 +39,10 @@ struct Runtime {                      // per-call execution context
     cudaStream_t stream;
     int strict;
     int f16 = 0;                      // normalisation layers hand f16 tensors to the tcgen05 convs (non-strict, tcgen05 on)
+    // optional second stream + fork / join events: independent branches of the DAG (the 1x1 skip conv of a ResBlock next to
+    // its norm0 -> conv0 chain) run beside the main chain -- also inside a captured graph, where they become parallel branches
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // zero-initialised arena for per-(n,c) statistics (View::stats); bump-allocated, re-zeroed by the caller per pass
     double* stats_base = nullptr;
     size_t stats_cap = 0;
