@@ -339,16 +339,25 @@ def test_group_norm_film_silu_pool(C, H, pool):
     assert G.err(G.norm(x, 32, gamma, beta, f0, f1, act=2, pool=pool), ref)[0] < 5e-5
 
 
-def test_attention_vs_reference():
+@pytest.mark.parametrize('strict', [0, 1])
+def test_attention_vs_reference(strict):
+    """strict: the fp32 kernel; default mode: the mma.sync kernel with f16 operands (10-bit mantissa on q, k, P and v:
+    a CPU emulation of exactly that rounding gives max 7.2e-3 / mean 2.9e-4 on this input)."""
     g = _gen(11)
     qkv = torch.randn(2, 768, 16, 16, generator=g)
+    qkv[:, :512] *= 2.0                       # logits of a few units: a peaked softmax, not a uniform one
     b, c, L, heads = 2, 256, 256, 8
     q, k, v = qkv.reshape(b, 3 * c, L).chunk(3, dim=1)
     scale = 1.0 / math.sqrt(math.sqrt(c // heads))
     w = torch.einsum('bct,bcs->bts', (q * scale).reshape(b * heads, c // heads, L), (k * scale).reshape(b * heads, c // heads, L))
     w = torch.softmax(w, dim=-1)
     ref = torch.einsum('bts,bcs->bct', w, v.reshape(b * heads, c // heads, L)).reshape(b, c, 16, 16)
-    assert G.err(G.attention(qkv), ref)[0] < 2e-5
+    G.ctx().set_option('strict', strict)
+    try:
+        mx, mean = G.err(G.attention(qkv), ref)
+    finally:
+        G.ctx().set_option('strict', 0)
+    assert (mx < 2e-5) if strict else (mx < 1.5e-2 and mean < 6e-4), (strict, mx, mean)     # CPU emulation of the f16 rounding: 7.2e-3 / 2.9e-4
 
 
 def test_linear_silu():

@@ -260,6 +260,8 @@ int tha4_set_option(tha4_ctx* ctx, const char* name, int64_t value) {
         else if (!strcmp(name, "tc_stride2")) conv_tc_enable_stride2(value != 0);
         else if (!strcmp(name, "small_bn")) conv_tc_enable_small_bn(value != 0);
         else if (!strcmp(name, "attn_split16")) attention_enable_split16(value != 0);
+        else if (!strcmp(name, "tail_persist")) tail_tc_enable_persist(value != 0);
+        else if (!strcmp(name, "attn_mma")) attention_enable_mma(value != 0);
         else if (!strcmp(name, "half_operands")) ctx->half_operands = value ? 1 : 0;
         else if (!strcmp(name, "pdl")) g_use_pdl = value != 0;
         else if (!strcmp(name, "profile")) { prof_enable(value != 0); if (value == 2) prof_reset(); }
@@ -799,7 +801,7 @@ int tha4_test_attention(tha4_ctx* ctx, const float* qkv, int N, int C, int heads
         View q; q.N = N; q.H = 16; q.W = 16; q.C = 3 * C; q.ld = 3 * C; q.p = P->alloc((size_t)N * 256 * 3 * C);
         nchw_to_nhwc(make_img(qkv, N, 3 * C, 16, 16), q, s);
         View o; o.N = N; o.H = 16; o.W = 16; o.C = C; o.ld = C; o.p = P->alloc((size_t)N * 256 * C);
-        attention_forward(q, heads, o, s);
+        attention_forward(q, heads, o, s, !ctx->strict);
         nhwc_to_nchw(o, out, s);
     });
 }

@@ -548,7 +548,7 @@ void UNetNet::attn_block(Runtime& rt, const AttnW& w, const View& x, const View&
     View qkv = make_view(rt.scratch, x.N, x.H, x.W, 3 * x.C);
     run_conv(rt, w.qkv, t, qkv);
     View a = make_view(rt.scratch, x.N, x.H, x.W, x.C);
-    attention_forward(qkv, 8, a, s);
+    attention_forward(qkv, 8, a, s, !rt.strict);
     run_conv(rt, w.proj, a, out, 0, &x, RES_SAME);
 }
 
@@ -717,7 +717,7 @@ struct UNetFused {
         const ConvNormIn n = norm_in(x.f, w.norm, 32, ACT_NONE);
         run_conv_tc(rt, w.qkv, x.h, &n, qkv);
         View a = make_view(rt.scratch, x.f.N, x.f.H, x.f.W, x.f.C);
-        attention_forward(qkv.f, 8, a, rt.stream);
+        attention_forward(qkv.f, 8, a, rt.stream, true);
         run_conv_tc(rt, w.proj, a, nullptr, out, &x.f, RES_SAME);
     }
 };

@@ -36,7 +36,9 @@ void linear_forward(const float* x, int x_ld, int N, int I, const float* W, cons
 // ---------------------------------------------------------------- attention (attention.cu)
 // qkv: NHWC [N,L=H*W,3C] with q|k|v channel blocks ("new order", unet.py:192-202), heads of C/heads channels.
 // out: NHWC [N,L,C].  L must be 256, head dim 32.
-void attention_forward(const View& qkv, int heads, const View& out, cudaStream_t s);
+// fast: the default precision mode may use the tensor-core kernel (f16 operands); strict callers pass false.
+void attention_forward(const View& qkv, int heads, const View& out, cudaStream_t s, bool fast = false);
+void attention_enable_mma(bool on);       // option "attn_mma" (default on)
 void attention_enable_split16(bool on);   // 16 CTAs per (sample, head) instead of 4 (B=1 latency; opt-in)
 
 // ---------------------------------------------------------------- image glue (image_ops.cu)
@@ -91,6 +93,7 @@ void tail_forward(TailKind kind, const TailWeights& tw, const View& feature, con
 // tcgen05 variant (tail_tc.cu): `feature` is the RAW f16 feature map with the statistics its producer accumulated
 void tail_make_half(TailWeights& tw, cudaStream_t s);     // f16 B-operand copy of the head weights (recorded in the active AllocSink)
 bool tail_tc_supported(const TailWeights& tw, const View& feature);
+void tail_tc_enable_persist(bool on);      // option "tail_persist": persistent pipelined tcgen05 tail (default on)
 void tail_tc_forward(TailKind kind, const TailWeights& tw, const View& feature, const NormSpecTail& ns, const ImgView& image0,
                      const ImgView& image1, float* const* outputs, cudaStream_t s);
 

@@ -200,6 +200,227 @@ __global__ void __launch_bounds__(TT_THREADS) tail_tc_kernel(const __grid_consta
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PERSISTENT, software-pipelined version (the default).  The kernel above runs one tile per CTA and its phases -- statistics
+// fold, halo TMA, in-place normalisation, MMAs, gather / blend / store drain -- are a serial chain, co-resident CTAs all start
+// together, so nothing overlaps (ncu at B=1, Upscaler02 site: 46 us, every unit < 16 % busy).  Here ONE CTA per SM walks a
+// contiguous range of tiles with the phases on different warps and different tiles:
+//   warp 0      TMA producer: halo boxes into an NS-deep ring (the head weights once)
+//   warp 1      MMA issuer: TR x 9 x C/16 tcgen05.mma per tile into one of TWO accumulator slots in TMEM
+//   warps 2-5   normalise + activate the landed halo in place (the per-channel affine is rebuilt once per SAMPLE, not per tile)
+//   warps 6..   drain: one thread per output pixel of the tile (4 * TR warps): tcgen05.ld -> tail_epilogue
+// mbarriers: h_full (TMA -> transform), h_xf (transform -> MMA, 128 arrivals), h_empty (MMA commit -> TMA), acc_full (MMA
+// commit -> drain), acc_empty (drain -> MMA, one arrival per drain warp once its tcgen05.ld has completed).
+template <int C, int TR> struct TailPCfg {
+    static constexpr int ROWB = 2 * C;
+    static constexpr int HROWS = (TR + 2) * TT_HW;
+    static constexpr int A_BYTES = ((HROWS * ROWB + 1023) / 1024) * 1024;
+    static constexpr int NS = C == 32 ? 3 : 2;                              // halo ring depth
+    static constexpr int B_BYTES = 9 * TT_N * ROWB;
+    static constexpr int ACC_COLS = TR * TT_N;                              // TMEM columns of one accumulator slot
+    static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS; // 64 / 128: a power of two
+    static constexpr int DRAIN_WARPS = 4 * TR;
+    static constexpr int THREADS = (6 + DRAIN_WARPS) * 32;
+    static constexpr int NBARS = 3 * NS + 5;
+    static constexpr size_t SMEM = 1024 + (size_t)NS * A_BYTES + B_BYTES + 2 * C * sizeof(double) + 2 * C * sizeof(float) + 16 * sizeof(float) +
+                                   NBARS * sizeof(uint64_t) + 16;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+template <int KIND, int C, int TR>
+__global__ void __launch_bounds__(TailPCfg<C, TR>::THREADS, 1) tail_tc_persist_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmW,
+                                                                                      const TailTcParams p) {
+    using Cfg = TailPCfg<C, TR>;
+    constexpr int ROWB = Cfg::ROWB, NCH = ROWB / 16, NS = Cfg::NS;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + NS * Cfg::A_BYTES;
+    double* chs = reinterpret_cast<double*>(smB + Cfg::B_BYTES);         // [C][2] folded statistics
+    float* cA = reinterpret_cast<float*>(chs + 2 * C);                   // [C] affine
+    float* cB = cA + C;
+    float* sbias = cB + C;                                               // [16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 16);
+    uint64_t* h_full = bars, *h_xf = bars + NS, *h_empty = bars + 2 * NS;
+    uint64_t* acc_full = bars + 3 * NS, *acc_empty = acc_full + 2, *w_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (p.S + TT_W - 1) / TT_W, tiles_y = p.S / TR, per_n = tiles_x * tiles_y;
+    const int total = per_n * p.N;
+    const int t_begin = (int)((long)blockIdx.x * total / gridDim.x);
+    const int nt = (int)((long)(blockIdx.x + 1) * total / gridDim.x) - t_begin;       // contiguous tiles of this CTA (>= 1: grid <= total)
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(h_full + s), 1); mbar_init(smem_u32(h_xf + s), 128); mbar_init(smem_u32(h_empty + s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(acc_full + a), 1); mbar_init(smem_u32(acc_empty + a), Cfg::DRAIN_WARPS); }
+        mbar_init(smem_u32(w_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmF) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" :: "l"(&tmW) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid >= 64 && tid < 80) sbias[tid - 64] = (tid - 64) < TAIL_CO_PAD ? __ldg(p.bias + (tid - 64)) : 0.0f;     // weights: independent of the previous kernel
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    if (tid == 0) {        // the head weights do not depend on the previous kernel: fetch them ahead of the dependency wait
+        mbar_expect_tx(smem_u32(w_full), Cfg::B_BYTES);
+        tma_load_3d(smem_u32(smB), &tmW, 0, 0, 0, smem_u32(w_full));
+    }
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== TMA producer =====
+            for (int i = 0; i < nt; ++i) {
+                const int s = i % NS;
+                int t = t_begin + i;
+                const int n = t / per_n; t -= n * per_n;
+                const int ty = t / tiles_x, tx = t - ty * tiles_x;
+                mbar_wait(smem_u32(h_empty + s), ((i / NS) & 1) ^ 1);
+                mbar_expect_tx(smem_u32(h_full + s), Cfg::HROWS * ROWB);
+                tma_load_4d(smem_u32(smA + s * Cfg::A_BYTES), &tmF, 0, tx * TT_W - 1, ty * TR - 1, n, smem_u32(h_full + s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ===== MMA issuer: TR tile rows x 9 taps = row-shifted views of the halo =====
+            constexpr uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TT_N >> 3) << 17) | ((128u >> 4) << 24);
+            mbar_wait(smem_u32(w_full), 0);
+            for (int i = 0; i < nt; ++i) {
+                const int s = i % NS, a = i & 1;
+                mbar_wait(smem_u32(acc_empty + a), ((i >> 1) & 1) ^ 1);
+                mbar_wait(smem_u32(h_xf + s), (i / NS) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint8_t* hA = smA + s * Cfg::A_BYTES;
+#pragma unroll 1
+                for (int r = 0; r < TR; ++r)
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap - 3 * dy;
+                        const uint64_t adesc = make_smem_desc_sw<ROWB>(smem_u32(hA + ((r + dy) * TT_HW + dx) * ROWB));
+                        const uint64_t bdesc = make_smem_desc_sw<ROWB>(smem_u32(smB + tap * TT_N * ROWB));
+#pragma unroll
+                        for (int k = 0; k < C / 16; ++k)
+                            umma_f16(tmem_base + (uint32_t)(a * Cfg::ACC_COLS + r * TT_N), adesc + 2 * k, bdesc + 2 * k, idesc, (tap > 0 || k > 0) ? 1u : 0u);
+                    }
+                umma_commit(smem_u32(h_empty + s));          // the halo slot is free once these MMAs have read it
+                umma_commit(smem_u32(acc_full + a));
+            }
+        }
+    } else if (warp < 6) {   // ===== warps 2-5: per-sample affine, then normalise + activate every landed halo in place =====
+        const int te = tid - 64;
+        const int cpg = p.groups == 0 ? 1 : C / p.groups;
+        const bool silu = p.act == ACT_SILU || p.act == ACT_SILU_FAST;
+        int cur_n = -1;
+        for (int i = 0; i < nt; ++i) {
+            const int s = i % NS;
+            int t = t_begin + i;
+            const int n = t / per_n; t -= n * per_n;
+            const int ty = t / tiles_x, tx = t - ty * tiles_x;
+            const int x0 = tx * TT_W, y0 = ty * TR;
+            if (n != cur_n) {
+                cur_n = n;
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");          // everyone is done with the previous sample's table
+                for (int c = te; c < C; c += 128) {
+                    const double2 v = fold_stat_replicas(p.stats + ((long)n * p.stats_ld + c) * 2, p.stats_rep_stride, p.stats_rep);
+                    chs[2 * c] = v.x; chs[2 * c + 1] = v.y;
+                }
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                for (int c = te; c < C; c += 128) {
+                    const int g0 = (c / cpg) * cpg;
+                    double su = 0.0, sq = 0.0;
+                    for (int j = 0; j < cpg; ++j) { su += chs[2 * (g0 + j)]; sq += chs[2 * (g0 + j) + 1]; }
+                    const double cnt = (double)p.S * p.S * cpg;
+                    const double mean = su / cnt;
+                    double var = sq / cnt - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    float A = (float)(1.0 / sqrt(var + 1e-5)) * __ldg(p.gamma + c);
+                    float B = __ldg(p.beta + c) - (float)mean * A;
+                    if (silu) { A *= 0.5f; B *= 0.5f; }                            // silu(v) = h + h * tanh(h), h = v / 2
+                    cA[c] = A; cB[c] = B;
+                }
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            }
+            mbar_wait(smem_u32(h_full + s), (i / NS) & 1);
+            uint8_t* hbase = smA + s * Cfg::A_BYTES;
+            for (int row = te; row < Cfg::HROWS; row += 128) {
+                const int hy = row / TT_HW, hx = row - hy * TT_HW;
+                const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                if (gy < 0 || gy >= p.S || gx < 0 || gx >= p.S) continue;          // zero padding stays zero
+                uint8_t* rowp = hbase + row * ROWB;
+                const int swz = ROWB == 128 ? (row & 7) : ((row >> 1) & 3);
+#pragma unroll
+                for (int j = 0; j < NCH; ++j) {
+                    uint4* dp = reinterpret_cast<uint4*>(rowp + ((j ^ swz) << 4));
+                    uint4 d = *dp;
+                    const float4 a0 = *reinterpret_cast<const float4*>(cA + 8 * j), a1 = *reinterpret_cast<const float4*>(cA + 8 * j + 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(cB + 8 * j), b1 = *reinterpret_cast<const float4*>(cB + 8 * j + 4);
+                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    __half2* hp = reinterpret_cast<__half2*>(&d);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float2 v = __half22float2(hp[e]);
+                        v.x = fmaf(v.x, av[2 * e], bv[2 * e]); v.y = fmaf(v.y, av[2 * e + 1], bv[2 * e + 1]);
+                        if (silu) {
+                            float tx2, ty2;
+                            asm("tanh.approx.f32 %0, %1;\n" : "=f"(tx2) : "f"(v.x));
+                            asm("tanh.approx.f32 %0, %1;\n" : "=f"(ty2) : "f"(v.y));
+                            v.x = fmaf(v.x, tx2, v.x); v.y = fmaf(v.y, ty2, v.y);
+                        } else if (p.act == ACT_RELU) {
+                            v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f);
+                        }
+                        hp[e] = __floats2half2_rn(v.x, v.y);
+                    }
+                    *dp = d;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes -> the tensor core's async-proxy reads
+            mbar_arrive(smem_u32(h_xf + s));
+        }
+    } else {                 // ===== drain warps: thread = one output pixel of the tile =====
+        const int dw = warp - 6;
+        const int q = warp & 3;                                                  // TMEM lane quadrant this warp may access
+        const int r = dw >> 2;                                                   // tile row (each quadrant appears once per row)
+        for (int i = 0; i < nt; ++i) {
+            const int a = i & 1;
+            int t = t_begin + i;
+            const int n = t / per_n; t -= n * per_n;
+            const int ty = t / tiles_x, tx = t - ty * tiles_x;
+            mbar_wait(smem_u32(acc_full + a), (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            uint32_t acc[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + r * TT_N), acc);
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            if (lane == 0) mbar_arrive(smem_u32(acc_empty + a));                 // the accumulator slot may be overwritten
+            const int x = tx * TT_W + q * 32 + lane, y = ty * TR + r;
+            if (x < p.S) {
+                float o[TAIL_CO_PAD];
+#pragma unroll
+                for (int j = 0; j < TAIL_CO_PAD; ++j) o[j] = fmaf(__uint_as_float(acc[j]), p.acc_scale, sbias[j]);
+                tail_epilogue<KIND>(o, n, y, x, p.S, p.img0, p.img1, p.base, p.o[0], p.o[1], p.o[2], p.o[3], p.o[4], p.o[5], p.o[6], p.o[7]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -292,9 +513,51 @@ void launch_tail_tc(const TailWeights& tw, const View& f, const NormSpecTail& ns
     THA4_LAUNCH_CHECK();
 }
 
+bool g_tail_persist = true;       // option "tail_persist": the persistent pipelined kernel (default) / one tile per CTA
+
+int tail_num_sms() {
+    static int sms[THA4_MAX_DEVICES] = {};
+    const int d = current_device();
+    if (!sms[d]) THA4_CUDA_CHECK(cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d));
+    return sms[d];
+}
+
+template <int KIND, int C, int TR>
+void launch_tail_persist(const TailWeights& tw, const View& f, const NormSpecTail& ns, const ImgView& i0, const ImgView& i1, float* const* o, int nout,
+                         cudaStream_t s) {
+    using Cfg = TailPCfg<C, TR>;
+    TailTcParams p{};
+    p.S = f.H; p.N = f.N;
+    p.stats = f.stats; p.stats_ld = f.stats_ld; p.stats_rep = std::max(1, f.stats_rep); p.stats_rep_stride = f.stats_rep_stride;
+    p.groups = ns.groups; p.act = ns.act; p.gamma = ns.gamma; p.beta = ns.beta;
+    p.bias = tw.bias; p.acc_scale = 1.0f / tw.w16_scale;
+    p.img0 = i0; p.img1 = i1; p.base = base_grid_table(f.H);
+    for (int i = 0; i < 8; ++i) p.o[i] = i < nout ? o[i] : nullptr;
+    THA4_ENSURE_SMEM((tail_tc_persist_kernel<KIND, C, TR>), Cfg::SMEM);
+    const long total = (long)ceil_div(f.W, TT_W) * (f.H / TR) * f.N;
+    dim3 grid((unsigned)std::min<long>(total, tail_num_sms()));
+    ProfScope prof(PROF_TAIL, s);
+    {   // compulsory traffic as SURVEY 8d defines it (fp32 element size): feature map + image(s) read once, every returned tensor written once
+        const int out_ch[4] = {15, 18, 24, 24};
+        const int img_ch = (KIND == TAIL_COMBINER) ? 8 : 4;
+        prof_add_work(PROF_TAIL, 2.0 * f.pixels() * 9 * tw.C * tw.CO, (double)f.pixels() * (f.C + img_ch + out_ch[KIND]) * 4);
+    }
+    launch_pdl(tail_tc_persist_kernel<KIND, C, TR>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, 1, feature_map(f, TR), head_weight_map(tw), p);
+    THA4_LAUNCH_CHECK();
+}
+
 template <int KIND>
 void launch_tail_tc_c(const TailWeights& tw, const View& f, const NormSpecTail& ns, const ImgView& i0, const ImgView& i1, float* const* o, int nout,
                       cudaStream_t s) {
+    if (g_tail_persist) {
+        // tile rows per step: 4 when that still gives every SM two tiles or more, else 2 (more, smaller tiles: the small sites at
+        // B = 1 are one latency chain per CTA)
+        const long tiles4 = (long)ceil_div(f.W, TT_W) * (f.H / 4) * f.N;
+        const bool tr4 = tiles4 >= 2L * tail_num_sms();
+        if (tw.C == 32) { if (tr4) launch_tail_persist<KIND, 32, 4>(tw, f, ns, i0, i1, o, nout, s); else launch_tail_persist<KIND, 32, 2>(tw, f, ns, i0, i1, o, nout, s); }
+        else            { if (tr4) launch_tail_persist<KIND, 64, 4>(tw, f, ns, i0, i1, o, nout, s); else launch_tail_persist<KIND, 64, 2>(tw, f, ns, i0, i1, o, nout, s); }
+        return;
+    }
     if (tw.C == 32) launch_tail_tc<KIND, 32>(tw, f, ns, i0, i1, o, nout, s);
     else launch_tail_tc<KIND, 64>(tw, f, ns, i0, i1, o, nout, s);
 }
@@ -323,6 +586,8 @@ void tail_make_half(TailWeights& tw, cudaStream_t s) {
     THA4_LAUNCH_CHECK();
     tw.w16 = h; tw.w16_scale = scale;
 }
+
+void tail_tc_enable_persist(bool on) { g_tail_persist = on; }
 
 bool tail_tc_supported(const TailWeights& tw, const View& feature) {
     return feature.f16 && feature.stats != nullptr && (tw.C == 32 || tw.C == 64) && feature.C == tw.C && feature.ld == tw.C &&
