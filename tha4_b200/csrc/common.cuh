@@ -174,4 +174,17 @@ __device__ __forceinline__ double2 fold_stat_replicas(const double* __restrict__
     return make_double2(su, sq);
 }
 
+// Same sum in the same order (replica 0 first), all loads of up to 16 replicas in flight at once: one L2 round trip.
+__device__ __forceinline__ double2 fold_stat_replicas16(const double* __restrict__ p, long rep_stride, int rep) {
+    if (rep > 16) return fold_stat_replicas(p, rep_stride, rep);
+    double2 v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        v[j] = (j < rep) ? __ldg(reinterpret_cast<const double2*>(p + (long)j * rep_stride)) : make_double2(0.0, 0.0);
+    double su = 0.0, sq = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { su += v[j].x; sq += v[j].y; }
+    return make_double2(su, sq);
+}
+
 }  // namespace tha4

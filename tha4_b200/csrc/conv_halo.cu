@@ -180,12 +180,16 @@ __global__ void __launch_bounds__(TC_THREADS, halo_min_ctas(BN, SA, CS, OP)) con
                     mbar_wait(smem_u32(a_full + sa), (ci / SA) & 1);
                     if (te == 0 && ci == 0) HSTAMP(2, 1);
                     const int c0 = (cb0 + ci) * KCE;
-                    for (int row = te; row < HALO_ROWS; row += 128) {
+                    // items = (halo row, half row): 360 items over 128 threads (3 at most) instead of 180 whole rows (2 at most:
+                    // 52 threads did twice the work of the others and set the length of the stage)
+                    constexpr int HC = ROWB / 32;                                             // chunks per half row
+                    for (int it = te; it < 2 * HALO_ROWS; it += 128) {
+                        const int row = it >> 1, half = it & 1;
                         const int hy = row / HALO_W, hx = row - hy * HALO_W;
                         const int iy = y0 - 1 + hy, ix = x0 - 1 + hx;
                         if (iy < 0 || iy >= p.inH || ix < 0 || ix >= p.inW) continue;      // zero padding stays zero
                         const int swz = ROWB == 128 ? (row & 7) : ((row >> 1) & 3);
-                        xf_row<ROWB>(smA + sa * A_BYTES + row * ROWB, swz, c0, p, hA, hB, silu);
+                        xf_chunks<HC>(smA + sa * A_BYTES + row * ROWB, swz, half * HC, c0, p, hA, hB, silu);
                     }
                     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                     mbar_arrive(smem_u32(a_xf + sa));

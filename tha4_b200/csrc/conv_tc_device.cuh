@@ -67,8 +67,17 @@ __device__ __forceinline__ void xf_build_coef(const TcParams& p, int n, int te, 
     const int cpg = p.xf_groups == 0 ? 1 : p.xf_C / p.xf_groups;
     c_lo = (c_lo / cpg) * cpg;
     c_hi = min(p.xf_C, ((c_hi + cpg - 1) / cpg) * cpg);
+    // The layer constants of this thread's first channel are requested BEFORE the statistics: with the loads behind the
+    // barrier below, the table cost three dependent L2 round trips (replicas 0-7, replicas 8-15, constants) = 3 900 cycles of
+    // every XF CTA's start-up (profiles/r02_halo_phase_stamps.txt, pdl -> coef); now one.
+    const int c1 = c_lo + te;
+    const bool h1 = c1 < c_hi;
+    const float* f1p = p.xf_film1 ? p.xf_film1 + (long)n * p.xf_film1_ld : nullptr;
+    const float g1 = h1 ? __ldg(p.xf_gamma + c1) : 0.0f, b1 = h1 ? __ldg(p.xf_beta + c1) : 0.0f;
+    const float f0s = (h1 && p.xf_film0) ? __ldg(p.xf_film0 + c1) : 0.0f, f0h = (h1 && p.xf_film0) ? __ldg(p.xf_film0 + p.xf_C + c1) : 0.0f;
+    const float f1s = (h1 && f1p) ? __ldg(f1p + c1) : 0.0f, f1h = (h1 && f1p) ? __ldg(f1p + p.xf_C + c1) : 0.0f;
     for (int c = c_lo + te; c < c_hi; c += 128)
-        chs[c] = fold_stat_replicas(p.in_stats + ((long)n * p.in_stats_ld + c) * 2, p.in_stats_rep_stride, p.in_stats_rep);
+        chs[c] = fold_stat_replicas16(p.in_stats + ((long)n * p.in_stats_ld + c) * 2, p.in_stats_rep_stride, p.in_stats_rep);
     asm volatile("bar.sync 1, 128;\n" ::: "memory");
     const bool silu = p.xf_act == ACT_SILU || p.xf_act == ACT_SILU_FAST;
     for (int c = c_lo + te; c < c_hi; c += 128) {
@@ -79,30 +88,35 @@ __device__ __forceinline__ void xf_build_coef(const TcParams& p, int n, int te, 
         const double mean = su / cnt;
         double var = sq / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
-        float A = (float)(1.0 / sqrt(var + 1e-5)) * __ldg(p.xf_gamma + c);
-        float B = __ldg(p.xf_beta + c) - (float)mean * A;
-        if (p.xf_film0) { const float sc = 1.0f + __ldg(p.xf_film0 + c), sh = __ldg(p.xf_film0 + p.xf_C + c); A *= sc; B = B * sc + sh; }
-        if (p.xf_film1) { const float* f = p.xf_film1 + (long)n * p.xf_film1_ld; const float sc = 1.0f + __ldg(f + c), sh = __ldg(f + p.xf_C + c); A *= sc; B = B * sc + sh; }
+        const bool pre = c == c1;
+        float A = (float)(1.0 / sqrt(var + 1e-5)) * (pre ? g1 : __ldg(p.xf_gamma + c));
+        float B = (pre ? b1 : __ldg(p.xf_beta + c)) - (float)mean * A;
+        if (p.xf_film0) { const float sc = 1.0f + (pre ? f0s : __ldg(p.xf_film0 + c)), sh = pre ? f0h : __ldg(p.xf_film0 + p.xf_C + c); A *= sc; B = B * sc + sh; }
+        if (f1p) { const float sc = 1.0f + (pre ? f1s : __ldg(f1p + c)), sh = pre ? f1h : __ldg(f1p + p.xf_C + c); A *= sc; B = B * sc + sh; }
         if (silu) { A *= 0.5f; B *= 0.5f; }                      // silu(v) = h + h * tanh(h) with h = v / 2
         hA[c] = __float2half_rn(fminf(fmaxf(A, -65504.0f), 65504.0f)); hB[c] = __float2half_rn(fminf(fmaxf(B, -65504.0f), 65504.0f));
     }
     asm volatile("bar.sync 1, 128;\n" ::: "memory");
 }
 
-// One operand row (ROWB bytes = ROWB / 2 channels starting at channel c0) normalised + activated in place.  swz: the
-// row's XOR term of the TMA / UMMA swizzle; every thread walks the LOGICAL chunks in the same order, so the coefficient
-// reads are broadcasts and the data accesses of 8 consecutive rows hit 8 different 16-byte bank groups.
-template <int ROWB>
-__device__ __forceinline__ void xf_row(uint8_t* rowp, int swz, int c0, const TcParams& p, const __half* hA, const __half* hB, bool silu) {
-    constexpr int NCH = ROWB / 16;
+// NC consecutive 16-byte chunks (8 channels each, logical chunk index j0 .. j0 + NC) of one operand row normalised +
+// activated in place.  swz: the row's XOR term of the TMA / UMMA swizzle; c0: the channel of logical chunk 0.
+// ALL chunks are loaded before the first is transformed and stored after the last: with one load -> transform -> store per
+// chunk the compiler must keep the shared-memory accesses in program order (it cannot prove that the store of chunk j and the
+// load of chunk j + 1 do not alias), which made the stage one dependent ~200-cycle chain per chunk on a single warp per
+// scheduler (profiles/r02_halo_phase_stamps.txt: a_full -> xf_done 3 300 cycles for 2 rows x 8 chunks).
+template <int NC>
+__device__ __forceinline__ void xf_chunks(uint8_t* rowp, int swz, int j0, int c0, const TcParams& p, const __half* hA, const __half* hB, bool silu) {
+    uint4 d[NC];
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-        const int cb = c0 + j * 8;
-        if (cb >= p.xf_C) break;
-        uint4* dp = reinterpret_cast<uint4*>(rowp + ((j ^ swz) << 4));
-        uint4 d = *dp;
+    for (int j = 0; j < NC; ++j) d[j] = *reinterpret_cast<const uint4*>(rowp + (((j0 + j) ^ swz) << 4));
+    const bool relu = p.xf_act == ACT_RELU;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const int cb = c0 + (j0 + j) * 8;
+        if (cb >= p.xf_C) continue;                      // pass-through channels (pose planes, padding)
         const uint4 a4 = *reinterpret_cast<const uint4*>(hA + cb), b4 = *reinterpret_cast<const uint4*>(hB + cb);
-        __half2* x2 = reinterpret_cast<__half2*>(&d);
+        __half2* x2 = reinterpret_cast<__half2*>(&d[j]);
         const __half2* a2 = reinterpret_cast<const __half2*>(&a4);
         const __half2* b2 = reinterpret_cast<const __half2*>(&b4);
 #pragma unroll
@@ -112,13 +126,20 @@ __device__ __forceinline__ void xf_row(uint8_t* rowp, int swz, int c0, const TcP
                 uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
                 asm("tanh.approx.f16x2 %0, %1;\n" : "=r"(tu) : "r"(hu));
                 h = __hfma2(h, *reinterpret_cast<__half2*>(&tu), h);
-            } else if (p.xf_act == ACT_RELU) {
+            } else if (relu) {
                 h = __hmax2(h, __float2half2_rn(0.0f));
             }
             x2[e] = h;
         }
-        *dp = d;
     }
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+        if (c0 + (j0 + j) * 8 < p.xf_C) *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ swz) << 4)) = d[j];
+}
+// whole row
+template <int ROWB>
+__device__ __forceinline__ void xf_row(uint8_t* rowp, int swz, int c0, const TcParams& p, const __half* hA, const __half* hB, bool silu) {
+    xf_chunks<ROWB / 16>(rowp, swz, 0, c0, p, hA, hB, silu);
 }
 
 // ===== cluster split-K, step 1 (epilogue warps, after a cluster barrier that says every peer's accumulator is complete and
@@ -364,7 +385,7 @@ __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base
             atomicAdd(base + 2 * c + 1, (double)a.y + (double)b.y + (double)cc.y + (double)d.y);
         }
     }
-    if (NSLOT > 0 && st_tma && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // stores complete before the CTA retires
+    if (NSLOT > 0 && st_tma && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the staging slots have been read before the CTA retires (the writes themselves complete with the grid)
 }
 
 // ===== cluster split-K, step 2 (epilogue warps, after the cluster barrier that publishes the pushes): sum the CS slots of this

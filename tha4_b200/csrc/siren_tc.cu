@@ -199,44 +199,43 @@ __global__ void __launch_bounds__(ST_THREADS) siren_tc_kernel(const __grid_const
                     *reinterpret_cast<uint4*>(smA + a_off(r, c8)) = pk;
                 }
             } else {
-                // bilinear x2 of the previous level (align_corners = False)
+                // bilinear x2 of the previous level (align_corners = False).  Thread = tile pixel: ONE horizontal tap pair, four corner
+                // row pointers and four packed-half weights per thread and tile, then per 8-channel group four 16-byte loads,
+                // 1 HMUL2 + 3 HFMA2 per channel pair, one 16-byte store into the swizzled operand.  The first version walked
+                // (pixel, group) items: an integer division, a lerp_locate, four 64-bit addresses and 32 half->float conversions
+                // per item made this prologue 25 % of the level's instructions and -- with its three exposed L2 round trips --
+                // 41 % of the compute warps' time, more than the sine layers (ncu source page, profiles/r02_siren_tc_notes.txt).
+                // The taps 0 / 0.25 / 0.75 / 1 and their products are exact in fp16; the weighted sum is rounded per operation
+                // (<= 2 ulp of the fp16 operand it becomes) instead of once.
                 const int Rh = p.R >> 1, CP = p.prev_c, groups = CP >> 3;
                 const __half* prev = p.prev + (size_t)n * Rh * Rh * CP;
                 const LerpTap ty = lerp_locate(y, 0.5f, Rh);
-                // four (pixel, channel-group) items per round, their 16 corner loads issued before any is consumed: a
-                // one-item loop exposed one L2 round trip per item (12 - 24 per tile)
-                const int items = ST_TILE * groups;
-                for (int i0 = te; i0 < items; i0 += 4 * 128) {
+                const LerpTap tx = lerp_locate(x0 + te, 0.5f, Rh);
+                const uint4* pa = reinterpret_cast<const uint4*>(prev + ((size_t)ty.i0 * Rh + tx.i0) * CP);
+                const uint4* pb = reinterpret_cast<const uint4*>(prev + ((size_t)ty.i0 * Rh + tx.i1) * CP);
+                const uint4* pc = reinterpret_cast<const uint4*>(prev + ((size_t)ty.i1 * Rh + tx.i0) * CP);
+                const uint4* pd = reinterpret_cast<const uint4*>(prev + ((size_t)ty.i1 * Rh + tx.i1) * CP);
+                const __half2 w00 = __float2half2_rn(ty.l0 * tx.l0), w01 = __float2half2_rn(ty.l0 * tx.l1);
+                const __half2 w10 = __float2half2_rn(ty.l1 * tx.l0), w11 = __float2half2_rn(ty.l1 * tx.l1);
+#pragma unroll 1
+                for (int cg0 = 0; cg0 < groups; cg0 += 4) {
                     uint4 va[4], vb[4], vc[4], vd[4];
-                    int rr[4], cgs[4];
-                    float lx0[4], lx1[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + u * 128;
-                        const int ii = i < items ? i : te;
-                        rr[u] = ii / groups; cgs[u] = ii - rr[u] * groups;
-                        const LerpTap tx = lerp_locate(x0 + rr[u], 0.5f, Rh);
-                        lx0[u] = tx.l0; lx1[u] = tx.l1;
-                        va[u] = __ldg(reinterpret_cast<const uint4*>(prev + ((size_t)ty.i0 * Rh + tx.i0) * CP + cgs[u] * 8));
-                        vb[u] = __ldg(reinterpret_cast<const uint4*>(prev + ((size_t)ty.i0 * Rh + tx.i1) * CP + cgs[u] * 8));
-                        vc[u] = __ldg(reinterpret_cast<const uint4*>(prev + ((size_t)ty.i1 * Rh + tx.i0) * CP + cgs[u] * 8));
-                        vd[u] = __ldg(reinterpret_cast<const uint4*>(prev + ((size_t)ty.i1 * Rh + tx.i1) * CP + cgs[u] * 8));
+                        const int cg = min(cg0 + u, groups - 1);
+                        va[u] = __ldg(pa + cg); vb[u] = __ldg(pb + cg); vc[u] = __ldg(pc + cg); vd[u] = __ldg(pd + cg);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        if (i0 + u * 128 >= items) break;
+                        if (cg0 + u >= groups) break;
                         const __half2* ah = reinterpret_cast<const __half2*>(&va[u]); const __half2* bh = reinterpret_cast<const __half2*>(&vb[u]);
                         const __half2* ch = reinterpret_cast<const __half2*>(&vc[u]); const __half2* dh = reinterpret_cast<const __half2*>(&vd[u]);
                         uint4 o;
                         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float2 fa = __half22float2(ah[k]), fb = __half22float2(bh[k]), fc = __half22float2(ch[k]), fd = __half22float2(dh[k]);
-                            const float r0 = ty.l0 * (lx0[u] * fa.x + lx1[u] * fb.x) + ty.l1 * (lx0[u] * fc.x + lx1[u] * fd.x);
-                            const float r1 = ty.l0 * (lx0[u] * fa.y + lx1[u] * fb.y) + ty.l1 * (lx0[u] * fc.y + lx1[u] * fd.y);
-                            oh[k] = __floats2half2_rn(r0, r1);
-                        }
-                        *reinterpret_cast<uint4*>(smA + a_off(rr[u], cgs[u] * 8)) = o;
+                        for (int k = 0; k < 4; ++k)
+                            oh[k] = __hfma2(w11, dh[k], __hfma2(w10, ch[k], __hfma2(w01, bh[k], __hmul2(w00, ah[k]))));
+                        *reinterpret_cast<uint4*>(smA + a_off(te, (cg0 + u) * 8)) = o;
                     }
                 }
             }

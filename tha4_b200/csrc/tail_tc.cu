@@ -208,10 +208,12 @@ __global__ void __launch_bounds__(TT_THREADS) tail_tc_kernel(const __grid_consta
 // contiguous range of tiles with the phases on different warps and different tiles:
 //   warp 0      TMA producer: halo boxes into an NS-deep ring (the head weights once)
 //   warp 1      MMA issuer: TR x 9 x C/16 tcgen05.mma per tile into one of TWO accumulator slots in TMEM
-//   warps 2-5   normalise + activate the landed halo in place (the per-channel affine is rebuilt once per SAMPLE, not per tile)
-//   warps 6..   drain: one thread per output pixel of the tile (4 * TR warps): tcgen05.ld -> tail_epilogue
-// mbarriers: h_full (TMA -> transform), h_xf (transform -> MMA, 128 arrivals), h_empty (MMA commit -> TMA), acc_full (MMA
-// commit -> drain), acc_empty (drain -> MMA, one arrival per drain warp once its tcgen05.ld has completed).
+//   warps 2..   workers (4 * TR + 4 warps), two stages on the same warps, one tile apart:
+//               transform(i + 1): normalise + activate the landed halo in place (the per-channel affine is rebuilt once per
+//                                 SAMPLE, not per tile), every worker thread;
+//               drain(i):         one thread per output pixel of the tile (4 * TR warps): tcgen05.ld -> tail_epilogue.
+// mbarriers: h_full (TMA -> transform), h_xf (transform -> MMA, one arrival per worker thread), h_empty (MMA commit -> TMA),
+// acc_full (MMA commit -> drain), acc_empty (drain -> MMA, one arrival per drain warp once its tcgen05.ld has completed).
 template <int C, int TR> struct TailPCfg {
     static constexpr int ROWB = 2 * C;
     static constexpr int HROWS = (TR + 2) * TT_HW;
@@ -220,11 +222,13 @@ template <int C, int TR> struct TailPCfg {
     static constexpr int B_BYTES = 9 * TT_N * ROWB;
     static constexpr int ACC_COLS = TR * TT_N;                              // TMEM columns of one accumulator slot
     static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS; // 64 / 128: a power of two
-    static constexpr int DRAIN_WARPS = 4 * TR;
-    static constexpr int THREADS = (6 + DRAIN_WARPS) * 32;
+    static constexpr int DRAIN_WARPS = 4 * TR;                              // one thread per output pixel of a tile
+    static constexpr int WORKER_WARPS = DRAIN_WARPS + 4;                    // every worker warp transforms; the first DRAIN_WARPS also drain
+    static constexpr int THREADS = (2 + WORKER_WARPS) * 32;
     static constexpr int NBARS = 3 * NS + 5;
+    static constexpr int MAX_S = 512;                                       // base-grid copy in shared memory
     static constexpr size_t SMEM = 1024 + (size_t)NS * A_BYTES + B_BYTES + 2 * C * sizeof(double) + 2 * C * sizeof(float) + 16 * sizeof(float) +
-                                   NBARS * sizeof(uint64_t) + 16;
+                                   MAX_S * sizeof(float) + NBARS * sizeof(uint64_t) + 16;
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -249,7 +253,8 @@ __global__ void __launch_bounds__(TailPCfg<C, TR>::THREADS, 1) tail_tc_persist_k
     float* cA = reinterpret_cast<float*>(chs + 2 * C);                   // [C] affine
     float* cB = cA + C;
     float* sbias = cB + C;                                               // [16]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + 16);
+    float* sbase = sbias + 16;                                           // [S] affine_grid coordinates (one dependent global round trip less per pixel)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sbase + Cfg::MAX_S);
     uint64_t* h_full = bars, *h_xf = bars + NS, *h_empty = bars + 2 * NS;
     uint64_t* acc_full = bars + 3 * NS, *acc_empty = acc_full + 2, *w_full = acc_empty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(TailPCfg<C, TR>::THREADS, 1) tail_tc_persist_k
     const int nt = (int)((long)(blockIdx.x + 1) * total / gridDim.x) - t_begin;       // contiguous tiles of this CTA (>= 1: grid <= total)
 
     if (tid == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(h_full + s), 1); mbar_init(smem_u32(h_xf + s), 128); mbar_init(smem_u32(h_empty + s), 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(h_full + s), 1); mbar_init(smem_u32(h_xf + s), Cfg::WORKER_WARPS * 32); mbar_init(smem_u32(h_empty + s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(acc_full + a), 1); mbar_init(smem_u32(acc_empty + a), Cfg::DRAIN_WARPS); }
         mbar_init(smem_u32(w_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(TailPCfg<C, TR>::THREADS, 1) tail_tc_persist_k
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid >= 64 && tid < 80) sbias[tid - 64] = (tid - 64) < TAIL_CO_PAD ? __ldg(p.bias + (tid - 64)) : 0.0f;     // weights: independent of the previous kernel
+    for (int i = tid; i < p.S; i += Cfg::THREADS) sbase[i] = __ldg(p.base + i);                                     // constant table
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -321,57 +327,81 @@ __global__ void __launch_bounds__(TailPCfg<C, TR>::THREADS, 1) tail_tc_persist_k
                 umma_commit(smem_u32(acc_full + a));
             }
         }
-    } else if (warp < 6) {   // ===== warps 2-5: per-sample affine, then normalise + activate every landed halo in place =====
-        const int te = tid - 64;
+    } else {
+        // ===== worker warps (2 ..): BOTH remaining stages, on every warp =====
+        //   transform(i + 1): normalise + activate the landed halo of the NEXT tile in place, all WORKERS threads;
+        //   drain(i):         one thread per output pixel of the current tile (the first 4 * TR warps).
+        // The first version gave the transform four dedicated warps: one warp per scheduler, 0.2 IPC on dependent
+        // conversions / MUFU, 7 000 cycles per tile and the slowest stage of the pipeline while sixteen drain warps waited
+        // (ncu source page, profiles/r02_tail_persist_notes.txt).  A thread owns ONE 16-byte chunk column (8 channels) of the
+        // halo rows wt / NCH + k * (WORKERS / NCH): its 16 coefficients live in registers, XU rows are in flight at once.
+        constexpr int WORKERS = Cfg::WORKER_WARPS * 32;
+        constexpr int RSTEP = WORKERS / NCH;
+        constexpr int ITEMS = (Cfg::HROWS + RSTEP - 1) / RSTEP, ITERS = (ITEMS + 5) / 6, XU = (ITEMS + ITERS - 1) / ITERS;
+        const int wt = tid - 64, wid = warp - 2;
+        const int jc = wt % NCH, r_first = wt / NCH;
         const int cpg = p.groups == 0 ? 1 : C / p.groups;
         const bool silu = p.act == ACT_SILU || p.act == ACT_SILU_FAST;
+        const bool relu = p.act == ACT_RELU;
+        const int q = warp & 3;                                                  // TMEM lane quadrant this warp may access
+        const int dr = wid >> 2;                                                 // drain: tile row (each quadrant appears once per row)
+        float av[8], bv[8];
         int cur_n = -1;
-        for (int i = 0; i < nt; ++i) {
+
+        auto transform = [&](int i) {
             const int s = i % NS;
             int t = t_begin + i;
             const int n = t / per_n; t -= n * per_n;
             const int ty = t / tiles_x, tx = t - ty * tiles_x;
             const int x0 = tx * TT_W, y0 = ty * TR;
-            if (n != cur_n) {
+            if (n != cur_n) {            // per-SAMPLE affine of the pending normalisation, from the producer's statistics
                 cur_n = n;
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");          // everyone is done with the previous sample's table
-                for (int c = te; c < C; c += 128) {
-                    const double2 v = fold_stat_replicas(p.stats + ((long)n * p.stats_ld + c) * 2, p.stats_rep_stride, p.stats_rep);
-                    chs[2 * c] = v.x; chs[2 * c + 1] = v.y;
+                float g1 = 0.0f, b1 = 0.0f;
+                if (wt < C) { g1 = __ldg(p.gamma + wt); b1 = __ldg(p.beta + wt); }     // requested ahead of the statistics
+                asm volatile("bar.sync 1, %0;\n" :: "n"(WORKERS) : "memory");           // everyone is done with the previous table
+                if (wt < C) {
+                    const double2 v = fold_stat_replicas16(p.stats + ((long)n * p.stats_ld + wt) * 2, p.stats_rep_stride, p.stats_rep);
+                    chs[2 * wt] = v.x; chs[2 * wt + 1] = v.y;
                 }
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                for (int c = te; c < C; c += 128) {
-                    const int g0 = (c / cpg) * cpg;
+                asm volatile("bar.sync 1, %0;\n" :: "n"(WORKERS) : "memory");
+                if (wt < C) {
+                    const int g0 = (wt / cpg) * cpg;
                     double su = 0.0, sq = 0.0;
                     for (int j = 0; j < cpg; ++j) { su += chs[2 * (g0 + j)]; sq += chs[2 * (g0 + j) + 1]; }
                     const double cnt = (double)p.S * p.S * cpg;
                     const double mean = su / cnt;
                     double var = sq / cnt - mean * mean;
                     if (var < 0.0) var = 0.0;
-                    float A = (float)(1.0 / sqrt(var + 1e-5)) * __ldg(p.gamma + c);
-                    float B = __ldg(p.beta + c) - (float)mean * A;
+                    float A = (float)(1.0 / sqrt(var + 1e-5)) * g1;
+                    float B = b1 - (float)mean * A;
                     if (silu) { A *= 0.5f; B *= 0.5f; }                            // silu(v) = h + h * tanh(h), h = v / 2
-                    cA[c] = A; cB[c] = B;
+                    cA[wt] = A; cB[wt] = B;
                 }
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                asm volatile("bar.sync 1, %0;\n" :: "n"(WORKERS) : "memory");
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { av[e] = cA[8 * jc + e]; bv[e] = cB[8 * jc + e]; }
             }
             mbar_wait(smem_u32(h_full + s), (i / NS) & 1);
             uint8_t* hbase = smA + s * Cfg::A_BYTES;
-            for (int row = te; row < Cfg::HROWS; row += 128) {
-                const int hy = row / TT_HW, hx = row - hy * TT_HW;
-                const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
-                if (gy < 0 || gy >= p.S || gx < 0 || gx >= p.S) continue;          // zero padding stays zero
-                uint8_t* rowp = hbase + row * ROWB;
-                const int swz = ROWB == 128 ? (row & 7) : ((row >> 1) & 3);
+#pragma unroll 1
+            for (int row0 = r_first; row0 < Cfg::HROWS; row0 += XU * RSTEP) {
+                uint4 d[XU];
+                uint4* dp[XU];
+                bool ok[XU];
 #pragma unroll
-                for (int j = 0; j < NCH; ++j) {
-                    uint4* dp = reinterpret_cast<uint4*>(rowp + ((j ^ swz) << 4));
-                    uint4 d = *dp;
-                    const float4 a0 = *reinterpret_cast<const float4*>(cA + 8 * j), a1 = *reinterpret_cast<const float4*>(cA + 8 * j + 4);
-                    const float4 b0 = *reinterpret_cast<const float4*>(cB + 8 * j), b1 = *reinterpret_cast<const float4*>(cB + 8 * j + 4);
-                    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                    __half2* hp = reinterpret_cast<__half2*>(&d);
+                for (int u = 0; u < XU; ++u) {
+                    const int row = row0 + u * RSTEP;
+                    const int hy = row / TT_HW, hx = row - hy * TT_HW;
+                    const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                    ok[u] = row < Cfg::HROWS && gy >= 0 && gy < p.S && gx >= 0 && gx < p.S;       // zero padding stays zero
+                    const int swz = ROWB == 128 ? (row & 7) : ((row >> 1) & 3);
+                    dp[u] = reinterpret_cast<uint4*>(hbase + row * ROWB + ((jc ^ swz) << 4));
+                    if (ok[u]) d[u] = *dp[u];
+                }
+#pragma unroll
+                for (int u = 0; u < XU; ++u) {
+                    if (!ok[u]) continue;
+                    __half2* hp = reinterpret_cast<__half2*>(&d[u]);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         float2 v = __half22float2(hp[e]);
@@ -381,39 +411,47 @@ __global__ void __launch_bounds__(TailPCfg<C, TR>::THREADS, 1) tail_tc_persist_k
                             asm("tanh.approx.f32 %0, %1;\n" : "=f"(tx2) : "f"(v.x));
                             asm("tanh.approx.f32 %0, %1;\n" : "=f"(ty2) : "f"(v.y));
                             v.x = fmaf(v.x, tx2, v.x); v.y = fmaf(v.y, ty2, v.y);
-                        } else if (p.act == ACT_RELU) {
+                        } else if (relu) {
                             v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f);
                         }
                         hp[e] = __floats2half2_rn(v.x, v.y);
                     }
-                    *dp = d;
                 }
+#pragma unroll
+                for (int u = 0; u < XU; ++u)
+                    if (ok[u]) *dp[u] = d[u];
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes -> the tensor core's async-proxy reads
             mbar_arrive(smem_u32(h_xf + s));
-        }
-    } else {                 // ===== drain warps: thread = one output pixel of the tile =====
-        const int dw = warp - 6;
-        const int q = warp & 3;                                                  // TMEM lane quadrant this warp may access
-        const int r = dw >> 2;                                                   // tile row (each quadrant appears once per row)
-        for (int i = 0; i < nt; ++i) {
+        };
+
+        auto drain = [&](int i) {
             const int a = i & 1;
             int t = t_begin + i;
             const int n = t / per_n; t -= n * per_n;
             const int ty = t / tiles_x, tx = t - ty * tiles_x;
-            mbar_wait(smem_u32(acc_full + a), (i >> 1) & 1);
+            // ONE warp polls the mbarrier, the others park on a named barrier: sixteen warps spinning in try_wait executed more
+            // instructions than the rest of the kernel together (9.1 M of 16.1 M warp instructions in the first version)
+            if (wid == 0) mbar_wait(smem_u32(acc_full + a), (i >> 1) & 1);
+            asm volatile("bar.sync 2, %0;\n" :: "n"(Cfg::DRAIN_WARPS * 32) : "memory");
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             uint32_t acc[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + r * TT_N), acc);
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + dr * TT_N), acc);
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             if (lane == 0) mbar_arrive(smem_u32(acc_empty + a));                 // the accumulator slot may be overwritten
-            const int x = tx * TT_W + q * 32 + lane, y = ty * TR + r;
+            const int x = tx * TT_W + q * 32 + lane, y = ty * TR + dr;
             if (x < p.S) {
                 float o[TAIL_CO_PAD];
 #pragma unroll
                 for (int j = 0; j < TAIL_CO_PAD; ++j) o[j] = fmaf(__uint_as_float(acc[j]), p.acc_scale, sbias[j]);
-                tail_epilogue<KIND>(o, n, y, x, p.S, p.img0, p.img1, p.base, p.o[0], p.o[1], p.o[2], p.o[3], p.o[4], p.o[5], p.o[6], p.o[7]);
+                tail_epilogue<KIND>(o, n, y, x, p.S, p.img0, p.img1, sbase, p.o[0], p.o[1], p.o[2], p.o[3], p.o[4], p.o[5], p.o[6], p.o[7]);
             }
+        };
+
+        transform(0);
+        for (int i = 0; i < nt; ++i) {
+            if (i + 1 < nt) transform(i + 1);
+            if (wid < Cfg::DRAIN_WARPS) drain(i);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -533,6 +571,7 @@ void launch_tail_persist(const TailWeights& tw, const View& f, const NormSpecTai
     p.bias = tw.bias; p.acc_scale = 1.0f / tw.w16_scale;
     p.img0 = i0; p.img1 = i1; p.base = base_grid_table(f.H);
     for (int i = 0; i < 8; ++i) p.o[i] = i < nout ? o[i] : nullptr;
+    THA4_REQUIRE(f.H <= Cfg::MAX_S, "tail_tc: image size");
     THA4_ENSURE_SMEM((tail_tc_persist_kernel<KIND, C, TR>), Cfg::SMEM);
     const long total = (long)ceil_div(f.W, TT_W) * (f.H / TR) * f.N;
     dim3 grid((unsigned)std::min<long>(total, tail_num_sms()));
