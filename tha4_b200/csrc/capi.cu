@@ -785,7 +785,12 @@ int tha4_test_tail(tha4_ctx* ctx, int kind, const float* feature, int N, int C, 
             View f16v = f; f16v.f16 = 1; f16v.p = P->alloc(((size_t)N * S * S * C + 1) / 2);
             convert_f16(f, f16v, s);
             NormSpecTail ns; ns.groups = groups; ns.act = a; ns.gamma = gamma; ns.beta = beta;
-            tail_tc_forward((TailKind)kind, tw, f16v, ns, i0, i1, outputs, s);
+            // interleaved copies of the image(s), as the networks hand them over (their own NHWC input tensors)
+            View g0; g0.N = N; g0.H = S; g0.W = S; g0.C = 4; g0.ld = 4; g0.p = P->alloc((size_t)N * S * S * 4);
+            nchw_to_nhwc(i0, g0, s);
+            View g1 = g0;
+            if (image1) { g1.p = P->alloc((size_t)N * S * S * 4); nchw_to_nhwc(i1, g1, s); }
+            tail_tc_forward((TailKind)kind, tw, f16v, ns, i0, i1, outputs, s, &g0, image1 ? &g1 : nullptr);
         } else {
             tail_forward((TailKind)kind, tw, f, coef, a, i0, i1, outputs, s, strict);
         }

@@ -200,6 +200,10 @@ __device__ __forceinline__ void epi_direct(const TcParams& p, uint32_t tmem_base
                                            const CUtensorMap* tm32 = nullptr, const CUtensorMap* tm16 = nullptr,
                                            const CUtensorMap* tmR = nullptr, uint64_t* res_bars = nullptr) {
     const int q = warp & 3;                                    // TMEM lane quadrant this warp may access
+    // the bias lines of this tile's columns are pulled into L1 while the MMAs still run: the float4 reads below found them
+    // in L2 at best, one exposed round trip per 32-column step
+    if (p.bias && q == 0 && lane * 32 < BN && n0 + lane * 32 < p.outC)
+        asm volatile("prefetch.global.L1 [%0];\n" :: "l"(p.bias + n0 + lane * 32) : "memory");
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     // p.st_tma bit 2: the residual tile (same geometry as the fp32 output) ARRIVES by TMA as well, into the fp32 stage of

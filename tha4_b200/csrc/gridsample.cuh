@@ -55,6 +55,44 @@ __device__ __forceinline__ void gs_sample(const float* __restrict__ img, long sc
     }
 }
 
+// Same sampling from an INTERLEAVED copy of the RGBA image (NHWC, `ld` floats per pixel, the four channels 16-byte aligned;
+// img points at pixel (0, 0) of the sample): one 16-byte load per corner instead of four 4-byte loads from four planes.
+// The planar version needs sixteen 64-bit addresses per pixel; under the register cap of the fused tails the compiler reused
+// one address register pair and the loads serialised on its release (ncu source page: the long-scoreboard stalls of the
+// drain sat on the IADD3s between the LDGs).  Same products, same order of additions: bit-identical results.
+// issue: the four corner pixels of tap t (clamped offsets: every address is valid)
+__device__ __forceinline__ void gs_issue4_nhwc(const float* __restrict__ img, int ld, int W, int H, const GsTap& t, float4 (&v)[4]) {
+    const bool xin = (t.x0 + 1) < W, yin = (t.y0 + 1) < H;
+    const int p00 = t.y0 * W + t.x0;
+    const int p01 = p00 + (xin ? 1 : 0), p10 = p00 + (yin ? W : 0), p11 = p10 + (xin ? 1 : 0);
+    v[0] = __ldg(reinterpret_cast<const float4*>(img + (size_t)((unsigned)p00 * (unsigned)ld)));
+    v[1] = __ldg(reinterpret_cast<const float4*>(img + (size_t)((unsigned)p01 * (unsigned)ld)));
+    v[2] = __ldg(reinterpret_cast<const float4*>(img + (size_t)((unsigned)p10 * (unsigned)ld)));
+    v[3] = __ldg(reinterpret_cast<const float4*>(img + (size_t)((unsigned)p11 * (unsigned)ld)));
+}
+// combine: the bilinear blend of the loaded corners, in gs_sample's order of operations
+__device__ __forceinline__ void gs_combine4(const GsTap& t, int W, int H, const float4 (&v)[4], float (&out)[4]) {
+    const float wx1 = __fsub_rn(t.ix, t.fx), wx0 = __fsub_rn(__fadd_rn(t.fx, 1.0f), t.ix);
+    const float wy1 = __fsub_rn(t.iy, t.fy), wy0 = __fsub_rn(__fadd_rn(t.fy, 1.0f), t.iy);
+    const float wnw = __fmul_rn(wx0, wy0), wne = __fmul_rn(wx1, wy0), wsw = __fmul_rn(wx0, wy1), wse = __fmul_rn(wx1, wy1);
+    const bool xin = (t.x0 + 1) < W, yin = (t.y0 + 1) < H;
+    const float v00[4] = {v[0].x, v[0].y, v[0].z, v[0].w}, v01[4] = {v[1].x, v[1].y, v[1].z, v[1].w};
+    const float v10[4] = {v[2].x, v[2].y, v[2].z, v[2].w}, v11[4] = {v[3].x, v[3].y, v[3].z, v[3].w};
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        float acc = __fmul_rn(v00[ch], wnw);
+        if (xin) acc = __fadd_rn(acc, __fmul_rn(v01[ch], wne));
+        if (yin) acc = __fadd_rn(acc, __fmul_rn(v10[ch], wsw));
+        if (xin && yin) acc = __fadd_rn(acc, __fmul_rn(v11[ch], wse));
+        out[ch] = acc;
+    }
+}
+__device__ __forceinline__ void gs_sample4_nhwc(const float* __restrict__ img, int ld, int W, int H, const GsTap& t, float (&out)[4]) {
+    float4 v[4];
+    gs_issue4_nhwc(img, ld, W, H, t, v);
+    gs_combine4(t, W, H, v, out);
+}
+
 // interpolate(bilinear, align_corners=False) source coordinate for one axis.
 struct LerpTap { int i0, i1; float l0, l1; };
 __device__ __forceinline__ LerpTap lerp_locate(int dst, float scale, int in_size) {

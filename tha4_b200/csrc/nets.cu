@@ -380,7 +380,10 @@ void EncDecNet::forward_fused(Runtime& rt, const View& x0, const ImgView& image0
         View fv = feat.h;                                 // f16 data + the statistics slot of the tensor
         fv.stats = feat.f.stats; fv.stats_ld = feat.f.stats_ld; fv.stats_rep = feat.f.stats_rep; fv.stats_rep_stride = feat.f.stats_rep_stride;
         NormSpecTail ns; ns.groups = 0; ns.act = ACT_RELU; ns.gamma = up_n_[2].gamma; ns.beta = up_n_[2].beta;
-        tail_tc_forward(kind_, tail_, fv, ns, image0, image1, outputs, s);
+        // the network's own NHWC input holds interleaved copies of the image(s) the tail samples (combiner: [background | eyebrow])
+        const View g0 = kind_ == TAIL_COMBINER ? x0.slice(4, 4) : x0.slice(0, 4);
+        const View g1 = x0.slice(0, 4);
+        tail_tc_forward(kind_, tail_, fv, ns, image0, image1, outputs, s, &g0, kind_ == TAIL_COMBINER ? &g1 : nullptr);
     } else {
         float* coef = tail_coef(rt, feat.f, up_n_[2], 0);
         tail_forward(kind_, tail_, feat.f, coef, ACT_RELU, image0, image1, outputs, s, rt.strict);
@@ -835,7 +838,8 @@ void UNetNet::forward_fused(Runtime& rt, const ImgView& image, const float* coar
         View fv = feat.h;
         fv.stats = feat.f.stats; fv.stats_ld = feat.f.stats_ld; fv.stats_rep = feat.f.stats_rep; fv.stats_rep_stride = feat.f.stats_rep_stride;
         NormSpecTail ns; ns.groups = 32; ns.act = ACT_SILU_FAST; ns.gamma = last_n_.gamma; ns.beta = last_n_.beta;
-        tail_tc_forward(TAIL_UNET, tail_, fv, ns, image, none, outputs, s);
+        const View g0 = x0.slice(0, 4);       // channels 0-3 of the network input are the image the tail warps (Upscaler02: the rest image)
+        tail_tc_forward(TAIL_UNET, tail_, fv, ns, image, none, outputs, s, &g0);
     } else {
         float* coef = tail_coef(rt, feat.f, last_n_, 32);
         tail_forward(TAIL_UNET, tail_, feat.f, coef, ACT_SILU_FAST, image, none, outputs, s, rt.strict);

@@ -94,7 +94,9 @@ void tail_forward(TailKind kind, const TailWeights& tw, const View& feature, con
 void tail_make_half(TailWeights& tw, cudaStream_t s);     // f16 B-operand copy of the head weights (recorded in the active AllocSink)
 bool tail_tc_supported(const TailWeights& tw, const View& feature);
 void tail_tc_enable_persist(bool on);      // option "tail_persist": persistent pipelined tcgen05 tail (default on)
+// gather0 / gather1: optional fp32 NHWC copies of image0 / image1 (4-channel slices, 16-byte aligned pixels), e.g. the
+// network's own input tensor: the persistent kernel then reads a pixel's RGBA with one 16-byte load (same values, same results)
 void tail_tc_forward(TailKind kind, const TailWeights& tw, const View& feature, const NormSpecTail& ns, const ImgView& image0,
-                     const ImgView& image1, float* const* outputs, cudaStream_t s);
+                     const ImgView& image1, float* const* outputs, cudaStream_t s, const View* gather0 = nullptr, const View* gather1 = nullptr);
 
 }  // namespace tha4

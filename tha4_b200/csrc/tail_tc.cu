@@ -43,6 +43,7 @@ struct TailTcParams {
     const float* bias;               // [TAIL_CO_PAD]
     float acc_scale;
     ImgView img0, img1;
+    const float* g0; int g0_ld; const float* g1; int g1_ld;     // optional interleaved (NHWC) copies of img0 / img1 (tail_epilogue.cuh)
     const float* base;
     float* o[8];
 };
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(TT_THREADS) tail_tc_kernel(const __grid_consta
 // contiguous range of tiles with the phases on different warps and different tiles:
 //   warp 0      TMA producer: halo boxes into an NS-deep ring (the head weights once)
 //   warp 1      MMA issuer: TR x 9 x C/16 tcgen05.mma per tile into one of TWO accumulator slots in TMEM
-//   warps 2..   workers (4 * TR + 4 warps), two stages on the same warps, one tile apart:
+//   warps 2..   workers (4 * TR warps), two stages on the same warps, one tile apart:
 //               transform(i + 1): normalise + activate the landed halo in place (the per-channel affine is rebuilt once per
 //                                 SAMPLE, not per tile), every worker thread;
 //               drain(i):         one thread per output pixel of the tile (4 * TR warps): tcgen05.ld -> tail_epilogue.
@@ -223,7 +224,8 @@ template <int C, int TR> struct TailPCfg {
     static constexpr int ACC_COLS = TR * TT_N;                              // TMEM columns of one accumulator slot
     static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS; // 64 / 128: a power of two
     static constexpr int DRAIN_WARPS = 4 * TR;                              // one thread per output pixel of a tile
-    static constexpr int WORKER_WARPS = DRAIN_WARPS + 4;                    // every worker warp transforms; the first DRAIN_WARPS also drain
+    static constexpr int WORKER_WARPS = DRAIN_WARPS;                        // every worker warp transforms AND drains (18 / 10 warps per CTA: the
+                                                                            // register cap stays above what the split drain keeps live)
     static constexpr int THREADS = (2 + WORKER_WARPS) * 32;
     static constexpr int NBARS = 3 * NS + 5;
     static constexpr int MAX_S = 512;                                       // base-grid copy in shared memory
@@ -425,33 +427,58 @@ __global__ void __launch_bounds__(TailPCfg<C, TR>::THREADS, 1) tail_tc_persist_k
             mbar_arrive(smem_u32(h_xf + s));
         };
 
-        auto drain = [&](int i) {
-            const int a = i & 1;
+        // The drain of a tile is split around the transform of the next one: phase A reads the two grid_change outputs of the
+        // pixel and REQUESTS the four corner pixels of its sampling tap; the transform runs while they travel; phase B reads
+        // the accumulator again (cheap: TMEM) and finishes.  Unsplit, every tile paid one exposed global round trip with all
+        // sixteen drain warps waiting on it together (ncu source page: 60 % long-scoreboard in the drain, ~1.6 us per tile).
+        // Every drain warp polls acc_full itself: a common named barrier made fifteen warps wait for the slowest (23 % of all
+        // samples); with the drain behind the transform the accumulator has usually been complete for a while.
+        float4 pre[4];
+        bool have_pre = false;
+        auto tile_xy = [&](int i, int& n, int& x, int& y) {
             int t = t_begin + i;
-            const int n = t / per_n; t -= n * per_n;
+            n = t / per_n; t -= n * per_n;
             const int ty = t / tiles_x, tx = t - ty * tiles_x;
-            // ONE warp polls the mbarrier, the others park on a named barrier: sixteen warps spinning in try_wait executed more
-            // instructions than the rest of the kernel together (9.1 M of 16.1 M warp instructions in the first version)
-            if (wid == 0) mbar_wait(smem_u32(acc_full + a), (i >> 1) & 1);
-            asm volatile("bar.sync 2, %0;\n" :: "n"(Cfg::DRAIN_WARPS * 32) : "memory");
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            x = tx * TT_W + q * 32 + lane; y = ty * TR + dr;
+        };
+        auto load_acc = [&](int a, float (&o)[TAIL_CO_PAD]) {
             uint32_t acc[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + dr * TT_N), acc);
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            if (lane == 0) mbar_arrive(smem_u32(acc_empty + a));                 // the accumulator slot may be overwritten
-            const int x = tx * TT_W + q * 32 + lane, y = ty * TR + dr;
-            if (x < p.S) {
-                float o[TAIL_CO_PAD];
 #pragma unroll
-                for (int j = 0; j < TAIL_CO_PAD; ++j) o[j] = fmaf(__uint_as_float(acc[j]), p.acc_scale, sbias[j]);
-                tail_epilogue<KIND>(o, n, y, x, p.S, p.img0, p.img1, sbase, p.o[0], p.o[1], p.o[2], p.o[3], p.o[4], p.o[5], p.o[6], p.o[7]);
+            for (int j = 0; j < TAIL_CO_PAD; ++j) o[j] = fmaf(__uint_as_float(acc[j]), p.acc_scale, sbias[j]);
+        };
+        auto drain_issue = [&](int i) {
+            const int a = i & 1;
+            int n, x, y;
+            tile_xy(i, n, x, y);
+            mbar_wait(smem_u32(acc_full + a), (i >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            have_pre = false;
+            if (KIND != TAIL_DECOMPOSER && p.g0 != nullptr) {           // warp-uniform
+                float o[TAIL_CO_PAD];
+                load_acc(a, o);
+                if (x < p.S) have_pre = tail_gather_issue<KIND>(o, n, y, x, p.S, sbase, p.g0, p.g0_ld, pre);
             }
         };
+        auto drain_finish = [&](int i) {
+            const int a = i & 1;
+            int n, x, y;
+            tile_xy(i, n, x, y);
+            float o[TAIL_CO_PAD];
+            load_acc(a, o);
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            if (lane == 0) mbar_arrive(smem_u32(acc_empty + a));                 // the accumulator slot may be overwritten
+            if (x < p.S)
+                tail_epilogue<KIND>(o, n, y, x, p.S, p.img0, p.img1, sbase, p.o[0], p.o[1], p.o[2], p.o[3], p.o[4], p.o[5], p.o[6], p.o[7],
+                                    p.g0, p.g0_ld, p.g1, p.g1_ld, have_pre ? &pre : nullptr);
+        };
 
+        const bool drainer = wid < Cfg::DRAIN_WARPS;
         transform(0);
         for (int i = 0; i < nt; ++i) {
+            if (drainer) drain_issue(i);
             if (i + 1 < nt) transform(i + 1);
-            if (wid < Cfg::DRAIN_WARPS) drain(i);
+            if (drainer) drain_finish(i);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -562,7 +589,7 @@ int tail_num_sms() {
 
 template <int KIND, int C, int TR>
 void launch_tail_persist(const TailWeights& tw, const View& f, const NormSpecTail& ns, const ImgView& i0, const ImgView& i1, float* const* o, int nout,
-                         cudaStream_t s) {
+                         cudaStream_t s, const View* g0, const View* g1) {
     using Cfg = TailPCfg<C, TR>;
     TailTcParams p{};
     p.S = f.H; p.N = f.N;
@@ -570,6 +597,12 @@ void launch_tail_persist(const TailWeights& tw, const View& f, const NormSpecTai
     p.groups = ns.groups; p.act = ns.act; p.gamma = ns.gamma; p.beta = ns.beta;
     p.bias = tw.bias; p.acc_scale = 1.0f / tw.w16_scale;
     p.img0 = i0; p.img1 = i1; p.base = base_grid_table(f.H);
+    auto gather_ok = [&](const View* g) {      // fp32 NHWC view of the same geometry, four channels 16-byte aligned, offsets within 32 bits
+        return g && g->p && !g->f16 && g->N == f.N && g->H == f.H && g->W == f.W && g->ld % 4 == 0 && (reinterpret_cast<uintptr_t>(g->p) & 15) == 0 &&
+               (size_t)f.H * f.W * g->ld < (size_t)1 << 30;
+    };
+    if (gather_ok(g0)) { p.g0 = g0->p; p.g0_ld = g0->ld; }
+    if (gather_ok(g1)) { p.g1 = g1->p; p.g1_ld = g1->ld; }
     for (int i = 0; i < 8; ++i) p.o[i] = i < nout ? o[i] : nullptr;
     THA4_REQUIRE(f.H <= Cfg::MAX_S, "tail_tc: image size");
     THA4_ENSURE_SMEM((tail_tc_persist_kernel<KIND, C, TR>), Cfg::SMEM);
@@ -587,14 +620,14 @@ void launch_tail_persist(const TailWeights& tw, const View& f, const NormSpecTai
 
 template <int KIND>
 void launch_tail_tc_c(const TailWeights& tw, const View& f, const NormSpecTail& ns, const ImgView& i0, const ImgView& i1, float* const* o, int nout,
-                      cudaStream_t s) {
+                      cudaStream_t s, const View* g0, const View* g1) {
     if (g_tail_persist) {
         // tile rows per step: 4 when that still gives every SM two tiles or more, else 2 (more, smaller tiles: the small sites at
         // B = 1 are one latency chain per CTA)
         const long tiles4 = (long)ceil_div(f.W, TT_W) * (f.H / 4) * f.N;
         const bool tr4 = tiles4 >= 2L * tail_num_sms();
-        if (tw.C == 32) { if (tr4) launch_tail_persist<KIND, 32, 4>(tw, f, ns, i0, i1, o, nout, s); else launch_tail_persist<KIND, 32, 2>(tw, f, ns, i0, i1, o, nout, s); }
-        else            { if (tr4) launch_tail_persist<KIND, 64, 4>(tw, f, ns, i0, i1, o, nout, s); else launch_tail_persist<KIND, 64, 2>(tw, f, ns, i0, i1, o, nout, s); }
+        if (tw.C == 32) { if (tr4) launch_tail_persist<KIND, 32, 4>(tw, f, ns, i0, i1, o, nout, s, g0, g1); else launch_tail_persist<KIND, 32, 2>(tw, f, ns, i0, i1, o, nout, s, g0, g1); }
+        else            { if (tr4) launch_tail_persist<KIND, 64, 4>(tw, f, ns, i0, i1, o, nout, s, g0, g1); else launch_tail_persist<KIND, 64, 2>(tw, f, ns, i0, i1, o, nout, s, g0, g1); }
         return;
     }
     if (tw.C == 32) launch_tail_tc<KIND, 32>(tw, f, ns, i0, i1, o, nout, s);
@@ -634,15 +667,15 @@ bool tail_tc_supported(const TailWeights& tw, const View& feature) {
 }
 
 void tail_tc_forward(TailKind kind, const TailWeights& tw, const View& feature, const NormSpecTail& ns, const ImgView& image0,
-                     const ImgView& image1, float* const* outputs, cudaStream_t s) {
+                     const ImgView& image1, float* const* outputs, cudaStream_t s, const View* g0, const View* g1) {
     THA4_REQUIRE(tail_tc_supported(tw, feature), "tail_tc: unsupported configuration");
     THA4_REQUIRE(image0.H == feature.H && image0.W == feature.W && image0.C == 4, "tail_tc: image dims");
     THA4_REQUIRE(ns.groups == 0 || tw.C % ns.groups == 0, "tail_tc: groups");
     switch (kind) {
-        case TAIL_UNET: launch_tail_tc_c<TAIL_UNET>(tw, feature, ns, image0, image1, outputs, 5, s); break;
-        case TAIL_DECOMPOSER: launch_tail_tc_c<TAIL_DECOMPOSER>(tw, feature, ns, image0, image1, outputs, 6, s); break;
-        case TAIL_COMBINER: launch_tail_tc_c<TAIL_COMBINER>(tw, feature, ns, image0, image1, outputs, 8, s); break;
-        case TAIL_FACE: launch_tail_tc_c<TAIL_FACE>(tw, feature, ns, image0, image1, outputs, 8, s); break;
+        case TAIL_UNET: launch_tail_tc_c<TAIL_UNET>(tw, feature, ns, image0, image1, outputs, 5, s, g0, g1); break;
+        case TAIL_DECOMPOSER: launch_tail_tc_c<TAIL_DECOMPOSER>(tw, feature, ns, image0, image1, outputs, 6, s, g0, g1); break;
+        case TAIL_COMBINER: launch_tail_tc_c<TAIL_COMBINER>(tw, feature, ns, image0, image1, outputs, 8, s, g0, g1); break;
+        case TAIL_FACE: launch_tail_tc_c<TAIL_FACE>(tw, feature, ns, image0, image1, outputs, 8, s, g0, g1); break;
     }
 }
 
