@@ -60,7 +60,9 @@ const char* tha4_last_error(const tha4_ctx* ctx);
  *          "cluster_splitk" (1: K-split convs reduce through a thread-block cluster / DSMEM; 0: workspace + reduce kernel),
  *          "pdl" (1: programmatic dependent launch), "tc_stride2" (1: 4x4 stride-2 convs on tcgen05),
  *          "small_bn" (1: narrower N tiles for small unsplit launches), "siren_tc" (1: students on tcgen05; 0: mma.sync kernels),
- *          "attn_split16", "profile" (1: time every kernel class with CUDA events on the launching stream, 2: same + reset, 0: off).
+ *          "attn_split16", "attn_mma" (1: default-mode attention on mma.sync with f16 operands; 0: the fp32 kernel everywhere),
+ *          "tail_persist" (1: persistent software-pipelined decoder tail; 0: one tile per CTA),
+ *          "profile" (1: time every kernel class with CUDA events on the launching stream, 2: same + reset, 0: off).
  * "strict", "microbatch", "cuda_graphs" and "half_operands" belong to the context.  The other developer switches select
  * kernels PROCESS-WIDE (they are statics of the kernel translation units): changing one on any context changes it for all
  * contexts of the process, and every change drops the captured graphs / cached outputs of the context it was made on.

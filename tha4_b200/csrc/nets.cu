@@ -2,6 +2,7 @@
 #include "nets.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace tha4 {
 
@@ -99,6 +100,13 @@ __global__ void vec_add_kernel(float* dst, const float* a, const float* b, int n
     if (i < n) dst[i] = a[i] + b[i];
 }
 
+// Replicas of a tensor's statistics slot: producers spread their atomics over them, every consumer CTA folds all of them
+// (conv_tc_device.cuh: xf_build_coef).  Developer knob THA4_STATS_REP_MAX (default 16) bounds the count.
+int stats_rep_cap() {
+    static int cap = [] { const char* e = getenv("THA4_STATS_REP_MAX"); const int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+    return cap;
+}
+
 // rt != nullptr: the view also gets a (zeroed) statistics slot, to be filled by the conv that produces the tensor
 View make_view(Pool* pool, int N, int H, int W, int C, Runtime* rt = nullptr) {
     View v; v.N = N; v.H = H; v.W = W; v.C = C; v.ld = C;
@@ -106,7 +114,7 @@ View make_view(Pool* pool, int N, int H, int W, int C, Runtime* rt = nullptr) {
     if (rt) {   // replicas ~ tiles/16 (128-pixel conv tiles per sample), power of two in [1, 16]
         const int tiles = ((W + 15) / 16) * ((H + 7) / 8);
         int rep = 1;
-        while (rep < 16 && rep * 32 <= tiles) rep *= 2;
+        while (rep < stats_rep_cap() && rep * 32 <= tiles) rep *= 2;
         v.stats_rep = rep;
         v.stats_rep_stride = (long)N * C * 2;
         v.stats = rt->alloc_stats((size_t)rep * N * C * 2);
@@ -133,9 +141,9 @@ float* tail_coef(Runtime& rt, const View& x, const NormW& nw, int groups) {
 
 // normalisation layer = one elementwise pass: affine from x.stats rebuilt per CTA, activation / pool / residual fused
 void run_norm(Runtime& rt, const View& x, const NormW& nw, int groups, const float* film0, const float* film1,
-              int film1_ld, int act, int pool, const View* res, const View& y, const View* y16 = nullptr) {
+              int film1_ld, int act, int pool, const View* res, const View& y, const View* y16 = nullptr, const View* xpool = nullptr) {
     THA4_REQUIRE(nw.C == x.C, "norm: channel mismatch");
-    norm_apply_fused(x, groups, nw.gamma, nw.beta, film0, film1, film1_ld, act, pool, res, y, rt.stream, !rt.strict, y16);
+    norm_apply_fused(x, groups, nw.gamma, nw.beta, film0, film1, film1_ld, act, pool, res, y, rt.stream, !rt.strict, y16, xpool);
 }
 
 void run_conv(Runtime& rt, const ConvWeights& cw, const View& in, const View& out, int in_up = 0,
@@ -165,7 +173,7 @@ Tens make_act(Pool* pool, Runtime& rt, int N, int H, int W, int C, bool want_f32
         if (stats) {   // same replica rule as make_view
             const int tiles = ((W + 15) / 16) * ((H + 7) / 8);
             int rep = 1;
-            while (rep < 16 && rep * 32 <= tiles) rep *= 2;
+            while (rep < stats_rep_cap() && rep * 32 <= tiles) rep *= 2;
             v.stats_rep = rep; v.stats_rep_stride = (long)N * C * 2;
             v.stats = rt.alloc_stats((size_t)rep * N * C * 2); v.stats_ld = C;
         }
@@ -694,9 +702,11 @@ struct UNetFused {
                 run_conv_tc(rt, w.skip, x.h, nullptr, sk);
             }
         }
+        View xpool;
         if (mode == 2) {          // norm0 -> SiLU -> 2x2 mean as a pass (f16 result), then a plain conv
             View t0 = make_view16(rt.scratch, B, x.f.H / 2, x.f.W / 2, w.cin);
-            run_norm(rt, x.f, w.norm0, 32, nullptr, nullptr, 0, act, 1, nullptr, t0);
+            xpool = make_view(rt.scratch, B, x.f.H / 2, x.f.W / 2, w.cin);       // AvgPool2d(2) of the skip path, written by the same pass
+            run_norm(rt, x.f, w.norm0, 32, nullptr, nullptr, 0, act, 1, nullptr, t0, nullptr, &xpool);
             run_conv_tc(rt, w.conv0, t0, nullptr, h0);
         } else {                  // mode 1: conv0 was packed as CONV_UP2_3x3 (the upsample is folded into 4 phases of the low-res input)
             const ConvNormIn n0 = norm_in(x.f, w.norm0, 32, act);
@@ -709,7 +719,8 @@ struct UNetFused {
             if (rt.side) THA4_CUDA_CHECK(cudaStreamWaitEvent(rt.stream, rt.ev_join, 0));
             run_conv_tc(rt, w.conv1, h0.h, &n1, out, &sk.f, RES_SAME);
         } else {
-            run_conv_tc(rt, w.conv1, h0.h, &n1, out, &x.f, mode == 0 ? RES_SAME : (mode == 1 ? RES_UP2 : RES_DOWN2));
+            if (mode == 2) run_conv_tc(rt, w.conv1, h0.h, &n1, out, &xpool, RES_SAME);
+            else run_conv_tc(rt, w.conv1, h0.h, &n1, out, &x.f, mode == 0 ? RES_SAME : RES_UP2);
         }
     }
 

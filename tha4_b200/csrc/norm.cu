@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
                                                          const float* __restrict__ coef, int act, int pool,
                                                          const float* __restrict__ res, int res_ld,
                                                          float* __restrict__ y, int yH, int yW, int y_ld,
-                                                         __half* __restrict__ yh, int yh_ld, int C, long total,
-                                                         int round_out,
+                                                         __half* __restrict__ yh, int yh_ld, float* __restrict__ xpool, int xpool_ld,
+                                                         int C, long total, int round_out,
                                                          const double* __restrict__ sums, int stats_ld, int rep, long rep_stride,
                                                          int HW, int groups,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -208,16 +208,27 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(const float* __restrict
         const long pin = pix0 - (long)(FUSED ? 0 : n) * yH * yW;       // pixel index within the sample
         const int oy = (int)(pin / yW), ox = (int)(pin - (long)oy * yW);
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 raw[4];
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
                 const float4 v = *reinterpret_cast<const float4*>(
                     x + (((long)n * xH + 2 * oy + dy) * xW + 2 * ox + dx) * x_ld + 4 * q);
+                raw[2 * dy + dx] = v;
                 r.x += act_apply(v.x * c0.x + c0.y, act); r.y += act_apply(v.y * c0.z + c0.w, act);
                 r.z += act_apply(v.z * c1.x + c1.y, act); r.w += act_apply(v.w * c1.z + c1.w, act);
             }
         r.x *= 0.25f; r.y *= 0.25f; r.z *= 0.25f; r.w *= 0.25f;
+        if (xpool) {
+            // 2x2 mean of the RAW input as well (AvgPool2d(2) of the block's skip path, unet.py:58,164), in the order the conv
+            // epilogue's RES_DOWN2 used: the consumer then adds it as a same-resolution residual (one TMA tile instead of
+            // 128 scalar loads per thread: the unsplit RES_DOWN2 epilogues cost 28 - 37 us each, profiles/r02_halo_phase_stamps.txt)
+            float4 m;
+            m.x = 0.25f * ((raw[0].x + raw[1].x) + (raw[2].x + raw[3].x)); m.y = 0.25f * ((raw[0].y + raw[1].y) + (raw[2].y + raw[3].y));
+            m.z = 0.25f * ((raw[0].z + raw[1].z) + (raw[2].z + raw[3].z)); m.w = 0.25f * ((raw[0].w + raw[1].w) + (raw[2].w + raw[3].w));
+            *reinterpret_cast<float4*>(xpool + pix * xpool_ld + 4 * q) = m;
+        }
         if (res) {
             const float4 v = *reinterpret_cast<const float4*>(res + pix * res_ld + 4 * q);
             r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
@@ -274,15 +285,16 @@ void norm_apply(const View& x, const float* coef, int act, int pool, const View*
     prof_add_work(PROF_NORM, 0.0, ((double)x.pixels() + y.pixels() + (res ? y.pixels() : 0)) * x.C * 4);
     THA4_REQUIRE(!y.f16, "norm_apply: fp32 output");
     norm_apply_kernel<false><<<blocks, 256, 0, s>>>(x.p, x.H, x.W, x.ld, coef, act, pool, res ? res->p : nullptr,
-                                                    res ? res->ld : 0, y.p, y.H, y.W, y.ld, nullptr, 0, x.C, total, round_out,
+                                                    res ? res->ld : 0, y.p, y.H, y.W, y.ld, nullptr, 0, nullptr, 0, x.C, total, round_out,
                                                     nullptr, 0, 1, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, 0);
     THA4_LAUNCH_CHECK();
 }
 
 void norm_apply_fused(const View& x, int groups, const float* gamma, const float* beta, const float* film0,
                       const float* film1, int film1_ld, int act, int pool, const View* res, const View& y, cudaStream_t s,
-                      int round_out, const View* y16) {
+                      int round_out, const View* y16, const View* xpool) {
     check_apply(x, pool, res, y);
+    if (xpool) THA4_REQUIRE(pool && !xpool->f16 && xpool->N == y.N && xpool->H == y.H && xpool->W == y.W && xpool->C == y.C && xpool->ld % 4 == 0, "norm_apply_fused: pooled raw copy");
     THA4_REQUIRE(x.stats != nullptr, "norm_apply_fused: view has no statistics");
     // outputs: y fp32 (optionally with an extra f16 copy y16), or y itself f16
     float* yf = y.f16 ? nullptr : y.p;
@@ -298,7 +310,7 @@ void norm_apply_fused(const View& x, int groups, const float* gamma, const float
     // per-sample pointers: grid.y selects the sample, the kernel indexes within it
     dim3 grid(bx, y.N);
     launch_pdl(norm_apply_kernel<true>, grid, dim3(256), 2 * x.C * sizeof(float2) + x.C * sizeof(double2), s, 1,
-               (const float*)x.p, x.H, x.W, x.ld, (const float*)nullptr, act, pool, (const float*)(res ? res->p : nullptr), res ? res->ld : 0, yf, y.H, y.W, y.ld, yh, yh_ld, x.C, per_sample,
+               (const float*)x.p, x.H, x.W, x.ld, (const float*)nullptr, act, pool, (const float*)(res ? res->p : nullptr), res ? res->ld : 0, yf, y.H, y.W, y.ld, yh, yh_ld, xpool ? xpool->p : (float*)nullptr, xpool ? xpool->ld : 0, x.C, per_sample,
                round_out, (const double*)x.stats, x.stats_ld, x.stats_rep, x.stats_rep_stride, x.H * x.W, groups, gamma, beta, film0, film1, film1_ld);
     THA4_LAUNCH_CHECK();
 }

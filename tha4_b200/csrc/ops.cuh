@@ -20,7 +20,8 @@ void norm_finalize(const View& x, int groups, const float* gamma, const float* b
 // norm_finalize + norm_apply in one launch: every CTA rebuilds the affine of its sample in shared memory from x.stats.
 void norm_apply_fused(const View& x, int groups, const float* gamma, const float* beta, const float* film0,
                       const float* film1, int film1_ld, int act, int pool, const View* res, const View& y, cudaStream_t s,
-                      int round_out, const View* y16 = nullptr);   // y may itself be an f16 view; y16: extra f16 copy of an fp32 y
+                      int round_out, const View* y16 = nullptr,    // y may itself be an f16 view; y16: extra f16 copy of an fp32 y
+                      const View* xpool = nullptr);                // pool == 1: also the 2x2 mean of the RAW input (fp32), e.g. a down block's skip path
 
 // y = act(x * A + B) (+ res).  pool == 1: y has half the resolution and is the 2x2 mean of the activated values
 // (AvgPool2d(2) after SiLU, unet.py:58,158).  x and y may alias when pool == 0.

@@ -219,7 +219,8 @@ template <int C, int TR> struct TailPCfg {
     static constexpr int ROWB = 2 * C;
     static constexpr int HROWS = (TR + 2) * TT_HW;
     static constexpr int A_BYTES = ((HROWS * ROWB + 1023) / 1024) * 1024;
-    static constexpr int NS = C == 32 ? 3 : 2;                              // halo ring depth
+    static constexpr int NS = 3;                                            // halo ring depth (the transform runs two tiles ahead of the drain)
+    static_assert(C == 32 || TR == 2, "64-channel sites: TR = 2 (three 66 KB halo slots fit, three 100 KB slots do not)");
     static constexpr int B_BYTES = 9 * TT_N * ROWB;
     static constexpr int ACC_COLS = TR * TT_N;                              // TMEM columns of one accumulator slot
     static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS; // 64 / 128: a power of two
@@ -473,12 +474,15 @@ __global__ void __launch_bounds__(TailPCfg<C, TR>::THREADS, 1) tail_tc_persist_k
                                     p.g0, p.g0_ld, p.g1, p.g1_ld, have_pre ? &pre : nullptr);
         };
 
-        const bool drainer = wid < Cfg::DRAIN_WARPS;
+        // The transform runs TWO tiles ahead of the drain (the halo ring is three deep): the MMAs of tile i + 1 then have the
+        // whole of drain(i) and transform(i + 2) to complete in.  One tile ahead, with the drain split around the transform,
+        // they had only the second half of drain(i): 31 % of all samples were drain warps polling acc_full (ncu, v5).
         transform(0);
+        if (nt > 1) transform(1);
         for (int i = 0; i < nt; ++i) {
-            if (drainer) drain_issue(i);
-            if (i + 1 < nt) transform(i + 1);
-            if (drainer) drain_finish(i);
+            drain_issue(i);
+            if (i + 2 < nt) transform(i + 2);
+            drain_finish(i);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -622,12 +626,12 @@ template <int KIND>
 void launch_tail_tc_c(const TailWeights& tw, const View& f, const NormSpecTail& ns, const ImgView& i0, const ImgView& i1, float* const* o, int nout,
                       cudaStream_t s, const View* g0, const View* g1) {
     if (g_tail_persist) {
-        // tile rows per step: 4 when that still gives every SM two tiles or more, else 2 (more, smaller tiles: the small sites at
-        // B = 1 are one latency chain per CTA)
+        // tile rows per step (32-channel sites): 4 when that still gives every SM two tiles or more, else 2 (more, smaller tiles:
+        // the small sites at B = 1 are one latency chain per CTA)
         const long tiles4 = (long)ceil_div(f.W, TT_W) * (f.H / 4) * f.N;
         const bool tr4 = tiles4 >= 2L * tail_num_sms();
         if (tw.C == 32) { if (tr4) launch_tail_persist<KIND, 32, 4>(tw, f, ns, i0, i1, o, nout, s, g0, g1); else launch_tail_persist<KIND, 32, 2>(tw, f, ns, i0, i1, o, nout, s, g0, g1); }
-        else            { if (tr4) launch_tail_persist<KIND, 64, 4>(tw, f, ns, i0, i1, o, nout, s, g0, g1); else launch_tail_persist<KIND, 64, 2>(tw, f, ns, i0, i1, o, nout, s, g0, g1); }
+        else            launch_tail_persist<KIND, 64, 2>(tw, f, ns, i0, i1, o, nout, s, g0, g1);        // three halo slots of 66 KB
         return;
     }
     if (tw.C == 32) launch_tail_tc<KIND, 32>(tw, f, ns, i0, i1, o, nout, s);
