@@ -345,6 +345,13 @@ void launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap
     THA4_LAUNCH_CHECK();
 }
 
+int halo_num_sms() {
+    static int sms[THA4_MAX_DEVICES] = {};
+    const int d = current_device();
+    if (!sms[d]) THA4_CUDA_CHECK(cudaDeviceGetAttribute(&sms[d], cudaDevAttrMultiProcessorCount, d));
+    return sms[d];
+}
+
 // SBD: weight-ring depth of the cluster split-K launches (few CTAs per SM, the ring is what hides the DRAM latency of weights
 // that are fetched ahead of the dependency wait); SBS: depth of the unsplit launches (many tiles: a shallow ring keeps
 // the CTA small so that 2 - 4 of them share an SM and overlap each other's load -> transform -> MMA -> drain chains).
@@ -359,6 +366,11 @@ void launch_halo_cs(int cs, const CUtensorMap& ma, const CUtensorMap& mb, const 
     if (cs == 8) launch_halo<OP, BN, SA, SBD, 8, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
     else if (cs == 4) launch_halo<OP, BN, SA, SBD, 4, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
     else if (cs == 2) launch_halo<OP, BN, SA, SBD, 2, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
+    else if ((long)grid.x * grid.y * grid.z <= halo_num_sms())
+        // unsplit and at most one CTA per SM (e.g. 256 -> 256 channels at 128 x 128: 128 tiles): nothing shares the SM, so the
+        // CTA takes the deep weight ring.  With two 32 KB stages the MMA phase of that layer ran at 294 cycles per 128 x 256 x 16
+        // MMA (28 B/clk/SM of weights from L2; the tensor pipe needs 128 cycles): profiles/r02_halo_phase_stamps.txt, section F
+        launch_halo<OP, BN, SA, SBD, 1, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
     else launch_halo<OP, BN, SA, SBS, 1, XF>(ma, mb, mo32, mo16, mr, p, grid, s);
 }
 
@@ -405,6 +417,7 @@ void conv_halo_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s)
         THA4_REQUIRE(ni.groups == 0 || (ni.C == a.in.C && ni.C % ni.groups == 0), "conv_halo: GroupNorm spans the whole input");
         p.in_stats = ni.stats; p.in_stats_ld = ni.stats_ld; p.in_stats_rep = std::max(1, ni.stats_rep); p.in_stats_rep_stride = ni.stats_rep_stride;
         p.xf_C = ni.C; p.xf_groups = ni.groups; p.xf_act = ni.act;
+        p.xf_inv_cnt = 1.0 / ((double)a.in.H * a.in.W * (ni.groups == 0 ? 1 : ni.C / ni.groups));
         p.xf_gamma = ni.gamma; p.xf_beta = ni.beta; p.xf_film0 = ni.film0; p.xf_film1 = ni.film1; p.xf_film1_ld = ni.film1_ld;
     }
     p.bias = cw.bias;

@@ -514,6 +514,7 @@ void conv_tc_forward(const ConvWeights& cw, const ConvArgs& a, cudaStream_t s) {
         THA4_REQUIRE(ni.groups == 0 || (ni.C == a.in.C && ni.C % ni.groups == 0), "conv_tc: GroupNorm spans the whole input");
         p.in_stats = ni.stats; p.in_stats_ld = ni.stats_ld; p.in_stats_rep = std::max(1, ni.stats_rep); p.in_stats_rep_stride = ni.stats_rep_stride;
         p.xf_C = ni.C; p.xf_groups = ni.groups; p.xf_act = ni.act;
+        p.xf_inv_cnt = 1.0 / ((double)a.in.H * a.in.W * (ni.groups == 0 ? 1 : ni.C / ni.groups));
         p.xf_gamma = ni.gamma; p.xf_beta = ni.beta; p.xf_film0 = ni.film0; p.xf_film1 = ni.film1; p.xf_film1_ld = ni.film1_ld;
     }
     p.bias = cw.bias;

@@ -37,6 +37,7 @@ struct TcParams {
     int inH, inW, inC;                             // geometry of the input tensor (zero padding must stay zero; statistics count)
     int xf_C;                                      // channels [0, xf_C) are normalised, the rest (pose planes, padding) pass through
     int xf_groups, xf_act;                         // 0: InstanceNorm (one group per channel); activation (ACT_*)
+    double xf_inv_cnt;                             // 1 / (inH * inW * channels per group), from the host
     const float* xf_gamma; const float* xf_beta; const float* xf_film0; const float* xf_film1; int xf_film1_ld;
     signed char dy[CONV_MAX_PHASES][CONV_MAX_TAPS];
     signed char dx[CONV_MAX_PHASES][CONV_MAX_TAPS];
@@ -84,12 +85,14 @@ __device__ __forceinline__ void xf_build_coef(const TcParams& p, int n, int te, 
         const int g0 = (c / cpg) * cpg;
         double su = 0.0, sq = 0.0;
         for (int j = 0; j < cpg; ++j) { const double2 v = chs[g0 + j]; su += v.x; sq += v.y; }
-        const double cnt = (double)p.inH * p.inW * cpg;
-        const double mean = su / cnt;
-        double var = sq / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
+        // fp64 only where it matters (the sums and the cancelling subtraction): the divisions and the square root of the
+        // first version were a dependent chain of ~100 double-precision instructions per channel -- 3 600 cycles per 128
+        // channels of every fused-normalisation CTA's start-up (the coefficient is rounded to fp16 anyway)
+        const double mean = su * p.xf_inv_cnt;
+        const double vard = fma(sq, p.xf_inv_cnt, -mean * mean);
+        const float var = fmaxf((float)vard, 0.0f);
         const bool pre = c == c1;
-        float A = (float)(1.0 / sqrt(var + 1e-5)) * (pre ? g1 : __ldg(p.xf_gamma + c));
+        float A = rsqrtf(var + 1e-5f) * (pre ? g1 : __ldg(p.xf_gamma + c));
         float B = (pre ? b1 : __ldg(p.xf_beta + c)) - (float)mean * A;
         if (p.xf_film0) { const float sc = 1.0f + (pre ? f0s : __ldg(p.xf_film0 + c)), sh = pre ? f0h : __ldg(p.xf_film0 + p.xf_C + c); A *= sc; B = B * sc + sh; }
         if (f1p) { const float sc = 1.0f + (pre ? f1s : __ldg(f1p + c)), sh = pre ? f1h : __ldg(f1p + p.xf_C + c); A *= sc; B = B * sc + sh; }

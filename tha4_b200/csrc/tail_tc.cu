@@ -112,11 +112,10 @@ __global__ void __launch_bounds__(TT_THREADS) tail_tc_kernel(const __grid_consta
         const int g0 = (c / cpg) * cpg;
         double su = 0.0, sq = 0.0;
         for (int j = 0; j < cpg; ++j) { su += chs[2 * (g0 + j)]; sq += chs[2 * (g0 + j) + 1]; }
-        const double cnt = (double)p.S * p.S * cpg;
-        const double mean = su / cnt;
-        double var = sq / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        float A = (float)(1.0 / sqrt(var + 1e-5)) * __ldg(p.gamma + c);
+        const double inv_cnt = 1.0 / ((double)p.S * p.S * cpg);          // fp64 for the sums and the cancelling subtraction only
+        const double mean = su * inv_cnt;
+        const float var = fmaxf((float)fma(sq, inv_cnt, -mean * mean), 0.0f);
+        float A = rsqrtf(var + 1e-5f) * __ldg(p.gamma + c);
         float B = __ldg(p.beta + c) - (float)mean * A;
         if (silu) { A *= 0.5f; B *= 0.5f; }                                // silu(v) = h + h * tanh(h), h = v / 2
         cA[c] = A; cB[c] = B;
@@ -371,11 +370,10 @@ __global__ void __launch_bounds__(TailPCfg<C, TR>::THREADS, 1) tail_tc_persist_k
                     const int g0 = (wt / cpg) * cpg;
                     double su = 0.0, sq = 0.0;
                     for (int j = 0; j < cpg; ++j) { su += chs[2 * (g0 + j)]; sq += chs[2 * (g0 + j) + 1]; }
-                    const double cnt = (double)p.S * p.S * cpg;
-                    const double mean = su / cnt;
-                    double var = sq / cnt - mean * mean;
-                    if (var < 0.0) var = 0.0;
-                    float A = (float)(1.0 / sqrt(var + 1e-5)) * g1;
+                    const double inv_cnt = 1.0 / ((double)p.S * p.S * cpg);          // fp64 for the sums and the cancelling subtraction only
+                    const double mean = su * inv_cnt;
+                    const float var = fmaxf((float)fma(sq, inv_cnt, -mean * mean), 0.0f);
+                    float A = rsqrtf(var + 1e-5f) * g1;
                     float B = b1 - (float)mean * A;
                     if (silu) { A *= 0.5f; B *= 0.5f; }                            // silu(v) = h + h * tanh(h), h = v / 2
                     cA[wt] = A; cB[wt] = B;
