@@ -313,6 +313,16 @@ def test_tail_site_vs_reference_ops(site, strict):
     for i, (a, b) in enumerate(zip(outs, refs)):
         mx, mean = G.err(a, b)
         assert mx <= max_tol and mean <= mean_tol, (site, strict, i, mx, mean)
+    if not strict:
+        # the default mode's kernel is the persistent pipelined one; the one-tile-per-CTA kernel (option tail_persist = 0) is the
+        # same arithmetic in the same order: identical outputs
+        G.ctx().set_option('tail_persist', 0)
+        try:
+            one_tile = G.tail(kind, feature, gamma, beta, groups, act, ws, bs, image0, image1, strict=0)
+        finally:
+            G.ctx().set_option('tail_persist', 1)
+        for i, (a, b) in enumerate(zip(outs, one_tile)):
+            assert torch.equal(a, b), (site, i, G.err(a, b))
 
 
 @pytest.mark.parametrize('C,H', [(64, 48), (512, 16), (128, 24)])
