@@ -44,6 +44,19 @@ def test_round2_default_bench_line_has_the_sub_objects():
     assert ref['impl'] == 'reference' and ref['config'] == d['config'], 'the two arms must print the same config'
 
 
+def test_round2_final_bench_line_if_committed():
+    """The bench line of the end of round 2 (second half), when its evidence run made it into profiles/."""
+    f = os.path.join(ROOT, 'profiles', 'r02b_final_bench_default.json')
+    if not os.path.exists(f):
+        return
+    d = json.load(open(f))
+    assert BASE_KEYS <= set(d) and d['n_gpus'] == 1 and d['gpu_launches'] > 0 and d['value'] > 0
+    assert d['e2e']['value'] > 0 and d['e2e']['d2h_bytes_per_step'] == 512 * 512 * 4
+    for key in ('pose_sweep_512', 'distill', 'student_b64', 'torch_cuda_eager', 'roofline', 'roofline_tail', 'cpu_baseline', 'clocks'):
+        assert key in d, key
+    assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+
+
 def test_committed_bench_lines_are_complete():
     files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r01_final_bench_*.json')))
     assert files, 'round-1 bench lines missing from profiles/'
