@@ -208,10 +208,12 @@ __global__ void __launch_bounds__(TT_THREADS) tail_tc_kernel(const __grid_consta
 // contiguous range of tiles with the phases on different warps and different tiles:
 //   warp 0      TMA producer: halo boxes into an NS-deep ring (the head weights once)
 //   warp 1      MMA issuer: TR x 9 x C/16 tcgen05.mma per tile into one of TWO accumulator slots in TMEM
-//   warps 2..   workers (4 * TR warps), two stages on the same warps, one tile apart:
-//               transform(i + 1): normalise + activate the landed halo in place (the per-channel affine is rebuilt once per
+//   warps 2..   workers (4 * TR warps), two stages on the same warps, two tiles apart, the drain split around the transform:
+//               drain A(i):       tcgen05.ld of the pixel's grid_change outputs -> gs_locate -> the four corner pixels requested;
+//               transform(i + 2): normalise + activate the landed halo in place (the per-channel affine is rebuilt once per
 //                                 SAMPLE, not per tile), every worker thread;
-//               drain(i):         one thread per output pixel of the tile (4 * TR warps): tcgen05.ld -> tail_epilogue.
+//               drain B(i):       tcgen05.ld again -> tail_epilogue with the corners that arrived meanwhile (thread = pixel).
+// (profiles/r02_tail_persist_notes.txt: the seven versions on the way here and what the ncu source page showed for each)
 // mbarriers: h_full (TMA -> transform), h_xf (transform -> MMA, one arrival per worker thread), h_empty (MMA commit -> TMA),
 // acc_full (MMA commit -> drain), acc_empty (drain -> MMA, one arrival per drain warp once its tcgen05.ld has completed).
 template <int C, int TR> struct TailPCfg {
